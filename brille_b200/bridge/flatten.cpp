@@ -1,0 +1,378 @@
+// brille_b200 bridge: flatten brille's host C++ objects into plain SoA tables.
+//
+// This translation unit is the *reference-side* half of the drop-in boundary:
+// it is compiled against brille's own headers and walks the already-constructed host objects
+// (BrillouinZone, BrillouinZoneTrellis3/Nest3/Mesh3, DualInterpolator, GammaTable) ONCE, emitting
+// plain contiguous arrays -- the `b200_tables_t` of include/brille_b200.h -- that are then uploaded
+// to the GPU through the C ABI.  Construction (lattice, symmetry, polyhedra, TetGen, fill, sort)
+// stays brille's host C++; nothing here runs per Q point.
+//
+// Quantities that brille recomputes at the start of every `moveinto` call (plane points in the
+// primitive lattice, normalised face normals, tau vectors: bz_move.cpp:118-140) are produced here by
+// calling the very same brille functions, so the tables hold bit-identical numbers.
+//
+// Non-public members are reached without touching the reference sources:
+//   * protected members through a derived "spy" class and a pointer-to-member
+//   * private members through the explicit-instantiation access idiom (Access<Tag, &T::member>)
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <pybind11/numpy.h>
+#include <pybind11/complex.h>
+#include <complex>
+#include <cstring>
+#include <deque>
+#include "bz_trellis.hpp"
+#include "bz_nest.hpp"
+#include "bz_mesh.hpp"
+
+namespace py = pybind11;
+using namespace brille;
+using cplx = std::complex<double>;
+
+// ---------------------------------------------------------------------------------------------
+// access helpers
+// ---------------------------------------------------------------------------------------------
+struct BZSpy : BrillouinZone {
+  static double ftol(const BrillouinZone& b) { return b.*(&BZSpy::float_tolerance); }
+  static int atol(const BrillouinZone& b) { return b.*(&BZSpy::approx_tolerance); }
+  static bool nomirror(const BrillouinZone& b) { return b.*(&BZSpy::no_ir_mirroring); }
+  static bool isprim(const BrillouinZone& b) { return b.*(&BZSpy::is_primitive); }
+  static const poly_t& first(const BrillouinZone& b) { return b.*(&BZSpy::_first); }
+};
+struct PolyNodeSpy : brille::PolyNode {
+  static const std::vector<std::array<ind_t, 4>>& vi(const brille::PolyNode& n) { return n.*(&PolyNodeSpy::vi_t); }
+  static const std::vector<std::array<double, 4>>& ci(const brille::PolyNode& n) { return n.*(&PolyNodeSpy::ci_t); }
+  static const std::vector<double>& vol(const brille::PolyNode& n) { return n.*(&PolyNodeSpy::vol_t); }
+};
+struct CubeNodeSpy : brille::CubeNode {
+  static const std::array<ind_t, 8>& vi(const brille::CubeNode& n) { return n.*(&CubeNodeSpy::vertex_indices); }
+};
+template <class T, class R, class S>
+struct TrellisSpy : BrillouinZoneTrellis3<T, R, S> {
+  using base = BrillouinZoneTrellis3<T, R, S>;
+  static const typename base::knots_t& knots(const base& g) { return g.*(&TrellisSpy::knots_); }
+  static const typename base::nodes_t& nodes(const base& g) { return g.*(&TrellisSpy::nodes_); }
+};
+template <class T>
+struct InterpSpy : Interpolator<T> {
+  static LengthUnit lenunit(const Interpolator<T>& i) { return i.*(&InterpSpy::lenunit_); }
+};
+template <class T, class R>
+struct DualSpy : DualInterpolator<T, R> {
+  static const PermutationTable& table(const DualInterpolator<T, R>& d) { return d.*(&DualSpy::permutation_table_); }
+};
+struct PermSpy : PermutationTable {
+  static const std::map<size_t, size_t>& map(const PermutationTable& p) { return p.*(&PermSpy::ijmap); }
+  static const std::vector<std::vector<ind_t>>& perms(const PermutationTable& p) { return p.*(&PermSpy::permutations); }
+  static size_t nidx(const PermutationTable& p) { return p.*(&PermSpy::IndexSize); }
+};
+
+// private-member access (legal: explicit instantiation may name private members)
+template <class Tag, typename Tag::type M>
+struct Access {
+  friend typename Tag::type get(Tag) { return M; }
+};
+struct LeafCR { using type = std::array<double, 4> NestLeaf::*; friend type get(LeafCR); };
+template struct Access<LeafCR, &NestLeaf::centre_radius>;
+
+// ---------------------------------------------------------------------------------------------
+// numpy helpers (always own a copy: tables must outlive the host objects)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+static py::array_t<T> np1(const std::vector<T>& v) {
+  py::array_t<T> a(static_cast<py::ssize_t>(v.size()));
+  if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(T));
+  return a;
+}
+template <class T>
+static py::array_t<T> np2(const std::vector<T>& v, size_t cols) {
+  py::array_t<T> a({static_cast<py::ssize_t>(cols ? v.size() / cols : 0), static_cast<py::ssize_t>(cols)});
+  if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(T));
+  return a;
+}
+template <class T, class A>
+static py::array_t<T> np_from_a2(const A& arr) {  // (n, m) Array2 / LVec -> contiguous numpy
+  std::vector<T> v;
+  v.reserve(static_cast<size_t>(arr.size(0)) * arr.size(1));
+  for (ind_t i = 0; i < arr.size(0); ++i)
+    for (ind_t j = 0; j < arr.size(1); ++j) v.push_back(static_cast<T>(arr.val(i, j)));
+  return np2(v, arr.size(1));
+}
+template <class T, size_t N>
+static py::array_t<T> np_arr(const std::array<T, N>& a) {
+  return np1(std::vector<T>(a.begin(), a.end()));
+}
+
+// ---------------------------------------------------------------------------------------------
+// BrillouinZone  ->  tables used by ir_moveinto   (bz_move.cpp:103-296)
+// ---------------------------------------------------------------------------------------------
+static py::dict flatten_bz(const BrillouinZone& bz) {
+  using namespace brille::lattice;
+  py::dict d;
+  const auto outer = bz.get_lattice();
+  const auto inner = bz.get_primitive_lattice();
+  PrimitiveTransform PT(outer.bravais());
+  // bz_move.cpp:111 (Q is always given in the outer lattice on this path)
+  const bool transform_needed = PT.does_anything();
+  if (transform_needed != BZSpy::isprim(bz))
+    throw std::runtime_error(
+        "brille_b200: BrillouinZone built with primitive=false on a centred lattice is not supported "
+        "(the reference's own moveinto throws for it)");
+  d["transform_needed"] = transform_needed ? 1 : 0;
+  d["P6t"] = np_arr<int>(PT.get_6Pt());      // transform.hpp:175 (inverse_angstrom: 6*P^T, then /6)
+  d["invPt"] = np_arr<int>(PT.get_invPt());  // transform.hpp:213
+  const auto work = transform_needed ? outer.primitive() : outer;
+  d["w_recip_metric"] = np_arr<double>(work.metric(LengthUnit::inverse_angstrom));
+  d["w_real_metric"] = np_arr<double>(work.metric(LengthUnit::angstrom));
+  d["w_recip_volume"] = work.volume(LengthUnit::inverse_angstrom);
+  d["o_recip_metric"] = np_arr<double>(outer.metric(LengthUnit::inverse_angstrom));
+  d["o_real_metric"] = np_arr<double>(outer.metric(LengthUnit::angstrom));
+  d["o_recip_volume"] = outer.volume(LengthUnit::inverse_angstrom);
+  d["to_xyz"] = np_arr<double>(outer.to_xyz(LengthUnit::inverse_angstrom));  // array_lvec_methods.tpp:40-52
+
+  // first-Brillouin-zone planes: conventional (isinside re-check, bz.hpp:631-642) and working lattice
+  const auto& first = BZSpy::first(bz);
+  auto [a, b, c] = first.planes();
+  d["ca"] = np_from_a2<double>(a);
+  d["cb"] = np_from_a2<double>(b);
+  d["cc"] = np_from_a2<double>(c);
+  auto pa = parallel_transform_to_primitive(outer, a, 1);  // bz_move.cpp:124-126
+  auto pb = parallel_transform_to_primitive(outer, b, 1);
+  auto pc = parallel_transform_to_primitive(outer, c, 1);
+  d["pa"] = np_from_a2<double>(pa);
+  d["pb"] = np_from_a2<double>(pb);
+  d["pc"] = np_from_a2<double>(pc);
+  auto normals = bz.get_primitive_normals();  // bz_move.cpp:137-140
+  normals = normals / norm(normals);
+  auto taus = (2.0 * bz.get_primitive_points()).round();
+  auto tau_lens = norm(taus);
+  d["normals"] = np_from_a2<double>(normals);
+  d["taus"] = np_from_a2<int>(taus);
+  d["tau_lens"] = np_from_a2<double>(tau_lens).attr("reshape")(-1);
+
+  // irreducible wedge (bz.hpp:757-763)
+  auto wn = bz.get_ir_wedge_normals();
+  d["wedge_normals"] = np_from_a2<double>(wn).attr("reshape")(-1, 3);
+  d["no_ir_mirroring"] = BZSpy::nomirror(bz) ? 1 : 0;
+  d["float_tolerance"] = BZSpy::ftol(bz);
+  d["approx_tolerance"] = BZSpy::atol(bz);
+  d["time_reversal"] = bz.add_time_reversal();
+
+  // point group in the order ir_moveinto scans it (bz_move.cpp:257-285)
+  PointSymmetry ps = bz.get_pointgroup_symmetry();
+  std::vector<int> rot;
+  std::vector<int> inv;
+  for (size_t i = 0; i < ps.size(); ++i) {
+    auto r = ps.get(i);
+    rot.insert(rot.end(), r.begin(), r.end());
+    inv.push_back(static_cast<int>(ps.get_inverse_index(i)));  // pointsymmetry.cpp:131-142
+  }
+  d["rotations"] = np2(rot, 9);
+  d["inverse_index"] = np1(inv);
+  d["identity_index"] = static_cast<int>(ps.find_identity_index());
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PermutationTable lookup identical to safe_get (permutation_table.hpp:193-198,214)
+// ---------------------------------------------------------------------------------------------
+struct PermLookup {
+  const std::map<size_t, size_t>& m;
+  size_t n;
+  explicit PermLookup(const PermutationTable& t) : m(PermSpy::map(t)), n(PermSpy::nidx(t)) {}
+  unsigned row(size_t i, size_t j) const {
+    size_t key = (i == j) ? 0u : i * n + j;
+    auto it = m.find(key);
+    return (it != m.end() && it->second >= 1u) ? static_cast<unsigned>(it->second - 1u) : 0u;
+  }
+};
+
+template <class T, class R>
+static void flatten_perm_rows(const DualInterpolator<T, R>& data, py::dict& d, bool& any_nonidentity) {
+  const auto& rows = PermSpy::perms(DualSpy<T, R>::table(data));
+  std::vector<unsigned> flat;
+  size_t m = rows.empty() ? 0 : rows[0].size();
+  for (const auto& r : rows) flat.insert(flat.end(), r.begin(), r.end());
+  d["perm_rows"] = np2(flat, m);
+  any_nonidentity = rows.size() > 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// interpolation data   (interpolatordual.hpp, interpolator.hpp, phonon.hpp)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+static void flatten_interp(const Interpolator<T>& in, const char* prefix, py::dict& d) {
+  std::string p(prefix);
+  const auto& a = in.data();  // Array2 (n_pt, branches*span)
+  py::array_t<T> arr({static_cast<py::ssize_t>(a.size(0)), static_cast<py::ssize_t>(a.size(1))});
+  T* dst = arr.mutable_data();
+  for (ind_t i = 0; i < a.size(0); ++i)
+    for (ind_t j = 0; j < a.size(1); ++j) dst[static_cast<size_t>(i) * a.size(1) + j] = a.val(i, j);
+  d[(p + "_data").c_str()] = arr;
+  auto sh = in.shape();
+  d[(p + "_shape").c_str()] = std::vector<unsigned>(sh.begin(), sh.end());
+  auto el = in.elements();
+  d[(p + "_elements").c_str()] = np1(std::vector<unsigned>(el.begin(), el.end()));
+  d[(p + "_rotlike").c_str()] = static_cast<int>(in.rotateslike());
+  d[(p + "_lenunit").c_str()] = static_cast<int>(InterpSpy<T>::lenunit(in));
+  d[(p + "_branches").c_str()] = in.branches();
+  d[(p + "_span").c_str()] = in.branch_span();
+}
+
+template <class Grid>
+static void flatten_gamma(const Grid& g, py::dict& d) {
+  // identical arguments to bz_trellis.hpp:182-186
+  auto bz = g.get_brillouinzone();
+  auto cfg = g.approx_config();
+  auto lat = bz.get_lattice();
+  bool has_basis = lat.basis().size() > 0;
+  PointSymmetry ps = bz.get_pointgroup_symmetry();
+  const size_t nops = ps.size();
+  // Cartesian rotation matrices used when LengthUnit::angstrom (interpolator.hpp:409-423)
+  std::vector<double> rc(nops * 9);
+  std::array<double, 9> t0;
+  for (size_t j = 0; j < nops; ++j) {
+    brille::utils::mul_mat_mat(t0.data(), 3u, lat.to_xyz(LengthUnit::angstrom).data(), ps.data(j));
+    brille::utils::mul_mat_mat(&rc[9 * j], 3u, t0.data(), lat.from_xyz(LengthUnit::angstrom).data());
+  }
+  d["rot_cart"] = np2(rc, 9);
+  if (!has_basis) {
+    d["gamma_natoms"] = 0;
+    return;
+  }
+  GammaTable gt(true, lat, bz.add_time_reversal(), cfg.template direct<double>(), cfg.digit());
+  const size_t nat = lat.basis().size();
+  std::vector<unsigned> f0(nat * nops), vi(nat * nops);
+  for (size_t k = 0; k < nat; ++k)
+    for (size_t r = 0; r < nops; ++r) {
+      f0[k * nops + r] = gt.F0(k, r);
+      vi[k * nops + r] = gt.vector_index(k, r);
+    }
+  d["gamma_natoms"] = nat;
+  d["gamma_F0"] = np2(f0, nops);
+  d["gamma_vidx"] = np2(vi, nops);
+  d["gamma_vectors"] = np_from_a2<double>(gt.vectors());
+}
+
+template <class Grid>
+static py::dict flatten_data_common(const Grid& g, py::dict d) {
+  const auto& data = g.data();
+  flatten_interp(data.values(), "values", d);
+  flatten_interp(data.vectors(), "vectors", d);
+  bool gamma_needed = RotatesLike::Gamma == data.vectors().rotateslike() ||
+                      RotatesLike::Gamma == data.values().rotateslike();
+  d["gamma_needed"] = gamma_needed ? 1 : 0;
+  try {
+    flatten_gamma(g, d);
+  } catch (const std::exception& e) {
+    if (gamma_needed) throw;
+    d["gamma_natoms"] = 0;
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PolyTrellis   (trellis_poly.hpp, trellis_node.hpp)
+// ---------------------------------------------------------------------------------------------
+template <class T, class R, class S>
+static py::dict flatten_trellis(const BrillouinZoneTrellis3<T, R, S>& g) {
+  using Spy = TrellisSpy<T, R, S>;
+  py::dict d;
+  d["kind"] = "trellis";
+  d["bz"] = flatten_bz(g.get_brillouinzone());
+  const auto& knots = Spy::knots(g);
+  d["knots0"] = np1(knots[0]);
+  d["knots1"] = np1(knots[1]);
+  d["knots2"] = np1(knots[2]);
+  const auto& nodes = Spy::nodes(g);
+  const size_t nn = nodes.size();
+  std::vector<uint8_t> ntype(nn);
+  std::vector<unsigned> nidx(nn, 0xffffffffu);
+  std::vector<unsigned> cubes, poff{0u}, tvi;
+  std::vector<double> tci, tvol;
+  unsigned ncube = 0, npoly = 0;
+  for (size_t i = 0; i < nn; ++i) {
+    auto t = nodes.type(static_cast<ind_t>(i));
+    ntype[i] = static_cast<uint8_t>(t);  // enums.hpp:43
+    if (NodeType::cube == t) {
+      nidx[i] = ncube++;
+      for (auto v : CubeNodeSpy::vi(nodes.cube_at(static_cast<ind_t>(i)))) cubes.push_back(v);
+    } else if (NodeType::poly == t) {
+      nidx[i] = npoly++;
+      const auto& pn = nodes.poly_at(static_cast<ind_t>(i));
+      const auto& vi = PolyNodeSpy::vi(pn);
+      const auto& ci = PolyNodeSpy::ci(pn);
+      const auto& vol = PolyNodeSpy::vol(pn);
+      for (size_t k = 0; k < vi.size(); ++k) {
+        for (int j = 0; j < 4; ++j) tvi.push_back(vi[k][j]);
+        for (int j = 0; j < 4; ++j) tci.push_back(ci[k][j]);
+        tvol.push_back(vol[k]);
+      }
+      poff.push_back(static_cast<unsigned>(tvol.size()));
+    }
+  }
+  d["node_type"] = np1(ntype);
+  d["node_index"] = np1(nidx);
+  d["cube_vertices"] = np2(cubes, 8);
+  d["poly_offsets"] = np1(poff);
+  d["tet_vertices"] = np2(tvi, 4);
+  d["tet_circum"] = np2(tci, 4);
+  d["tet_volume"] = np1(tvol);
+  d["vertices"] = np_from_a2<double>(g.vertices());
+  auto cfg = g.approx_config();
+  d["approx_digit"] = cfg.digit();
+  d["approx_direct"] = cfg.template direct<double>();
+  d["approx_reciprocal"] = cfg.template reciprocal<double>();
+  return d;
+}
+
+template <class T, class R, class S>
+static py::dict flatten_trellis_data(const BrillouinZoneTrellis3<T, R, S>& g) {
+  py::dict d;
+  flatten_data_common(g, d);
+  bool any = false;
+  flatten_perm_rows(g.data(), d, any);
+  d["perm_nonidentity"] = any ? 1 : 0;
+  if (any) {
+    // per-cell pair -> permutation-row index, so the device needs no map lookups
+    using Spy = TrellisSpy<T, R, S>;
+    PermLookup look(DualSpy<T, R>::table(g.data()));
+    const auto& nodes = Spy::nodes(g);
+    std::vector<unsigned> cp, tp;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      auto t = nodes.type(static_cast<ind_t>(i));
+      if (NodeType::cube == t) {
+        const auto& vi = CubeNodeSpy::vi(nodes.cube_at(static_cast<ind_t>(i)));
+        for (int a = 0; a < 8; ++a)
+          for (int b = 0; b < 8; ++b) cp.push_back(look.row(vi[a], vi[b]));
+      } else if (NodeType::poly == t) {
+        for (const auto& vi : PolyNodeSpy::vi(nodes.poly_at(static_cast<ind_t>(i))))
+          for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) tp.push_back(look.row(vi[a], vi[b]));
+      }
+    }
+    d["cube_perm"] = np2(cp, 64);
+    d["tet_perm"] = np2(tp, 16);
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// module
+// ---------------------------------------------------------------------------------------------
+template <class T, class R>
+static void def_trellis(py::module& m) {
+  using G = BrillouinZoneTrellis3<T, R, double>;
+  m.def("flatten", [](const G& g) { return flatten_trellis(g); }, py::arg("grid"),
+        "Structure tables (Brillouin zone + trellis) of a BZTrellisQ* object");
+  m.def("flatten_data", [](const G& g) { return flatten_trellis_data(g); }, py::arg("grid"),
+        "Data tables (values, vectors, permutations, gamma table) of a BZTrellisQ* object");
+}
+
+PYBIND11_MODULE(_bridge, m) {
+  m.doc() = "brille_b200 bridge: flatten brille host objects into SoA tables";
+  m.def("flatten_bz", &flatten_bz, py::arg("bz"));
+  def_trellis<double, double>(m);
+  def_trellis<double, cplx>(m);
+  def_trellis<cplx, cplx>(m);
+}

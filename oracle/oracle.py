@@ -1,0 +1,81 @@
+"""ctypes front end of the plain-C oracle (oracle/brille_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from brille_b200 import tables as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "brille_oracle.c")
+LIB = os.path.join(HERE, "liboracle.so")
+
+
+def build(force=False):
+    """gcc -O2 without FMA contraction (the reference is x86-64 baseline code: no fused multiply-add)."""
+    hdr = os.path.join(ROOT, "include", "brille_b200.h")
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        return LIB
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fopenmp", "-I", os.path.join(ROOT, "include"), SRC, "-o", LIB, "-lm"]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_interpolate_at.restype = C.c_int
+        _lib.oracle_interpolate_at.argtypes = [
+            C.c_int, C.POINTER(T.BZTables), C.c_void_p, C.POINTER(T.DataTables), C.c_void_p, C.c_size_t,
+            C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(T.Probe),
+        ]
+        _lib.oracle_moveinto.restype = C.c_int
+        _lib.oracle_moveinto.argtypes = [C.POINTER(T.BZTables), C.c_void_p, C.c_size_t, C.c_int, C.POINTER(T.Probe)]
+    return _lib
+
+
+class Oracle:
+    """The oracle over one set of flat tables (bridge dictionaries)."""
+
+    def __init__(self, structure, data=None):
+        self.kind = {"trellis": T.GRID_TRELLIS, "nest": T.GRID_NEST, "mesh": T.GRID_MESH}[str(structure["kind"])]
+        self.bz = T.pack_bz(structure["bz"])
+        self.structure = {T.GRID_TRELLIS: T.pack_trellis}[self.kind](structure)
+        self.data = T.pack_data(data) if data is not None else None
+
+    def set_data(self, data):
+        self.data = T.pack_data(data)
+
+    def row_shapes(self):
+        d = self.data
+        vs = d.values.branches * sum(d.values.elements)
+        ws = d.vectors.branches * sum(d.vectors.elements)
+        return vs, ws
+
+    def interpolate_at(self, Q, ir=True, no_move=False, probe=True):
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, 3)
+        n = Q.shape[0]
+        vs, ws = self.row_shapes()
+        vals = np.zeros((n, vs), dtype=np.complex128 if self.data.values.is_complex else np.float64)
+        vecs = np.zeros((n, ws), dtype=np.complex128 if self.data.vectors.is_complex else np.float64)
+        pr = T.ProbeArrays(n) if probe else None
+        rc = lib().oracle_interpolate_at(
+            self.kind, C.byref(self.bz), C.cast(C.pointer(self.structure), C.c_void_p), C.byref(self.data),
+            Q.ctypes.data, n, T.FLAG_NO_MOVE if no_move else 0, 1 if ir else 0, vals.ctypes.data, vecs.ctypes.data,
+            pr.byref() if pr is not None else None,
+        )
+        return rc, vals, vecs, pr
+
+    def moveinto(self, Q, ir=True):
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, 3)
+        pr = T.ProbeArrays(Q.shape[0], fields=("q_ir", "x_ir", "tau", "ridx", "invridx", "status"))
+        rc = lib().oracle_moveinto(C.byref(self.bz), Q.ctypes.data, Q.shape[0], 1 if ir else 0, pr.byref())
+        return rc, pr

@@ -1,0 +1,2 @@
+#pragma once
+#include "H5File.hpp"
