@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""bench.py -- Q-points/s through ir_interpolate_at (eigenvalues + rotated eigenvectors) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the north-star target is quoted on): P6_3/mmc hexagonal
+4-atom cell, BZTrellisQdc hybrid cube/tetrahedron trellis at V_ir/2000, 12 modes, eigenvalues + Gamma-rotated
+eigenvectors, 1e7 uniformly random Q in [-3,3)^3 rlu per GPU per step (weak scaling: Q is sharded, tables are
+replicated, no collective on the data path).  One step = one pass of the whole path over the batch.
+
+The printed JSON line follows the driver's contract.  `value` is timed with CUDA events with Q and the outputs
+resident in HBM; `e2e` goes through the host-buffer C-ABI call (pinned host buffers, H2D of Q and D2H of both
+results inside the timed region); `roofline` is the dominant (interpolation) kernel against the measured HBM copy
+bandwidth; `cpu_baseline` is the reference's own OpenMP implementation (oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Q-points/sec interpolated (eigvals+eigvecs)"
+UNIT = "Q/s"
+NQ = 10_000_000           # Q per GPU per step (BASELINE.json configs[2])
+E2E_NQ = 2_000_000        # Q per e2e step (host buffers; the rate is flat in nQ, 24 GB of pinned output is not)
+CPU_SAMPLE_NQ = 200_000   # bounded sample for the CPU reference legs
+Q_SEED = 3
+
+
+def build_workload():
+    """Host-side construction with brille's own C++ (oracle/_ref is the unmodified reference build)."""
+    from oracle import ref
+    from brille_b200 import workloads as W
+
+    return W.c3_p63mmc(ref.host())
+
+
+def workload_config(wl, extra=None):
+    cfg = {
+        "workload": "C3: P6_3/mmc 4-atom cell, BZTrellisQdc V_ir/2000 (hybrid cube/tetrahedron), 12 modes eigvals+eigvecs (Gamma), 1e7 uniform random Q per GPU per step",
+        "q_per_gpu_per_step": NQ,
+        "modes": wl.modes,
+        "atoms": wl.n_atoms,
+        "vertices": int(wl.grid.rlu.shape[0]),
+        "bytes_per_q": wl.bytes_per_q,
+        "sharding": "Q sharded across GPUs, tables replicated, no data-path collective",
+        "cache": "inputs+outputs (24.5 GB per step) far larger than the 126 MB L2; the 7.3 MB vertex table is L2-resident by design",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def cpu_reference_rate(wl, nq, threads, repeats=1):
+    """The reference's own ir_interpolate_at (oracle/_ref, unmodified brille) on the host cores."""
+    Q = wl.make_q(nq, Q_SEED + 100)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        wl.grid.ir_interpolate_at(Q, True, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nq / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = build_workload()
+    cores = os.cpu_count() or 1
+    nq = CPU_SAMPLE_NQ
+    Q = wl.make_q(nq, Q_SEED + 100)
+    for _ in range(args.warmup):
+        wl.grid.ir_interpolate_at(Q[: nq // 10], True, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wl.grid.ir_interpolate_at(Q, True, cores)
+    dt = time.perf_counter() - t0
+    value = nq * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(wl, {"reference_sample_q_per_step": nq}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{nq} Q per step of the same workload, brille ir_interpolate_at(Q, True, {cores}) from oracle/_ref"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import brille_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- brille_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    wl = build_workload()
+    grid = brille_b200.accelerate(wl.grid, device=local)
+    bpq = grid.bytes_per_q
+    assert bpq == wl.bytes_per_q
+
+    # this rank's shard of the (world * NQ)-point job; different points on every rank
+    Q = wl.make_q(NQ, Q_SEED + 1000 * rank)
+    dQ = torch.from_numpy(Q).to(dev)
+    vals = torch.empty((NQ, wl.modes, 1), dtype=torch.float64, device=dev)
+    vecs = torch.empty((NQ, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(check=False):
+        grid.ir_interpolate_at_device(dQ, vals, vecs, check=check, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(check=(i == 0))  # the first warm-up step also verifies that every Q was placed
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = grid.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = grid.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * NQ * args.steps / (ms_max * 1e-3)
+
+    # per-kernel durations with CUDA events on the launching stream (separate pass so the events do not perturb `value`)
+    grid.enable_timing(True)
+    k_loc, k_int = [], []
+    for _ in range(3):
+        step()
+        k_loc.append(grid.kernel_ms("locate"))
+        k_int.append(grid.kernel_ms("interpolate"))
+    grid.enable_timing(False)
+    torch.cuda.synchronize(dev)
+    loc_ms, int_ms = float(np.mean(k_loc)), float(np.mean(k_int))
+
+    # end to end through the host-buffer C-ABI call: pinned host Q in, pinned host results out, every step
+    ne = E2E_NQ
+    hq = brille_b200.PinnedArray((ne, 3), np.float64)
+    hv = brille_b200.PinnedArray((ne, wl.modes, 1), np.float64)
+    hw = brille_b200.PinnedArray((ne, wl.modes, wl.n_atoms, 3), np.complex128)
+    hq.array[:] = Q[:ne]
+    for _ in range(2):
+        grid.ir_interpolate_at(hq.array, out=(hv.array, hw.array))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        grid.ir_interpolate_at(hq.array, out=(hv.array, hw.array))
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ne * args.steps / float(t.item())
+    checksum = float(hv.array[:1000].sum())
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = bpq * NQ / (int_ms * 1e-3) / 1e9
+        traffic = profiled_traffic()
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, secs = cpu_reference_rate(wl, CPU_SAMPLE_NQ, cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"{CPU_SAMPLE_NQ} Q of the same workload in one call of the unmodified reference (oracle/_ref) ir_interpolate_at(Q, True, {cores}): {secs:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(wl, {"e2e_q_per_step": ne, "parallelism": f"q-shard x{world}"}),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * ne, "d2h_bytes_per_step": (bpq - 24) * ne,
+                    "note": "b200_ir_interpolate_at with pinned host buffers; chunked H2D/kernels/D2H overlapped on two streams", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_interp (interpolate+rotate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_q": bpq,
+                         "kernel_ms": int_ms, "locate_kernel_ms": loc_ms,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    grid.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

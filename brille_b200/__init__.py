@@ -1,0 +1,33 @@
+"""brille_b200 -- B200-native batched Q-point interpolation for brille grids.
+
+One hot path of brille (``BZ{Trellis,Nest,Mesh}Q*.ir_interpolate_at``) re-built as hand-written sm_100a CUDA
+kernels behind a C ABI (``include/brille_b200.h``).  Construction stays brille's host C++.
+
+>>> import brille_b200
+>>> grid = brille_b200.BZTrellisQdc(bz, max_volume)          # brille constructs, the tables go to the GPU
+>>> grid.fill(vals, vals_elements, vecs, vecs_elements)
+>>> vals, vecs = grid.ir_interpolate_at(Q)                   # same signature and results as brille
+"""
+from __future__ import annotations
+
+from . import tables  # noqa: F401
+from .capi import B200Error  # noqa: F401
+from .grid import B200Grid, PinnedArray, accelerate  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def _factory(name):
+    def make(bz, *args, device=0, **kwargs):
+        from . import host
+
+        return B200Grid(getattr(host.get(), name)(bz, *args, **kwargs), device=device)
+
+    make.__name__ = name
+    make.__doc__ = f"Construct brille's ``{name}`` on the host and move its interpolation path to the GPU."
+    return make
+
+
+for _n in ("BZTrellisQdd", "BZTrellisQdc", "BZTrellisQcc", "BZNestQdd", "BZNestQdc", "BZNestQcc", "BZMeshQdd", "BZMeshQdc", "BZMeshQcc"):
+    globals()[_n] = _factory(_n)
+del _n

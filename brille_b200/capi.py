@@ -1,0 +1,99 @@
+"""ctypes binding of the C ABI (``include/brille_b200.h``) exported by ``libbrille_b200.so``.
+
+There is no CPU fallback: if the CUDA library is missing, or no CUDA device is present when a grid is
+created, the calls below raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import tables as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbrille_b200.so")
+
+#: every symbol include/brille_b200.h declares
+EXPORTS = (
+    "b200_grid_create",
+    "b200_grid_set_data",
+    "b200_grid_destroy",
+    "b200_ir_interpolate_at",
+    "b200_ir_interpolate_at_device",
+    "b200_interpolate_at",
+    "b200_moveinto",
+    "b200_alloc_pinned",
+    "b200_free_pinned",
+    "b200_last_error",
+    "b200_abi_version",
+    "b200_device_count",
+    "b200_grid_launch_count",
+    "b200_grid_enable_timing",
+    "b200_grid_kernel_ms",
+    "b200_grid_row_bytes",
+)
+
+
+class B200Error(RuntimeError):
+    """Raised for every non-zero return code; ``code`` is the B200_E_* value (mirrors brille's RuntimeError)."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m brille_b200.build` (nvcc, sm_100a). "
+            "brille_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.b200_grid_create.restype = C.c_int
+    L.b200_grid_create.argtypes = [C.c_int, C.POINTER(T.BZTables), vp, C.c_int, C.POINTER(vp)]
+    L.b200_grid_set_data.restype = C.c_int
+    L.b200_grid_set_data.argtypes = [vp, C.POINTER(T.DataTables)]
+    L.b200_grid_destroy.restype = None
+    L.b200_grid_destroy.argtypes = [vp]
+    for name in ("b200_ir_interpolate_at", "b200_interpolate_at"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp, C.POINTER(T.Probe)]
+    L.b200_ir_interpolate_at_device.restype = C.c_int
+    L.b200_ir_interpolate_at_device.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp, C.POINTER(T.Probe), vp, C.POINTER(C.c_uint64)]
+    L.b200_moveinto.restype = C.c_int
+    L.b200_moveinto.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(T.Probe)]
+    L.b200_alloc_pinned.restype = vp
+    L.b200_alloc_pinned.argtypes = [C.c_size_t]
+    L.b200_free_pinned.restype = None
+    L.b200_free_pinned.argtypes = [vp]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_abi_version.restype = C.c_int
+    L.b200_device_count.restype = C.c_int
+    L.b200_grid_launch_count.restype = C.c_uint64
+    L.b200_grid_launch_count.argtypes = [vp]
+    L.b200_grid_enable_timing.restype = C.c_int
+    L.b200_grid_enable_timing.argtypes = [vp, C.c_int]
+    L.b200_grid_kernel_ms.restype = C.c_double
+    L.b200_grid_kernel_ms.argtypes = [vp, C.c_char_p]
+    L.b200_grid_row_bytes.restype = C.c_int
+    L.b200_grid_row_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().b200_last_error()
+        raise B200Error(rc, msg.decode() if msg else f"brille_b200 error {rc}")
+
+
+def device_count() -> int:
+    return int(lib().b200_device_count())

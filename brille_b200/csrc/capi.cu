@@ -1,0 +1,697 @@
+// capi.cu -- the C ABI of include/brille_b200.h: table upload, workspace, streams, chunked host pipeline.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "brille_b200.h"
+#include "device_tables.cuh"
+
+namespace b200 {
+// locate.cu
+constexpr uint32_t MODE_NO_MOVE = 1u, MODE_IR = 2u, MODE_NO_LOCATE = 4u;
+cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
+                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
+                          cudaStream_t stream);
+// interp.cu
+struct LocateIn {
+  const double* q_ir;
+  const int32_t* ridx;
+  const int32_t* invridx;
+  const uint32_t* cell;
+  const int32_t* tet;
+  const int32_t* n_vert;
+  const uint32_t* vertex;
+  const double* weight;
+  const uint64_t* slots;
+  const uint32_t* status;
+  const uint8_t* node_type;
+  const uint32_t* node_index;
+};
+cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
+                          cudaStream_t stream);
+}  // namespace b200
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(B200_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);     \
+  } while (0)
+
+// owning device buffer list
+struct DevPool {
+  std::vector<void*> ptrs;
+  template <class T>
+  cudaError_t upload(const T* host, size_t count, const T** out) {
+    *out = nullptr;
+    if (count == 0) return cudaSuccess;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    e = cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    *out = static_cast<const T*>(p);
+    return e;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+struct Workspace {
+  size_t capacity = 0;
+  LocateOut lo{};
+  double* x_ir = nullptr;
+  int32_t* tau = nullptr;
+  std::vector<void*> ptrs;
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    capacity = 0;
+    lo = LocateOut{};
+    x_ir = nullptr;
+    tau = nullptr;
+  }
+  template <class T>
+  cudaError_t get(T** p, size_t count) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, count * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(v);
+    *p = static_cast<T*>(v);
+    return e;
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= capacity) return cudaSuccess;
+    release();
+    cudaError_t e;
+#define WS(field, type, per) if ((e = get<type>(&field, n * (per))) != cudaSuccess) return e;
+    WS(lo.q_ir, double, 3)
+    WS(x_ir, double, 3)
+    WS(tau, int32_t, 3)
+    WS(lo.ridx, int32_t, 1)
+    WS(lo.invridx, int32_t, 1)
+    WS(lo.cell, uint32_t, 1)
+    WS(lo.tet, int32_t, 1)
+    WS(lo.n_vert, int32_t, 1)
+    WS(lo.vertex, uint32_t, 8)
+    WS(lo.weight, double, 8)
+    WS(lo.slots, uint64_t, 1)
+    WS(lo.status, uint32_t, 1)
+#undef WS
+    capacity = n;
+    return cudaSuccess;
+  }
+};
+
+struct HostStage {  // device-side staging buffers of one pipeline slot of the host-pointer API
+  size_t capacity = 0;
+  double* dQ = nullptr;
+  double* dvals = nullptr;
+  double* dvecs = nullptr;
+  Workspace ws;
+  unsigned long long* d_fail = nullptr;  // 3 counters
+  unsigned long long* h_fail = nullptr;  // pinned mirror (keeps the D2H of the counters asynchronous)
+  cudaStream_t stream = nullptr;
+};
+
+struct b200_grid {
+  int device = 0, sm_count = 148, kind = 0;
+  BZDev h_bz;
+  BZDev* d_bz = nullptr;
+  double eps_w = 0, eps_o = 0;
+  TrellisDev tr{};
+  DevPool structure_pool, data_pool;
+  DataDev dd{};
+  bool has_data = false;
+  int values_rot_error = 0, vectors_rot_error = 0;  // B200_E_UNSUPPORTED raised at ir_interpolate_at time
+  size_t vals_row_bytes = 0, vecs_row_bytes = 0;
+  Workspace ws;                 // device-pointer API
+  unsigned long long* d_fail = nullptr;
+  HostStage stage[2];
+  uint64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
+};
+
+// ----------------------------------------------------------------------------------------------------
+// table derivation
+// ----------------------------------------------------------------------------------------------------
+static void tol_pair(double tol, int digit, double* rel, double* abs_) {
+  *rel = DBL_EPSILON * (double)digit * 10000.0;  // approx_float.hpp:78-100, TOL_MULT = 10000
+  *abs_ = 5.0 / 1000000000000000.0;
+  if (tol > *rel) *rel = tol;
+  if (tol > *abs_) *abs_ = tol;
+}
+static void matvec_h(double* c, const double* A, const double* b) {
+  for (int i = 0; i < 3; ++i) {
+    c[i] = 0.0;
+    for (int k = 0; k < 3; ++k) c[i] += A[i * 3 + k] * b[k];
+  }
+}
+// covector m_f with det_f(q) = sum_i (a_i - q_i) m_i == V* (a-q).((b-a)x(c-a)); returns the rounding bound
+static double face_covector(const double* a, const double* b, const double* c, double vol, double* m) {
+  double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  double v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+  m[0] = vol * (u[1] * v[2] - u[2] * v[1]);
+  m[1] = vol * (u[2] * v[0] - u[0] * v[2]);
+  m[2] = vol * (u[0] * v[1] - u[1] * v[0]);
+  double bound = 0.0;
+  for (int i = 0; i < 3; ++i) bound += (std::fabs(a[i]) + 4.0) * std::fabs(m[i]);
+  return 256.0 * DBL_EPSILON * bound;
+}
+
+static int build_bz(const b200_bz_tables_t* t, BZDev* d, double* eps_w, double* eps_o) {
+  if (t->n_faces < 4 || t->n_faces > MAX_FACES) return fail(B200_E_INVALID, "n_faces out of range");
+  if (t->n_ops < 1 || t->n_ops > MAX_OPS) return fail(B200_E_INVALID, "n_ops out of range");
+  if (t->n_wedge < 0 || t->n_wedge > MAX_WEDGE) return fail(B200_E_INVALID, "n_wedge out of range");
+  std::memset(d, 0, sizeof(BZDev));
+  tol_pair(t->float_tolerance, t->approx_tolerance, &d->cfg_rel, &d->cfg_abs);
+  tol_pair(0.0, 1, &d->def_rel, &d->def_abs);
+  d->transform_needed = t->transform_needed;
+  d->n_faces = t->n_faces;
+  d->n_wedge = t->n_wedge;
+  d->n_ops = t->n_ops;
+  d->no_ir_mirroring = t->no_ir_mirroring;
+  d->identity_index = t->identity_index;
+  for (int i = 0; i < 9; ++i) {
+    d->P6t[i] = (double)t->P6t[i];
+    d->invPt[i] = (double)t->invPt[i];
+    d->invPt_i[i] = t->invPt[i];
+    d->w_recip_metric[i] = t->w_recip_metric[i];
+    d->w_real_metric[i] = t->w_real_metric[i];
+    d->o_recip_metric[i] = t->o_recip_metric[i];
+    d->o_real_metric[i] = t->o_real_metric[i];
+    d->to_xyz[i] = t->to_xyz[i];
+  }
+  d->w_recip_volume = t->w_recip_volume;
+  d->o_recip_volume = t->o_recip_volume;
+  *eps_w = *eps_o = 0.0;
+  for (int f = 0; f < t->n_faces; ++f) {
+    for (int i = 0; i < 3; ++i) {
+      d->pa[f][i] = t->pa[3 * f + i];
+      d->pb[f][i] = t->pb[3 * f + i];
+      d->pc[f][i] = t->pc[3 * f + i];
+      d->ca[f][i] = t->ca[3 * f + i];
+      d->cb[f][i] = t->cb[3 * f + i];
+      d->cc[f][i] = t->cc[3 * f + i];
+      d->normals[f][i] = t->normals[3 * f + i];
+      d->taus[f][i] = t->taus[3 * f + i];
+    }
+    d->tau_lens[f] = t->tau_lens[f];
+    *eps_w = std::max(*eps_w, face_covector(d->pa[f], d->pb[f], d->pc[f], t->w_recip_volume, d->pm[f]));
+    *eps_o = std::max(*eps_o, face_covector(d->ca[f], d->cb[f], d->cc[f], t->o_recip_volume, d->cm[f]));
+  }
+  for (int k = 0; k < t->n_wedge; ++k) matvec_h(d->gw[k], t->o_recip_metric, t->wedge_normals + 3 * k);
+  for (int j = 0; j < t->n_ops; ++j) {
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) d->Rt[j][a * 3 + b] = (double)t->rotations[9 * j + b * 3 + a];
+    d->inverse_index[j] = t->inverse_index[j];
+  }
+  return B200_OK;
+}
+
+static int build_trellis(b200_grid* g, const b200_trellis_tables_t* t) {
+  TrellisDev& d = g->tr;
+  DevPool& pool = g->structure_pool;
+  std::vector<double> knots;
+  for (int i = 0; i < 3; ++i) {
+    if (t->n_knots[i] < 2) return fail(B200_E_INVALID, "trellis needs at least two knots per axis");
+    d.n_knots[i] = t->n_knots[i];
+    d.knot_offset[i] = (int)knots.size();
+    knots.insert(knots.end(), t->knots[i], t->knots[i] + t->n_knots[i]);
+  }
+  if (knots.size() > (size_t)MAX_KNOTS * 3) return fail(B200_E_INVALID, "too many trellis knots");
+  if ((size_t)(t->n_knots[0] - 1) * (t->n_knots[1] - 1) * (t->n_knots[2] - 1) != t->n_nodes)
+    return fail(B200_E_INVALID, "n_nodes does not match the knot vectors");
+  d.n_nodes = t->n_nodes;
+  d.n_cubes = t->n_cubes;
+  d.n_tets = t->n_tets;
+  d.n_vertices = t->n_vertices;
+  // packed per-cell geometry: the locate kernel reads one contiguous record per cube / tetrahedron
+  std::vector<double> cube_pack((size_t)t->n_cubes * 24), tet_pack((size_t)t->n_tets * TET_PACK, 0.0);
+  for (size_t c = 0; c < t->n_cubes; ++c)
+    for (int i = 0; i < 8; ++i) {
+      uint32_t v = t->cube_vertices[8 * c + i];
+      if (v >= t->n_vertices) return fail(B200_E_INVALID, "cube vertex index out of range");
+      for (int k = 0; k < 3; ++k) cube_pack[24 * c + 3 * i + k] = t->vertices[3 * (size_t)v + k];
+    }
+  for (size_t k = 0; k < t->n_tets; ++k) {
+    double* p = &tet_pack[k * TET_PACK];
+    const double* ci = t->tet_circum + 4 * k;
+    p[0] = ci[0]; p[1] = ci[1]; p[2] = ci[2];
+    p[3] = ci[3] * ci[3];  // r^2 exactly as trellis_node.hpp:359
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v = t->tet_vertices[4 * k + j];
+      if (v >= t->n_vertices) return fail(B200_E_INVALID, "tetrahedron vertex index out of range");
+      for (int c = 0; c < 3; ++c) p[4 + 3 * j + c] = t->vertices[3 * (size_t)v + c];
+    }
+    p[16] = t->tet_volume[k] * 6.0;  // trellis_node.hpp:330
+  }
+  CU(pool.upload(knots.data(), knots.size(), &d.knots));
+  CU(pool.upload(t->node_type, t->n_nodes, &d.node_type));
+  CU(pool.upload(t->node_index, t->n_nodes, &d.node_index));
+  CU(pool.upload(t->cube_vertices, (size_t)t->n_cubes * 8, &d.cube_vertices));
+  CU(pool.upload(cube_pack.data(), cube_pack.size(), &d.cube_pack));
+  CU(pool.upload(t->poly_offsets, (size_t)t->n_polys + 1, &d.poly_offsets));
+  CU(pool.upload(t->tet_vertices, (size_t)t->n_tets * 4, &d.tet_vertices));
+  CU(pool.upload(tet_pack.data(), tet_pack.size(), &d.tet_pack));
+  return B200_OK;
+}
+
+// rotation dispatch of Interpolator::rotate_in_place (interpolator.hpp:386-428)
+static int rot_kind_of(const b200_interp_desc_t& d, int* err) {
+  *err = 0;
+  const uint32_t no1 = d.elements[1] / 3u, no2 = d.elements[2] / 9u;
+  int kind = -1;
+  switch (d.length_unit) {
+    case B200_LEN_REAL_LATTICE:
+      if (d.rotates_like == B200_ROT_VECTOR) kind = 0;
+      else if (d.rotates_like == B200_ROT_PSEUDOVECTOR) kind = 2;
+      else if (d.rotates_like == B200_ROT_GAMMA) kind = 3;
+      else *err = B200_E_UNSUPPORTED;
+      break;
+    case B200_LEN_RECIPROCAL_LATTICE:
+      if (d.rotates_like == B200_ROT_VECTOR) kind = 1; else *err = B200_E_UNSUPPORTED;
+      break;
+    case B200_LEN_ANGSTROM:
+      if (d.rotates_like == B200_ROT_GAMMA) kind = 4; else *err = B200_E_UNSUPPORTED;
+      break;
+    default:
+      *err = B200_E_UNSUPPORTED;
+  }
+  if (*err) return -1;
+  if (kind >= 3 && !d.is_complex) {  // "RotatesLike == Gamma requires complex valued data!" interpolator.hpp:616-620
+    *err = B200_E_UNSUPPORTED;
+    return -1;
+  }
+  if (no1 == 0 && no2 == 0) return -1;  // pure scalars: rip_* return false immediately
+  if (kind >= 3) {
+    uint32_t Nmat = (uint32_t)(std::sqrt((double)no2)) / 3u;  // interpolator_gamma.tpp:66-70
+    if (no2 != 9 * Nmat * Nmat) return -1;
+  }
+  return kind;
+}
+
+static int fill_interp(b200_grid* g, const b200_interp_desc_t& s, uint32_t n_vertices, InterpDev* d, int* rot_err) {
+  d->is_complex = s.is_complex;
+  d->branches = s.branches;
+  d->no0 = s.elements[0];
+  if (s.elements[1] % 3) return fail(B200_E_INVALID, "Vectors must have 3N elements per branch");
+  if (s.elements[2] % 9) return fail(B200_E_INVALID, "Matrices must have 9N elements per branch");
+  d->no1 = s.elements[1] / 3u;
+  d->no2 = s.elements[2] / 9u;
+  d->span = s.elements[0] + s.elements[1] + s.elements[2];
+  d->rot_kind = rot_kind_of(s, rot_err);
+  size_t count = (size_t)n_vertices * s.branches * d->span * (s.is_complex ? 2 : 1);
+  if (count && !s.data) return fail(B200_E_INVALID, "interpolation data pointer is NULL");
+  CU(g->data_pool.upload(static_cast<const double*>(s.data), count, &d->data));
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// life cycle
+// ----------------------------------------------------------------------------------------------------
+extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void* structure, int device, b200_grid_t** out) {
+  if (!bz || !structure || !out) return fail(B200_E_INVALID, "NULL argument");
+  if (kind != B200_GRID_TRELLIS) return fail(B200_E_UNSUPPORTED, "only trellis grids are implemented so far");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B200_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); brille_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(B200_E_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  b200_grid* g = new b200_grid();
+  g->device = device;
+  g->kind = kind;
+  cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+  int rc = build_bz(bz, &g->h_bz, &g->eps_w, &g->eps_o);
+  if (rc == B200_OK) {
+    const BZDev* p = nullptr;
+    cudaError_t ce = g->structure_pool.upload(&g->h_bz, 1, &p);
+    g->d_bz = const_cast<BZDev*>(p);
+    if (ce != cudaSuccess) rc = fail(B200_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(ce));
+  }
+  if (rc == B200_OK) rc = build_trellis(g, static_cast<const b200_trellis_tables_t*>(structure));
+  if (rc == B200_OK && cudaMalloc(&g->d_fail, 3 * sizeof(unsigned long long)) != cudaSuccess)
+    rc = fail(B200_E_CUDA, "cudaMalloc failed");
+  for (int s = 0; s < 2 && rc == B200_OK; ++s) {
+    if (cudaStreamCreateWithFlags(&g->stage[s].stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&g->stage[s].d_fail, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc(&g->stage[s].h_fail, 3 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
+      rc = fail(B200_E_CUDA, "stream/counter creation failed");
+  }
+  for (int i = 0; i < 3 && rc == B200_OK; ++i)
+    if (cudaEventCreate(&g->ev[i]) != cudaSuccess) rc = fail(B200_E_CUDA, "event creation failed");
+  if (rc != B200_OK) {
+    b200_grid_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return B200_OK;
+}
+
+extern "C" void b200_grid_destroy(b200_grid_t* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  g->structure_pool.release();
+  g->data_pool.release();
+  g->ws.release();
+  if (g->d_fail) cudaFree(g->d_fail);
+  for (int s = 0; s < 2; ++s) {
+    HostStage& h = g->stage[s];
+    h.ws.release();
+    if (h.dQ) cudaFree(h.dQ);
+    if (h.dvals) cudaFree(h.dvals);
+    if (h.dvecs) cudaFree(h.dvecs);
+    if (h.d_fail) cudaFree(h.d_fail);
+    if (h.h_fail) cudaFreeHost(h.h_fail);
+    if (h.stream) cudaStreamDestroy(h.stream);
+  }
+  for (int i = 0; i < 3; ++i)
+    if (g->ev[i]) cudaEventDestroy(g->ev[i]);
+  delete g;
+}
+
+extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
+  if (!g || !t) return fail(B200_E_INVALID, "NULL argument");
+  CU(cudaSetDevice(g->device));
+  CU(cudaDeviceSynchronize());
+  g->data_pool.release();
+  g->has_data = false;
+  if (t->n_vertices != g->tr.n_vertices)
+    return fail(B200_E_INVALID, "Provided " + std::to_string(t->n_vertices) + " arrays but " + std::to_string(g->tr.n_vertices) + " were expected!");
+  if (t->values.branches != t->vectors.branches)
+    return fail(B200_E_INVALID, "Inconsistent values and vectors provided to DualInterpolator");  // interpolatordual.hpp:90-91
+  DataDev d{};
+  int rc = fill_interp(g, t->values, t->n_vertices, &d.values, &g->values_rot_error);
+  if (rc) return rc;
+  rc = fill_interp(g, t->vectors, t->n_vertices, &d.vectors, &g->vectors_rot_error);
+  if (rc) return rc;
+  const uint32_t B = t->values.branches;
+  d.n_perm_rows = t->n_perm_rows;
+  if (t->n_perm_rows > 1) {
+    if (!t->perm_rows || !t->cube_perm || !t->tet_perm) {
+      if (!t->perm_rows || (g->tr.n_cubes && !t->cube_perm) || (g->tr.n_tets && !t->tet_perm))
+        return fail(B200_E_INVALID, "permutation rows given without the per-cell pair tables");
+    }
+    CU(g->data_pool.upload(t->perm_rows, (size_t)t->n_perm_rows * B, &d.perm_rows));
+    CU(g->data_pool.upload(t->cube_perm, (size_t)g->tr.n_cubes * 64, &d.cube_perm));
+    CU(g->data_pool.upload(t->tet_perm, (size_t)g->tr.n_tets * 16, &d.tet_perm));
+  }
+  const int G = g->h_bz.n_ops;
+  d.n_ops = (uint32_t)G;
+  d.n_atoms = t->n_atoms;
+  const bool gamma = d.values.rot_kind >= 3 || d.vectors.rot_kind >= 3;
+  if (gamma) {
+    if (!t->n_atoms || !t->gamma_F0 || !t->gamma_vidx || !t->gamma_vectors)
+      return fail(B200_E_INVALID, "RotatesLike::Gamma data needs the GammaTable (an atom basis)");
+    auto check = [&](const InterpDev& i) {
+      return i.rot_kind < 3 || (i.no1 <= t->n_atoms && (uint32_t)(std::sqrt((double)i.no2)) / 3u <= t->n_atoms);
+    };
+    if (!check(d.values) || !check(d.vectors)) return fail(B200_E_INVALID, "Attempting to access out of bounds mapping!");  // phonon.hpp:190-193
+    for (size_t i = 0; i < (size_t)t->n_atoms * G; ++i)
+      if (t->gamma_F0[i] >= t->n_atoms || t->gamma_vidx[i] >= t->n_gamma_vectors) return fail(B200_E_INVALID, "GammaTable index out of range");
+    CU(g->data_pool.upload(t->gamma_F0, (size_t)t->n_atoms * G, &d.gamma_F0));
+    CU(g->data_pool.upload(t->gamma_vidx, (size_t)t->n_atoms * G, &d.gamma_vidx));
+    CU(g->data_pool.upload(t->gamma_vectors, (size_t)t->n_gamma_vectors * 3, &d.gamma_vectors));
+  }
+  if ((d.values.rot_kind == 4 || d.vectors.rot_kind == 4)) {
+    if (!t->rot_cart) return fail(B200_E_INVALID, "LengthUnit::angstrom Gamma data needs rot_cart");
+    CU(g->data_pool.upload(t->rot_cart, (size_t)G * 9, &d.rot_cart));
+  }
+  {  // rotations as doubles: [0,G) R, [G,2G) R^T ; determinants ; identity flags
+    std::vector<double> ri((size_t)G * 18), det(G);
+    std::vector<uint8_t> isid(G);
+    for (int j = 0; j < G; ++j) {
+      double R[9];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) R[3 * a + b] = g->h_bz.Rt[j][3 * b + a];
+      for (int i = 0; i < 9; ++i) {
+        ri[9 * j + i] = R[i];
+        ri[9 * (G + j) + i] = g->h_bz.Rt[j][i];
+      }
+      det[j] = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+      static const double E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      isid[j] = std::memcmp(R, E, sizeof(E)) == 0;
+    }
+    CU(g->data_pool.upload(ri.data(), ri.size(), &d.rot_int));
+    CU(g->data_pool.upload(det.data(), det.size(), &d.rot_det));
+    CU(g->data_pool.upload(isid.data(), isid.size(), &d.rot_is_identity));
+  }
+  g->dd = d;
+  g->vals_row_bytes = (size_t)B * d.values.span * (d.values.is_complex ? 16 : 8);
+  g->vecs_row_bytes = (size_t)B * d.vectors.span * (d.vectors.is_complex ? 16 : 8);
+  g->has_data = t->n_vertices > 0 && B > 0;
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// the path
+// ----------------------------------------------------------------------------------------------------
+static LocateIn as_input(const b200_grid* g, const LocateOut& lo) {
+  LocateIn in{};
+  in.q_ir = lo.q_ir; in.ridx = lo.ridx; in.invridx = lo.invridx; in.cell = lo.cell; in.tet = lo.tet;
+  in.n_vert = lo.n_vert; in.vertex = lo.vertex; in.weight = lo.weight; in.slots = lo.slots; in.status = lo.status;
+  in.node_type = g->tr.node_type;
+  in.node_index = g->tr.node_index;
+  return in;
+}
+
+static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+    auto& e = g->kernel_ms[name];
+    e.first += ms;
+    e.second += 1;
+  }
+}
+
+// enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
+static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
+                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
+  CU(ws.ensure(n));
+  CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
+  LocateOut lo = ws.lo;
+  lo.x_ir = ws.x_ir;
+  lo.tau = ws.tau;
+  if (g->timing) cudaEventRecord(g->ev[0], stream);
+  CU(launch_locate(g->d_bz, g->tr, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
+  g->launches += 1;
+  if (g->timing) cudaEventRecord(g->ev[1], stream);
+  if (interp) {
+    CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream));
+    g->launches += 1;
+    if (g->timing) cudaEventRecord(g->ev[2], stream);
+  }
+  if (g->timing) {
+    cudaEventSynchronize(interp ? g->ev[2] : g->ev[1]);
+    note_time(g, "locate", g->ev[0], g->ev[1]);
+    if (interp) note_time(g, "interpolate", g->ev[1], g->ev[2]);
+  }
+  return B200_OK;
+}
+
+static int status_error(const unsigned long long* c, size_t nQ) {
+  // order of the reference's checks: moveinto (bz_move.cpp:151-158), wedge (:288-294), then location
+  if (c[0]) return fail(B200_E_OUTSIDE_BZ, "Not all points inside Brillouin zone (" + std::to_string(c[0]) + " of " + std::to_string(nQ) + " still outside)");
+  if (c[1]) return fail(B200_E_OUTSIDE_WEDGE, std::to_string(c[1]) + " Q point(s) are outside of the irreducible BrillouinZone");
+  if (c[2]) return fail(B200_E_NOT_FOUND, "interpolate_at failed to find " + std::to_string(c[2]) + (c[2] > 1 ? " points." : " point."));
+  return B200_OK;
+}
+
+static int check_ready(b200_grid* g, bool need_data, int ir) {
+  if (!g) return fail(B200_E_INVALID, "NULL grid");
+  if (need_data && !g->has_data) return fail(B200_E_NODATA, "The interpolation data must be filled before interpolating.");
+  if (need_data && ir) {
+    if (g->values_rot_error || g->vectors_rot_error)
+      return fail(B200_E_UNSUPPORTED, "LengthUnit, RotatesLike combination not implemented");
+  }
+  return B200_OK;
+}
+
+static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_t flags, int ir, void* dvals, void* dvecs,
+                              b200_probe_t* dprobe, cudaStream_t stream, uint64_t* n_failed) {
+  int rc = check_ready(g, true, ir);
+  if (rc) return rc;
+  CU(cudaSetDevice(g->device));
+  if (g->timing) g->kernel_ms.clear();
+  uint32_t mode = (flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u;
+  if (ir) mode |= MODE_IR;
+  rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, ir, static_cast<double*>(dvals), static_cast<double*>(dvecs), stream);
+  if (rc) return rc;
+  if (dprobe) {
+    const LocateOut& lo = g->ws.lo;
+#define CP(dst, src, type, per) if (dprobe->dst) CU(cudaMemcpyAsync(dprobe->dst, src, nQ * (per) * sizeof(type), cudaMemcpyDeviceToDevice, stream));
+    CP(q_ir, lo.q_ir, double, 3) CP(x_ir, g->ws.x_ir, double, 3) CP(tau, g->ws.tau, int32_t, 3) CP(ridx, lo.ridx, int32_t, 1)
+    CP(invridx, lo.invridx, int32_t, 1) CP(cell, lo.cell, uint32_t, 1) CP(tet, lo.tet, int32_t, 1) CP(n_vert, lo.n_vert, int32_t, 1)
+    CP(vertex, lo.vertex, uint32_t, 8) CP(weight, lo.weight, double, 8) CP(status, lo.status, uint32_t, 1)
+#undef CP
+  }
+  if (n_failed) {
+    unsigned long long c[3];
+    CU(cudaMemcpyAsync(c, g->d_fail, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    *n_failed = c[0] + c[1] + c[2];
+    return status_error(c, nQ);
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_ir_interpolate_at_device(b200_grid_t* g, const double* dQ, size_t nQ, uint32_t flags, void* dvals,
+                                             void* dvecs, b200_probe_t* dprobe, void* stream, uint64_t* n_failed) {
+  return interpolate_device(g, dQ, nQ, flags, 1, dvals, dvecs, dprobe, static_cast<cudaStream_t>(stream), n_failed);
+}
+
+// host-pointer pipeline: chunks alternate between two stages (stream + staging buffers) so that the H2D copy of
+// chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i
+static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
+                         b200_probe_t* probe) {
+  CU(cudaSetDevice(g->device));
+  if (g->timing) g->kernel_ms.clear();
+  const size_t per_q = 24 + (interp ? g->vals_row_bytes + g->vecs_row_bytes : 0) + 200;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = std::min<size_t>(free_b / 4, (size_t)6 << 30);  // both stages together
+  size_t chunk = std::max<size_t>(1024, budget / 2 / per_q);
+  chunk = std::min(chunk, (size_t)1 << 22);
+  if (chunk > nQ) chunk = std::max<size_t>(nQ, 1);
+  unsigned long long total[3] = {0, 0, 0};
+  bool pending[2] = {false, false};
+  size_t nchunks = (nQ + chunk - 1) / chunk;
+  for (size_t c = 0; c < nchunks; ++c) {
+    HostStage& h = g->stage[c & 1];
+    if (pending[c & 1]) {  // staging buffers of this slot are reused: wait for its previous chunk
+      CU(cudaStreamSynchronize(h.stream));
+      for (int k = 0; k < 3; ++k) total[k] += h.h_fail[k];
+      pending[c & 1] = false;
+    }
+    const size_t lo = c * chunk, n = std::min(chunk, nQ - lo);
+    if (h.capacity < n) {
+      if (h.dQ) cudaFree(h.dQ);
+      if (h.dvals) cudaFree(h.dvals);
+      if (h.dvecs) cudaFree(h.dvecs);
+      h.dQ = h.dvals = h.dvecs = nullptr;
+      h.capacity = 0;
+      CU(cudaMalloc(&h.dQ, n * 3 * sizeof(double)));
+      if (interp) {
+        CU(cudaMalloc(&h.dvals, std::max<size_t>(n * g->vals_row_bytes, 8)));
+        CU(cudaMalloc(&h.dvecs, std::max<size_t>(n * g->vecs_row_bytes, 8)));
+      }
+      h.capacity = n;
+    } else if (interp && !h.dvals) {
+      CU(cudaMalloc(&h.dvals, std::max<size_t>(h.capacity * g->vals_row_bytes, 8)));
+      CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
+    }
+    CU(cudaMemcpyAsync(h.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h.stream));
+    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream);
+    if (rc) return rc;
+    if (interp) {
+      CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+      CU(cudaMemcpyAsync(static_cast<char*>(vecs) + lo * g->vecs_row_bytes, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+    }
+    if (probe) {
+      const LocateOut& w = h.ws.lo;
+#define CP(dst, src, type, per) if (probe->dst && src) CU(cudaMemcpyAsync(probe->dst + lo * (per), src, n * (per) * sizeof(type), cudaMemcpyDeviceToHost, h.stream));
+      CP(q_ir, w.q_ir, double, 3) CP(x_ir, h.ws.x_ir, double, 3) CP(tau, h.ws.tau, int32_t, 3) CP(ridx, w.ridx, int32_t, 1)
+      CP(invridx, w.invridx, int32_t, 1) CP(status, w.status, uint32_t, 1)
+      if (!(mode & MODE_NO_LOCATE)) {
+        CP(cell, w.cell, uint32_t, 1) CP(tet, w.tet, int32_t, 1) CP(n_vert, w.n_vert, int32_t, 1)
+        CP(vertex, w.vertex, uint32_t, 8) CP(weight, w.weight, double, 8)
+      }
+#undef CP
+    }
+    CU(cudaMemcpyAsync(h.h_fail, h.d_fail, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h.stream));
+    pending[c & 1] = true;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (pending[s]) {
+      CU(cudaStreamSynchronize(g->stage[s].stream));
+      for (int k = 0; k < 3; ++k) total[k] += g->stage[s].h_fail[k];
+    }
+  return status_error(total, nQ);
+}
+
+extern "C" int b200_ir_interpolate_at(b200_grid_t* g, const double* Q, size_t nQ, uint32_t flags, void* vals, void* vecs,
+                                      b200_probe_t* probe) {
+  int rc = check_ready(g, true, 1);
+  if (rc) return rc;
+  if (nQ && (!Q || !vals || !vecs)) return fail(B200_E_INVALID, "NULL buffer");
+  if (nQ == 0) return B200_OK;
+  uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
+  return host_pipeline(g, Q, nQ, mode, true, 1, vals, vecs, probe);
+}
+
+extern "C" int b200_interpolate_at(b200_grid_t* g, const double* Q, size_t nQ, uint32_t flags, void* vals, void* vecs,
+                                   b200_probe_t* probe) {
+  int rc = check_ready(g, true, 0);
+  if (rc) return rc;
+  if (nQ && (!Q || !vals || !vecs)) return fail(B200_E_INVALID, "NULL buffer");
+  if (nQ == 0) return B200_OK;
+  uint32_t mode = (flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u;
+  return host_pipeline(g, Q, nQ, mode, true, 0, vals, vecs, probe);
+}
+
+extern "C" int b200_moveinto(b200_grid_t* g, const double* Q, size_t nQ, int ir, b200_probe_t* probe) {
+  int rc = check_ready(g, false, 0);
+  if (rc) return rc;
+  if (nQ && (!Q || !probe)) return fail(B200_E_INVALID, "NULL buffer");
+  if (nQ == 0) return B200_OK;
+  return host_pipeline(g, Q, nQ, MODE_NO_LOCATE | (ir ? MODE_IR : 0u), false, ir, nullptr, nullptr, probe);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// introspection
+// ----------------------------------------------------------------------------------------------------
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" void* b200_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    g_err = "cudaHostAlloc failed";
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void b200_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+extern "C" int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" uint64_t b200_grid_launch_count(const b200_grid_t* g) { return g ? g->launches : 0; }
+extern "C" int b200_grid_enable_timing(b200_grid_t* g, int on) {
+  if (!g) return fail(B200_E_INVALID, "NULL grid");
+  g->timing = on != 0;
+  g->kernel_ms.clear();
+  return B200_OK;
+}
+extern "C" double b200_grid_kernel_ms(const b200_grid_t* g, const char* name) {
+  if (!g || !name) return -1.0;
+  auto it = g->kernel_ms.find(name);
+  if (it == g->kernel_ms.end() || it->second.second == 0) return -1.0;
+  return it->second.first / it->second.second;
+}
+extern "C" int b200_grid_row_bytes(const b200_grid_t* g, size_t* v, size_t* w) {
+  if (!g || !g->has_data) return fail(B200_E_NODATA, "The interpolation data must be filled before interpolating.");
+  if (v) *v = g->vals_row_bytes;
+  if (w) *w = g->vecs_row_bytes;
+  return B200_OK;
+}

@@ -1,0 +1,91 @@
+// device_tables.cuh -- device-side layouts derived from the flat host tables (include/brille_b200.h)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr int MAX_FACES = 32;  // faces of a first Brillouin zone (<= 14 for 3-D lattices)
+constexpr int MAX_OPS = 48;    // order of a crystallographic point group
+constexpr int MAX_WEDGE = 16;  // irreducible wedge normals
+constexpr int MAX_KNOTS = 1024;
+
+// Everything ir_moveinto needs, small enough (< 12 KB) to be staged in shared memory by every CTA.
+struct BZDev {
+  // approx_float tolerances (approx_float.hpp:78-100): configured (tol,digit) and default (0,1)
+  double cfg_rel, cfg_abs, def_rel, def_abs;
+  int transform_needed, n_faces, n_wedge, n_ops, no_ir_mirroring, identity_index;
+  double P6t[9];    // int matrix stored as double (products int*double are exact conversions)
+  double invPt[9];
+  int invPt_i[9];
+  double w_recip_metric[9], w_real_metric[9], w_recip_volume;
+  double o_recip_metric[9], o_real_metric[9], o_recip_volume;
+  double to_xyz[9];
+  // working-lattice faces: plane points (exact fallback) and covector fast path det_f(q) = sum_i (a_i-q_i) m_i
+  double pa[MAX_FACES][3], pb[MAX_FACES][3], pc[MAX_FACES][3], pm[MAX_FACES][3];
+  // conventional-lattice faces for the isinside re-check
+  double ca[MAX_FACES][3], cb[MAX_FACES][3], cc[MAX_FACES][3], cm[MAX_FACES][3];
+  double normals[MAX_FACES][3];  // n/|n|
+  int taus[MAX_FACES][3];
+  double tau_lens[MAX_FACES];
+  double gw[MAX_WEDGE][3];  // (G* n_k) of same_lattice_dot, computed once in the reference's order
+  double Rt[MAX_OPS][9];    // transposed rotations as doubles
+  int inverse_index[MAX_OPS];
+};
+
+struct TrellisDev {
+  int n_knots[3];
+  int knot_offset[3];
+  const double* knots;  // concatenated knot vectors
+  uint32_t n_nodes;
+  const uint8_t* node_type;
+  const uint32_t* node_index;
+  const uint32_t* cube_vertices;  // (n_cubes, 8)
+  const double* cube_pack;        // (n_cubes, 24): xyz of the 8 corners
+  const uint32_t* poly_offsets;
+  const uint32_t* tet_vertices;   // (n_tets, 4)
+  const double* tet_pack;         // (n_tets, 18): cx cy cz r^2 | v0 v1 v2 v3 (xyz) | 6*vol | pad
+  uint32_t n_cubes, n_tets, n_vertices;
+};
+constexpr int TET_PACK = 18;
+
+// per-Q result of the locate stage, consumed by the interpolation stage (SoA, all device pointers)
+struct LocateOut {
+  double* q_ir;      // (n,3)
+  double* x_ir;      // (n,3) optional
+  int32_t* tau;      // (n,3) optional
+  int32_t* ridx;     // (n)
+  int32_t* invridx;  // (n)
+  uint32_t* cell;    // (n) node linear index
+  int32_t* tet;      // (n) global tetrahedron index or -1
+  int32_t* n_vert;   // (n)
+  uint32_t* vertex;  // (n,8)
+  double* weight;    // (n,8)
+  uint64_t* slots;   // (n) 8 packed corner slots (emission order), byte j = slot of emitted vertex j
+  uint32_t* status;  // (n)
+};
+
+struct InterpDev {
+  const double* data;  // (n_vert, branches*span) double or complex (as double pairs)
+  int is_complex;
+  uint32_t branches, span, no0, no1, no2;  // scalars, #3-vectors, #3x3 matrices per mode
+  int rot_kind;  // 0 real vector, 1 reciprocal vector, 2 axial, 3 gamma (int R), 4 gamma (cartesian R), -1 nothing to rotate
+};
+
+struct DataDev {
+  InterpDev values, vectors;
+  uint32_t n_perm_rows;
+  const uint32_t* perm_rows;  // (n_perm_rows, branches)
+  const uint32_t* cube_perm;  // (n_cubes, 64)
+  const uint32_t* tet_perm;   // (n_tets, 16)
+  uint32_t n_atoms, n_ops;
+  const uint32_t* gamma_F0;
+  const uint32_t* gamma_vidx;
+  const double* gamma_vectors;
+  const double* rot_int;   // (G,9) rotations as doubles
+  const double* rot_cart;  // (G,9)
+  const double* rot_det;   // (G)
+  const uint8_t* rot_is_identity;  // (G)
+};
+
+}  // namespace b200

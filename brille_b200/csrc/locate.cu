@@ -1,0 +1,455 @@
+// locate.cu -- stage 1 of the path, one thread per Q:
+//   BrillouinZone::ir_moveinto  (bz_move.cpp:14-53,103-163,165-296)  -> q_ir, tau, Ridx, invRidx
+//   LVec::xyz                   (array_lvec_methods.tpp:40-52)       -> x = B q
+//   PolyTrellis::indices_weights (trellis_poly.hpp:245-255,382-434; trellis_node.hpp:130-149,273-364)
+//                                                                     -> (vertex, weight) list
+//
+// This file is compiled with -fmad=false: the reference is x86-64 baseline code (no fused
+// multiply-add), and every branch decision below is taken on numbers computed in the reference's
+// own operation order, so tau / R / node / tetrahedron / weights come out bit-identical.
+// The one place where a cheaper formula is used (first-Brillouin-zone inside test through a
+// pre-multiplied plane covector) is *certified*: when the cheap value lies within its rounding bound
+// of the decision threshold the reference's lattice-aware triple product is evaluated instead.
+#include "device_tables.cuh"
+#include "brille_b200.h"
+
+namespace b200 {
+
+#define TWO_PI 6.283185307179586476925286766559005768394338798750211641949889
+
+__device__ __forceinline__ bool approx_eq(double a, double b, double rel, double abs_) {
+  double x = fabs(a - b);  // approx_float.hpp:171-188
+  return x <= abs_ + rel * fabs(a + b) || x < 2.2250738585072014e-308;
+}
+
+__device__ __forceinline__ void matvec(double* c, const double* A, const double* b) {
+  // utilities.tpp:39-44 : C[i] = ((0 + A0*b0) + A1*b1) + A2*b2
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = ((0.0 + A[i * 3] * b[0]) + A[i * 3 + 1] * b[1]) + A[i * 3 + 2] * b[2];
+}
+
+// reference-exact lattice-aware triple product (geometry.hpp:118-138 through the LVec cross/star/dot of
+// array_functions.hpp:190-201,246-290 and array_lvec_methods.tpp:53-67); only used when the fast value
+// is within its error bound of the tolerance threshold
+__device__ __noinline__ double exact_face_min(const double* recip_metric, const double* real_metric, double recip_volume,
+                                               int nf, const double (*pa)[3], const double (*pb)[3],
+                                               const double (*pc)[3], const double* q) {
+  double m = 0.0;
+  const double s = recip_volume / TWO_PI;
+  for (int f = 0; f < nf; ++f) {
+    double u[3], v[3], w[3], cr[3], st[3], tmp[3];
+    for (int i = 0; i < 3; ++i) {
+      u[i] = pa[f][i] - q[i];
+      v[i] = pb[f][i] - q[i];
+      w[i] = pc[f][i] - q[i];
+    }
+    cr[0] = v[1] * w[2] - v[2] * w[1];
+    cr[1] = v[2] * w[0] - v[0] * w[2];
+    cr[2] = v[0] * w[1] - v[1] * w[0];
+    for (int i = 0; i < 3; ++i) cr[i] *= s;
+    matvec(st, real_metric, cr);
+    for (int i = 0; i < 3; ++i) st[i] /= TWO_PI;
+    matvec(tmp, recip_metric, u);
+    double o = ((0.0 + tmp[0] * st[0]) + tmp[1] * st[1]) + tmp[2] * st[2];
+    if (f == 0 || o < m) m = o;
+  }
+  return m;
+}
+
+// point_inside_all_planes (geometry.hpp:412-418) with tolerance (float_tolerance, approx_tolerance)
+__device__ __forceinline__ bool inside_planes(const BZDev& bz, bool working, const double* q, double eps) {
+  const double(*pa)[3] = working ? bz.pa : bz.ca;
+  const double(*pm)[3] = working ? bz.pm : bz.cm;
+  double m = 1e300;
+  for (int f = 0; f < bz.n_faces; ++f) {
+    double o = ((pa[f][0] - q[0]) * pm[f][0] + (pa[f][1] - q[1]) * pm[f][1]) + (pa[f][2] - q[2]) * pm[f][2];
+    m = fmin(m, o);
+  }
+  const double thr = -bz.cfg_abs;
+  if (m > thr + eps) return true;
+  if (m < thr - eps - 4.0 * bz.cfg_rel * bz.cfg_abs) return false;
+  // ambiguous: evaluate exactly what the reference evaluates
+  double e = working ? exact_face_min(bz.w_recip_metric, bz.w_real_metric, bz.w_recip_volume, bz.n_faces, bz.pa, bz.pb, bz.pc, q)
+                     : exact_face_min(bz.o_recip_metric, bz.o_real_metric, bz.o_recip_volume, bz.n_faces, bz.ca, bz.cb, bz.cc, q);
+  return e > 0 || approx_eq(e, 0.0, bz.cfg_rel, bz.cfg_abs);
+}
+
+// _inside_wedge_outer (bz.hpp:757-763; Array2::all array2.tpp:664-672)
+__device__ __forceinline__ bool inside_wedge(const BZDev& bz, const double* q) {
+  const int K = bz.n_wedge;
+  if (K == 0) return true;
+  if (bz.no_ir_mirroring) {
+    for (int k = 0; k < K; ++k) {
+      double d = ((0.0 + bz.gw[k][0] * q[0]) + bz.gw[k][1] * q[1]) + bz.gw[k][2] * q[2];
+      if (!(approx_eq(d, 0.0, bz.cfg_rel, bz.cfg_abs) || d > 0.0)) return false;
+    }
+    return true;
+  }
+  bool all_le = true, all_ge = true;  // le_ge drops the tolerances (array2.tpp:666-667)
+  for (int k = 0; k < K; ++k) {
+    double d = ((0.0 + bz.gw[k][0] * q[0]) + bz.gw[k][1] * q[1]) + bz.gw[k][2] * q[2];
+    bool z = approx_eq(d, 0.0, bz.def_rel, bz.def_abs);
+    if (!(z || d < 0.0)) all_le = false;
+    if (!(z || d > 0.0)) all_ge = false;
+  }
+  return all_le || all_ge;
+}
+
+// moveinto for one Q: part_moveinto_prim (bz_move.cpp:14-53) between the two lattice transforms
+__device__ __forceinline__ uint32_t moveinto_one(const BZDev& bz, double eps_w, double eps_o, const double* Q, double* qo, int* tauo) {
+  double q[3];
+  int tau[3], last[3];
+  {
+    double Qp[3];
+    if (bz.transform_needed) {
+      matvec(Qp, bz.P6t, Q);  // transform.hpp:182-190
+      for (int i = 0; i < 3; ++i) Qp[i] /= 6.0;
+    } else {
+      for (int i = 0; i < 3; ++i) Qp[i] = Q[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+      double r = round(Qp[i]);  // half away from zero, array2.tpp:498-505
+      tau[i] = (int)r;
+      q[i] = Qp[i] - (double)tau[i];
+      last[i] = tau[i];
+    }
+  }
+  const int F = bz.n_faces;
+  int count = 0;
+  while (count++ < F && !inside_planes(bz, true, q, eps_w)) {
+    double tmp[3];
+    matvec(tmp, bz.w_recip_metric, q);  // same_lattice_dot: (G q) . n
+    int max_nm = 0, max_at = 0;
+    double d_at = 0.0;
+    for (int j = 0; j < F; ++j) {
+      double d = ((0.0 + tmp[0] * bz.normals[j][0]) + tmp[1] * bz.normals[j][1]) + tmp[2] * bz.normals[j][2];
+      int N = (int)round(d / bz.tau_lens[j]);
+      if (N > 0 && N >= max_nm) {
+        bool ok = (0 == max_nm);
+        if (!ok) {
+          // norm(taus.view(j)+last_shift) > 0 (bz_move.cpp:38): the norm of an integer lattice vector is
+          // zero iff the vector is zero
+          bool nz = (bz.taus[j][0] + last[0]) != 0 || (bz.taus[j][1] + last[1]) != 0 || (bz.taus[j][2] + last[2]) != 0;
+          ok = nz && d > d_at;
+        }
+        if (ok) {
+          max_at = j;
+          max_nm = N;
+          d_at = d;
+        }
+      }
+    }
+    if (max_nm > 0) {
+      for (int i = 0; i < 3; ++i) {
+        int t = bz.taus[max_at][i];
+        q[i] -= (double)t * (double)max_nm;
+        tau[i] += t * max_nm;
+        last[i] = t * max_nm;
+      }
+    }
+  }
+  if (bz.transform_needed) {  // transform.hpp:222-230
+    matvec(qo, bz.invPt, q);
+    for (int i = 0; i < 3; ++i)
+      tauo[i] = bz.invPt_i[i * 3] * tau[0] + bz.invPt_i[i * 3 + 1] * tau[1] + bz.invPt_i[i * 3 + 2] * tau[2];
+  } else {
+    for (int i = 0; i < 3; ++i) {
+      qo[i] = q[i];
+      tauo[i] = tau[i];
+    }
+  }
+  // bz_move.cpp:149: every q is re-tested against the conventional-lattice planes
+  return inside_planes(bz, false, qo, eps_o) ? 0u : (uint32_t)B200_ST_OUTSIDE_BZ;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trellis
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_bin(const double* k, int n, double x) {
+  // trellis_poly.hpp:67-73: index of the first knot > x (knots ascend => binary search is the same scan)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (k[mid] > x) hi = mid; else lo = mid + 1;
+  }
+  int d = lo;
+  if (d > n - 1 && x < k[0]) d = 0;
+  return d > 0 ? d - 1 : d;
+}
+__device__ __forceinline__ int on_boundary(const double* k, int n, double x, int i, double rel, double abs_) {
+  if (i + 2 < n && approx_eq(k[i + 1], x, rel, abs_)) return 1;  // trellis_poly.hpp:75-81
+  if (i > 0 && approx_eq(k[i], x, rel, abs_)) return -1;
+  return 0;
+}
+__device__ __forceinline__ bool sub_ok(const TrellisDev& t, const int* sub) {
+  for (int d = 0; d < 3; ++d)
+    if (sub[d] < 0 || sub[d] >= t.n_knots[d] - 1) return false;
+  const int n0 = t.n_knots[0] - 1, n1 = t.n_knots[1] - 1;
+  uint8_t ty = t.node_type[sub[0] + n0 * (sub[1] + n1 * sub[2])];
+  return !(ty == B200_NODE_NULL || ty == B200_NODE_ASSUMED_NULL || ty == B200_NODE_FOUND_NULL);
+}
+
+__device__ __forceinline__ double orient3d_plain(const double* a, const double* b, const double* c, const double* d) {
+  // geometry.hpp:130-135 with bare-array dot/cross: (a-d).((b-d)x(c-d))
+  double u0 = a[0] - d[0], u1 = a[1] - d[1], u2 = a[2] - d[2];
+  double v0 = b[0] - d[0], v1 = b[1] - d[1], v2 = b[2] - d[2];
+  double w0 = c[0] - d[0], w1 = c[1] - d[1], w2 = c[2] - d[2];
+  double c0 = v1 * w2 - v2 * w1;
+  double c1 = v2 * w0 - v0 * w2;
+  double c2 = v0 * w1 - v1 * w0;
+  return ((0.0 + u0 * c0) + u1 * c1) + u2 * c2;
+}
+
+// weights of x in tetrahedron tp (packed), tetrahedra_contains without the shortcut (trellis_node.hpp:326-338)
+__device__ __forceinline__ double tet_weights(const double* tp, const double* x, double* w, double rel, double abs_) {
+  const double* p0 = tp + 4;
+  const double* p1 = tp + 7;
+  const double* p2 = tp + 10;
+  const double* p3 = tp + 13;
+  const double vol6 = tp[16];
+  w[0] = orient3d_plain(x, p1, p2, p3) / vol6;
+  w[1] = orient3d_plain(p0, x, p2, p3) / vol6;
+  w[2] = orient3d_plain(p0, p1, x, p3) / vol6;
+  w[3] = orient3d_plain(p0, p1, p2, x) / vol6;
+  bool neg = false;
+  for (int j = 0; j < 4; ++j) neg |= (w[j] < 0.0 && !approx_eq(w[j], 0.0, rel, abs_));
+  if (neg) return fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+  return 0.0;
+}
+
+struct Emit {
+  int n;
+  uint32_t v[8];
+  double w[8];
+  uint64_t slots;
+};
+
+__device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const TrellisDev& t, const double* knots, const double* x,
+                                                   Emit& e, uint32_t& cell, int& tet) {
+  uint32_t st = 0;
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  cell = 0xffffffffu;
+  int sub[3];
+  for (int d = 0; d < 3; ++d) sub[d] = find_bin(knots + t.knot_offset[d], t.n_knots[d], x[d]);
+  bool bad = !sub_ok(t, sub);
+  if (bad) {  // trellis_poly.hpp:391-424
+    int close[3], num_close = 0, ns[3] = {sub[0], sub[1], sub[2]};
+    for (int i = 0; i < 3; ++i) {
+      close[i] = on_boundary(knots + t.knot_offset[i], t.n_knots[i], x[i], sub[i], bz.def_rel, bz.def_abs);
+      num_close += close[i] != 0;
+    }
+    if (num_close > 0)
+      for (int i = 0; i < 3 && bad; ++i)
+        if (close[i]) {
+          ns[0] = sub[0]; ns[1] = sub[1]; ns[2] = sub[2];
+          ns[i] += close[i];
+          bad = !sub_ok(t, ns);
+        }
+    if (bad && num_close > 1)
+      for (int i = 0; i < 3 && bad; ++i)
+        if (close[i])
+          for (int j = 0; j < 3 && bad; ++j)
+            if (close[j]) {
+              ns[0] = sub[0]; ns[1] = sub[1]; ns[2] = sub[2];
+              ns[i] += close[i];
+              ns[j] += close[j];
+              bad = !sub_ok(t, ns);
+            }
+    if (bad && num_close > 2) {
+      for (int i = 0; i < 3; ++i) ns[i] = sub[i] + close[i];
+      bad = !sub_ok(t, ns);
+    }
+    if (bad) return st | B200_ST_NOT_FOUND;  // reference: null-node access -> std::logic_error
+    sub[0] = ns[0]; sub[1] = ns[1]; sub[2] = ns[2];
+    st |= B200_ST_NEIGHBOUR;
+  }
+  const int n0 = t.n_knots[0] - 1, n1 = t.n_knots[1] - 1;
+  cell = (uint32_t)(sub[0] + n0 * (sub[1] + n1 * sub[2]));
+  const uint32_t payload = t.node_index[cell];
+  if (t.node_type[cell] == B200_NODE_CUBE) {
+    // CubeNode::indices_weights (trellis_node.hpp:130-149)
+    const double* cp = t.cube_pack + 24 * (size_t)payload;
+    const uint32_t* vi = t.cube_vertices + 8 * (size_t)payload;
+    double c[24];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      double2 v = reinterpret_cast<const double2*>(cp)[i];
+      c[2 * i] = v.x;
+      c[2 * i + 1] = v.y;
+    }
+    const double vol = (fabs(c[0] - c[21]) * fabs(c[1] - c[22])) * fabs(c[2] - c[23]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double w = (fabs(x[0] - c[3 * i]) * fabs(x[1] - c[3 * i + 1])) * fabs(x[2] - c[3 * i + 2]);
+      w = w / vol;
+      if (!approx_eq(w, 0.0, bz.def_rel, bz.def_abs) && w > 0.0) {
+        e.v[e.n] = vi[7 - i];
+        e.w[e.n] = w;
+        e.slots |= (uint64_t)(7 - i) << (8 * e.n);
+        ++e.n;
+      }
+    }
+  } else {
+    // PolyNode::indices_weights (trellis_node.hpp:273-308), should_contain == true
+    const uint32_t t0 = t.poly_offsets[payload], t1 = t.poly_offsets[payload + 1];
+    double w[4];
+    double best = 0.0;
+    uint32_t best_at = t0;
+    int found = -1;
+    for (uint32_t k = t0; k < t1; ++k) {
+      const double* tp = t.tet_pack + (size_t)TET_PACK * k;
+      double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+      double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+      double v0 = c01.x - x[0], v1 = c01.y - x[1], v2 = c23.x - x[2];
+      double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
+      double mn;
+      if (d2 < c23.y || approx_eq(d2, c23.y, bz.def_rel, bz.def_abs))
+        mn = tet_weights(tp, x, w, bz.def_rel, bz.def_abs);
+      else
+        mn = -d2;
+      if (mn >= 0.0) {
+        found = (int)k;
+        break;
+      }
+      if (k == t0 || mn > best) {
+        best = mn;
+        best_at = k;
+      }
+    }
+    if (found < 0) {
+      if (t1 == t0) return st | B200_ST_NOT_FOUND;
+      st |= B200_ST_FALLBACK_TET;  // trellis_node.hpp:295-306
+      found = (int)best_at;
+      tet_weights(t.tet_pack + (size_t)TET_PACK * best_at, x, w, bz.def_rel, bz.def_abs);
+    }
+    tet = found;
+    const uint32_t* vi = t.tet_vertices + 4 * (size_t)found;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (!approx_eq(w[j], 0.0, bz.def_rel, bz.def_abs)) {
+        e.v[e.n] = vi[j];
+        e.w[e.n] = w[j];
+        e.slots |= (uint64_t)j << (8 * e.n);
+        ++e.n;
+      }
+  }
+  if (e.n < 1) st |= B200_ST_NOT_FOUND;
+  return st;
+}
+
+// mode bits
+constexpr uint32_t MODE_NO_MOVE = 1u;   // skip moveinto/ir_moveinto (do_not_move_points)
+constexpr uint32_t MODE_IR = 2u;        // ir_moveinto (wedge rotation) rather than moveinto
+constexpr uint32_t MODE_NO_LOCATE = 4u; // moveinto only (b200_moveinto)
+
+__global__ void __launch_bounds__(128)
+k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict__ Q, size_t n, uint32_t mode,
+         double eps_w, double eps_o, LocateOut out, unsigned long long* __restrict__ fail_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BZDev& bz = *reinterpret_cast<BZDev*>(smem_raw);
+  double* knots = reinterpret_cast<double*>(smem_raw + ((sizeof(BZDev) + 15) / 16) * 16);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(bzg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&bz);
+    for (int i = threadIdx.x; i < (int)(sizeof(BZDev) / 4); i += blockDim.x) dst[i] = src[i];
+    const int nk = (mode & MODE_NO_LOCATE) ? 0 : tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2];
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) knots[i] = tr.knots[i];
+  }
+  __syncthreads();
+  unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double Qi[3] = {Q[3 * i], Q[3 * i + 1], Q[3 * i + 2]};
+    double q[3];
+    int tau[3] = {0, 0, 0};
+    int ridx = bz.identity_index, invridx = bz.identity_index;
+    uint32_t st = 0;
+    if (mode & MODE_NO_MOVE) {
+      q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
+    } else {
+      st = moveinto_one(bz, eps_w, eps_o, Qi, q, tau);
+      if ((mode & MODE_IR) && !inside_wedge(bz, q)) {
+        // bz_move.cpp:262-285: first operation (storage order) whose transpose moves q into the wedge
+        bool done = false;
+        for (int j = 0; j < bz.n_ops && !done; ++j) {
+          double qj[3];
+          matvec(qj, bz.Rt[j], q);
+          if (inside_wedge(bz, qj)) {
+            q[0] = qj[0]; q[1] = qj[1]; q[2] = qj[2];
+            invridx = j;
+            ridx = bz.inverse_index[j];
+            done = true;
+          }
+        }
+        if (!done) {
+          st |= B200_ST_OUTSIDE_WEDGE;
+          ridx = invridx = 0;
+        }
+      }
+    }
+    double x[3];
+    matvec(x, bz.to_xyz, q);  // array_lvec_methods.tpp:40-52
+    out.q_ir[3 * i] = q[0]; out.q_ir[3 * i + 1] = q[1]; out.q_ir[3 * i + 2] = q[2];
+    if (out.x_ir) { out.x_ir[3 * i] = x[0]; out.x_ir[3 * i + 1] = x[1]; out.x_ir[3 * i + 2] = x[2]; }
+    if (out.tau) { out.tau[3 * i] = tau[0]; out.tau[3 * i + 1] = tau[1]; out.tau[3 * i + 2] = tau[2]; }
+    out.ridx[i] = ridx;
+    out.invridx[i] = invridx;
+    if (!(mode & MODE_NO_LOCATE)) {
+      Emit e;
+      uint32_t cell;
+      int tet;
+      st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
+      out.cell[i] = cell;
+      out.tet[i] = tet;
+      out.n_vert[i] = e.n;
+      out.slots[i] = e.slots;
+      uint4* vo = reinterpret_cast<uint4*>(out.vertex + 8 * i);
+      double2* wo = reinterpret_cast<double2*>(out.weight + 8 * i);
+      uint32_t v[8];
+      double w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = j < e.n ? e.v[j] : 0xffffffffu;
+        w[j] = j < e.n ? e.w[j] : 0.0;
+      }
+      vo[0] = make_uint4(v[0], v[1], v[2], v[3]);
+      vo[1] = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wo[j] = make_double2(w[2 * j], w[2 * j + 1]);
+    }
+    out.status[i] = st;
+    f_bz += (st & B200_ST_OUTSIDE_BZ) != 0;
+    f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
+    f_find += (st & B200_ST_NOT_FOUND) != 0;
+  }
+  // fail_count[0..2]: outside first zone / outside wedge / not found (all zero on the normal path)
+  if (f_bz) atomicAdd(fail_count + 0, f_bz);
+  if (f_wedge) atomicAdd(fail_count + 1, f_wedge);
+  if (f_find) atomicAdd(fail_count + 2, f_find);
+}
+
+size_t locate_smem_bytes(const TrellisDev& tr, uint32_t mode) {
+  size_t nk = (mode & MODE_NO_LOCATE) ? 0 : (size_t)(tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2]);
+  return ((sizeof(BZDev) + 15) / 16) * 16 + nk * sizeof(double);
+}
+
+cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
+                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
+                          cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int threads = 128;
+  size_t smem = locate_smem_bytes(tr, mode);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  size_t want = (n + threads - 1) / threads;
+  size_t cap = (size_t)sm_count * 16;  // grid-stride: a multiple of the SM count
+  int blocks = (int)(want < cap ? want : cap);
+  k_locate<<<blocks, threads, smem, stream>>>(bzg, tr, Q, n, mode, eps_w, eps_o, out, fail_count);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

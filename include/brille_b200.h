@@ -189,6 +189,11 @@ int b200_interpolate_at(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t 
  * fills probe->q_ir, tau, ridx, invridx, status (x_ir if requested).  ir=0 selects moveinto.                */
 int b200_moveinto(b200_grid_t* grid, const double* Q, size_t nQ, int ir, b200_probe_t* probe);
 
+/* Page-locked host memory for Q / output buffers: with pinned buffers the chunked copies of the host-buffer
+ * entry points overlap the kernels (pageable memory works too but serialises the copies).                  */
+void* b200_alloc_pinned(size_t bytes);
+void b200_free_pinned(void* ptr);
+
 /* ---- introspection ------------------------------------------------------------------------------------- */
 const char* b200_last_error(void);
 int b200_abi_version(void);

@@ -1,0 +1,78 @@
+"""Shared comparison helpers of the parity tests."""
+import os
+
+import numpy as np
+
+from brille_b200 import tables as T
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+#: relative tolerance BASELINE.json's north_star states for eigenvalues / rotated eigenvectors
+RTOL = 1e-10
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    out = {"s": {}, "d": {}, "d2": {}}
+    rest = {}
+    for key in z.files:
+        parts = key.split(".")
+        if parts[0] in out and len(parts) > 1:
+            d = out[parts[0]]
+            for p in parts[1:-1]:
+                d = d.setdefault(p, {})
+            v = z[key]
+            if v.dtype.kind in "US" and v.ndim == 0:
+                v = str(v)
+            elif v.ndim == 0:
+                v = v.item()
+            d[parts[-1]] = v
+        else:
+            rest[key] = z[key]
+    return out["s"], out["d"], out["d2"], rest
+
+
+def rel_err(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    scale = max(np.abs(b).max(), 1e-300)
+    return float(np.abs(a - b).max() / scale)
+
+
+def assert_values_close(got, want, rtol=RTOL):
+    got = np.asarray(got).reshape(np.asarray(want).shape)
+    assert rel_err(got, want) <= rtol, f"relative error {rel_err(got, want):.3e} > {rtol}"
+
+
+def assert_decisions_equal(pr, ref, what="oracle"):
+    """tau, rotation indices, vertex lists and weights must be identical (bit-exact) except for points that sit within
+    brille's approx tolerance of a face, which may take either valid side (checked by the caller through the values)."""
+    n = len(ref["tau"])
+    assert np.array_equal(pr.tau[:n], ref["tau"]), f"{what}: tau differs"
+    assert np.array_equal(pr.ridx[:n], ref["ridx"]), f"{what}: Ridx differs"
+    assert np.array_equal(pr.invridx[:n], ref["invridx"]), f"{what}: invRidx differs"
+    assert np.array_equal(pr.q_ir[:n], ref["q_ir"]), f"{what}: q_ir not bit-identical"
+    if "n_vert" in ref:
+        assert np.array_equal(pr.n_vert[:n], ref["n_vert"]), f"{what}: vertex counts differ"
+        assert np.array_equal(pr.vertex[:n], ref["vertex"]), f"{what}: vertex lists differ"
+        assert np.array_equal(pr.weight[:n], ref["weight"]), f"{what}: weights not bit-identical"
+
+
+def ref_decisions(rest, prefix="ref_"):
+    out = {"tau": rest[prefix + "tau"], "q_ir": rest[prefix + "q_ir"]}
+    if prefix + "ridx" in rest:
+        out["ridx"] = rest[prefix + "ridx"]
+        out["invridx"] = rest[prefix + "invridx"]
+    out["n_vert"] = rest[prefix + "n_vert"]
+    out["vertex"] = rest[prefix + "vertex"]
+    out["weight"] = rest[prefix + "weight"]
+    return out
+
+
+def remove_mode_phase(vec, like):
+    """Multiply every (Q, mode) eigenvector by the phase that makes <like|vec> real (the freedom brille leaves)."""
+    vec = np.asarray(vec)
+    like = np.asarray(like).reshape(vec.shape)
+    ax = tuple(range(2, vec.ndim))
+    ph = np.exp(-1j * np.angle(np.sum(np.conj(like) * vec, axis=ax)))
+    return vec * ph.reshape(ph.shape + (1,) * (vec.ndim - 2))

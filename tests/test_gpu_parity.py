@@ -1,0 +1,149 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle, the golden fixtures and the reference."""
+import numpy as np
+import pytest
+
+import brille_b200
+from brille_b200 import tables as T
+from brille_b200 import workloads as W
+from oracle.oracle import Oracle
+from helpers import RTOL, assert_decisions_equal, assert_values_close, load_golden, ref_decisions, remove_mode_phase
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scalar_trellis.npz", "p63mmc_trellis.npz", "p1_trellis_dd.npz"]
+
+
+def probe_dict(pr):
+    return {"tau": pr.tau, "q_ir": pr.q_ir, "ridx": pr.ridx, "invridx": pr.invridx, "n_vert": pr.n_vert, "vertex": pr.vertex, "weight": pr.weight}
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_golden_fixtures(name):
+    s, d, _, rest = load_golden(name)
+    g = brille_b200.B200Grid(None, structure=s, data=d)
+    vals, vecs, pr = g.ir_interpolate_at(rest["Q"], probe=True)
+    assert_decisions_equal(pr, ref_decisions(rest), "cuda")
+    assert_values_close(vals, rest["ref_values"])
+    assert_values_close(vecs, rest["ref_vectors"])
+    assert g.launch_count >= 2
+    g.close()
+
+
+def test_interpolate_at_without_rotation():
+    s, d, _, rest = load_golden("p1_trellis_dd.npz")
+    g = brille_b200.B200Grid(None, structure=s, data=d)
+    vals, vecs, pr = g.interpolate_at(rest["Q"], probe=True)
+    assert np.array_equal(pr.tau, rest["ref0_tau"])
+    assert_values_close(vals, rest["ref0_values"])
+    assert_values_close(vecs, rest["ref0_vectors"])
+    q, tau = g.moveinto(rest["Q"])
+    assert np.array_equal(tau, rest["ref0_tau"]) and np.array_equal(q, rest["ref0_q_ir"])
+
+
+def test_nacl_gamma_reference_golden_vectors():
+    s, d, d2, rest = load_golden("nacl_gamma.npz")
+    g = brille_b200.B200Grid(None, structure=s, data=d)
+    vals, vecs = g.ir_interpolate_at(rest["Q"])
+    assert_values_close(vals, rest["ref_values"])
+    assert_values_close(vecs, rest["ref_vectors"])
+    assert np.allclose(vals.reshape(48, 24), rest["golden_euphonic_values"])
+    br_vec = np.einsum("ba,ijkb->ijka", rest["golden_basis_vectors"], vecs.reshape(48, 24, 8, 3))
+    eu = rest["golden_euphonic_vectors"]
+    assert np.allclose(remove_mode_phase(br_vec, eu), eu)
+    # Cartesian eigenvectors (LengthUnit::angstrom)
+    g._set_data(d2)
+    vals2, vecs2 = g.ir_interpolate_at(rest["Q"])
+    assert_values_close(vecs2, rest["ref2_vectors"])
+    assert np.allclose(remove_mode_phase(vecs2.reshape(48, 24, 8, 3), eu), eu)
+
+
+def test_unsupported_combinations_raise():
+    s, d, d2, rest = load_golden("nacl_gamma.npz")
+    for rl, lu in [(0, 1), (1, 0), (2, 2), (2, 4)]:
+        dd = dict(d)
+        dd["vectors_rotlike"], dd["vectors_lenunit"] = rl, lu
+        g = brille_b200.B200Grid(None, structure=s, data=dd)
+        with pytest.raises(RuntimeError):
+            g.ir_interpolate_at(rest["Q"])
+        g.close()
+
+
+def test_errors_and_edge_cases():
+    s, d, _, rest = load_golden("nacl_prim_trellis.npz")
+    g = brille_b200.B200Grid(None, structure=s)
+    with pytest.raises(RuntimeError, match="must be filled"):
+        g.ir_interpolate_at(rest["Q"])
+    g._set_data(d)
+    vals, vecs = g.ir_interpolate_at(np.zeros((0, 3)))
+    assert vals.shape[0] == 0 and vecs.shape[0] == 0
+    with pytest.raises(RuntimeError):
+        g.ir_interpolate_at(np.zeros((4, 2)))
+    # points far outside the gridded irreducible zone, not moved: all-or-nothing failure like the reference
+    with pytest.raises(RuntimeError, match="failed to find|null"):
+        g.ir_interpolate_at(np.full((3, 3), 7.3), do_not_move_points=True)
+    one = g.ir_interpolate_at(rest["Q"][:1])
+    assert one[0].shape[0] == 1
+
+
+@pytest.mark.parametrize("builder,n", [("C1", 200000), ("C2", 100000), ("C3", 100000)])
+def test_against_oracle_and_reference(host, bridge, builder, n):
+    wl = W.BUILDERS[builder](host)
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(n, 11)
+    vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rc, ov, ow, opr = orc.interpolate_at(Q)
+    assert rc == 0
+    assert_decisions_equal(pr, probe_dict(opr), "cuda vs oracle")
+    assert np.array_equal(pr.cell, opr.cell) and np.array_equal(pr.tet, opr.tet) and np.array_equal(pr.status, opr.status)
+    assert_values_close(vals, ov)
+    assert_values_close(vecs, ow)
+    # and the reference itself on a slice
+    m = min(n, 20000)
+    rv, rw = wl.grid.ir_interpolate_at(Q[:m], True, 8)
+    assert_values_close(vals[:m], rv)
+    assert_values_close(vecs[:m], rw)
+
+
+def test_sorted_permutations_against_reference(host, bridge):
+    wl = W.c3_p63mmc(host, density=150, seed=9)
+    wl.grid.sort()
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(20000, 12)
+    vals, vecs = g.ir_interpolate_at(Q)
+    rv, rw = wl.grid.ir_interpolate_at(Q, True, 8)
+    assert_values_close(vals, rv)
+    assert_values_close(vecs, rw)
+
+
+def rel_close(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_full_size_properties(host):
+    """C3 at 1e6 Q (too many for the scalar oracle): size-independent properties.
+    (1) every point is placed, Q == R^T-equivalent of q_ir + tau is implied by (3);
+    (2) the device-resident and the host-buffer entry points agree bit for bit, as do differently chunked calls;
+    (3) Q and Q+G (G a reciprocal lattice vector) give the same eigenvalues;
+    (4) eigenvalues are invariant under the point group: Q and R^T Q interpolate to the same values."""
+    import torch
+
+    wl = W.c3_p63mmc(host)
+    g = brille_b200.accelerate(wl.grid)
+    n = 1_000_000
+    Q = wl.make_q(n, 3)
+    vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+    assert (pr.status & 7).max() == 0
+    dQ = torch.from_numpy(Q).cuda()
+    dv, dw = g.ir_interpolate_at_device(dQ)
+    assert np.array_equal(dv.cpu().numpy(), vals) and np.array_equal(dw.cpu().numpy(), vecs)
+    v3, w3 = g.ir_interpolate_at(Q[: n // 3])
+    assert np.array_equal(v3, vals[: n // 3]) and np.array_equal(w3, vecs[: n // 3])
+    shift = np.random.default_rng(1).integers(-3, 4, (n, 3)).astype(float)
+    v2, _ = g.ir_interpolate_at(Q + shift)
+    assert rel_close(v2, vals) <= 1e-9
+    ops = np.asarray(wl.bz.lattice.pointgroup.W)
+    sub = Q[:50000]
+    for j in (1, 5, 11, 17):
+        vr, _ = g.ir_interpolate_at(sub @ ops[j].astype(float))  # rows are R^T q
+        assert rel_close(vr, vals[:50000]) <= 1e-9

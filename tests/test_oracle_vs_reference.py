@@ -1,0 +1,47 @@
+"""CPU: the oracle restatement pinned against the reference itself (oracle/_ref) on freshly built grids."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from brille_b200 import workloads as W
+
+
+def _compare(host, probe, bridge, wl, n, seed, sort=False):
+    g = wl.grid
+    if sort:
+        g.sort()
+    orc = Oracle(bridge.flatten(g), bridge.flatten_data(g))
+    Q = wl.make_q(n, seed)
+    rv, rw = g.ir_interpolate_at(Q, True, 4)
+    rc, ov, ow, pr = orc.interpolate_at(Q)
+    assert rc == 0
+    q, x, tau, r, ri = probe.ir_moveinto_idx(wl.bz, Q, 1)
+    assert np.array_equal(tau, pr.tau) and np.array_equal(r, pr.ridx) and np.array_equal(ri, pr.invridx)
+    assert np.array_equal(q, pr.q_ir) and np.array_equal(x, pr.x_ir)
+    cnt, idx, wgt = probe.indices_weights(g, x)
+    assert np.array_equal(cnt, pr.n_vert) and np.array_equal(idx, pr.vertex) and np.array_equal(wgt, pr.weight)
+    assert np.array_equal(rv.reshape(ov.shape), ov)
+    assert np.array_equal(rw.reshape(ow.shape), ow)
+
+
+def test_c1_fd3m_scalar(host, probe, bridge):
+    _compare(host, probe, bridge, W.c1_fd3m_scalar(host, density=500), 20000, 1)
+
+
+def test_c2_nacl(host, probe, bridge):
+    _compare(host, probe, bridge, W.c2_nacl(host, density=300), 20000, 2)
+
+
+def test_c3_p63mmc(host, probe, bridge):
+    _compare(host, probe, bridge, W.c3_p63mmc(host, density=500), 20000, 3)
+
+
+def test_c3_p63mmc_sorted(host, probe, bridge):
+    _compare(host, probe, bridge, W.c3_p63mmc(host, density=100, seed=5), 5000, 4, sort=True)
+
+
+def test_powder_q_large_tau(host, probe, bridge):
+    wl = W.c3_p63mmc(host, density=200)
+    B = np.asarray(bridge.flatten_bz(wl.bz)["to_xyz"])
+    wl.make_q = lambda n, seed: W.powder_q(B, n, seed)
+    _compare(host, probe, bridge, wl, 10000, 6)
