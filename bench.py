@@ -242,14 +242,15 @@ def run_ours(args):
 
     # per-kernel durations with CUDA events on the launching stream (separate pass so the events do not perturb `value`)
     grid.enable_timing(True)
-    k_loc, k_int = [], []
+    k_loc, k_int, k_sort = [], [], []
     for _ in range(3):
         step()
         k_loc.append(grid.kernel_ms("locate"))
+        k_sort.append(grid.kernel_ms("sort"))
         k_int.append(grid.kernel_ms("interpolate"))
     grid.enable_timing(False)
     torch.cuda.synchronize(dev)
-    loc_ms, int_ms = float(np.mean(k_loc)), float(np.mean(k_int))
+    loc_ms, int_ms, sort_ms = float(np.mean(k_loc)), float(np.mean(k_int)), float(np.mean(k_sort))
 
     # end to end through the host-buffer C-ABI call: pinned host Q in, pinned host results out, every step
     ne = E2E_NQ
@@ -291,9 +292,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * ne, "d2h_bytes_per_step": (bpq - 24) * ne,
                     "note": "b200_ir_interpolate_at with pinned host buffers; chunked H2D/kernels/D2H overlapped on two streams", "checksum": checksum},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_interp (interpolate+rotate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_interp_cell (cell-batched interpolate+rotate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_q": bpq,
-                         "kernel_ms": int_ms, "locate_kernel_ms": loc_ms,
+                         "kernel_ms": int_ms, "locate_kernel_ms": loc_ms, "bucket_sort_ms": sort_ms,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},
             "cpu_baseline": cpu,
         }

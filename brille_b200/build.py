@@ -16,6 +16,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path
 SOURCES = {
     "locate.cu": ["-fmad=false"],
     "interp.cu": [],
+    "cellinterp.cu": [],
     "capi.cu": [],
 }
 

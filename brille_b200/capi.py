@@ -31,6 +31,7 @@ EXPORTS = (
     "b200_grid_enable_timing",
     "b200_grid_kernel_ms",
     "b200_grid_row_bytes",
+    "b200_grid_set_option",
 )
 
 
@@ -83,6 +84,8 @@ def lib():
     L.b200_grid_enable_timing.argtypes = [vp, C.c_int]
     L.b200_grid_kernel_ms.restype = C.c_double
     L.b200_grid_kernel_ms.argtypes = [vp, C.c_char_p]
+    L.b200_grid_set_option.restype = C.c_int
+    L.b200_grid_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.b200_grid_row_bytes.restype = C.c_int
     L.b200_grid_row_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L

@@ -33,7 +33,36 @@ struct LocateIn {
   const uint32_t* node_index;
 };
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
+// cellinterp.cu
+struct CellItem { uint32_t key, start, len; };
+struct BucketDev {
+  uint32_t n_buckets, chunk;
+  const uint32_t* cell_count;
+  uint32_t* cell_offset;
+  CellItem* items;
+  uint32_t* n_items;
+  uint32_t* order;
+};
+struct CellArgs {
+  DataDev dd;
+  const uint32_t* cube_vertices;
+  const uint32_t* tet_vertices;
+  uint32_t n_cubes;
+  BucketDev bk;
+  const double* weight;
+  const double* q_ir;
+  const int32_t* ridx;
+  const int32_t* invridx;
+  double* vals_out;
+  double* vecs_out;
+  int ir;
+  uint32_t modes_per_pass;
+};
+bool cell_path_eligible(const DataDev& dd);
+uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget);
+cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count, cudaStream_t stream);
+cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
 }  // namespace b200
 
 using namespace b200;
@@ -76,6 +105,12 @@ struct Workspace {
   LocateOut lo{};
   double* x_ir = nullptr;
   int32_t* tau = nullptr;
+  // counting sort by cell (cellinterp.cu)
+  uint32_t n_buckets = 0, chunk = 0;
+  uint32_t* key = nullptr;
+  uint32_t* rank = nullptr;
+  uint32_t* cell_count = nullptr;
+  BucketDev bk{};
   std::vector<void*> ptrs;
   void release() {
     for (void* p : ptrs) cudaFree(p);
@@ -84,6 +119,9 @@ struct Workspace {
     lo = LocateOut{};
     x_ir = nullptr;
     tau = nullptr;
+    key = rank = cell_count = nullptr;
+    bk = BucketDev{};
+    n_buckets = chunk = 0;
   }
   template <class T>
   cudaError_t get(T** p, size_t count) {
@@ -93,8 +131,9 @@ struct Workspace {
     *p = static_cast<T*>(v);
     return e;
   }
-  cudaError_t ensure(size_t n) {
-    if (n <= capacity) return cudaSuccess;
+  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch) {
+    if (n <= capacity && nb == n_buckets && ch == chunk) return cudaSuccess;
+    if (n < capacity) n = capacity;
     release();
     cudaError_t e;
 #define WS(field, type, per) if ((e = get<type>(&field, n * (per))) != cudaSuccess) return e;
@@ -110,7 +149,19 @@ struct Workspace {
     WS(lo.weight, double, 8)
     WS(lo.slots, uint64_t, 1)
     WS(lo.status, uint32_t, 1)
+    WS(key, uint32_t, 1)
+    WS(rank, uint32_t, 1)
+    WS(bk.order, uint32_t, 1)
 #undef WS
+    if ((e = get<uint32_t>(&cell_count, nb)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.cell_offset, (size_t)nb + 1)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.n_items, 4)) != cudaSuccess) return e;
+    if ((e = get<CellItem>(&bk.items, (n + ch - 1) / ch + nb)) != cudaSuccess) return e;
+    bk.n_buckets = nb;
+    bk.chunk = ch;
+    bk.cell_count = cell_count;
+    n_buckets = nb;
+    chunk = ch;
     capacity = n;
     return cudaSuccess;
   }
@@ -141,9 +192,11 @@ struct b200_grid {
   Workspace ws;                 // device-pointer API
   unsigned long long* d_fail = nullptr;
   HostStage stage[2];
+  int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
+  uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
   uint64_t launches = 0;
   bool timing = false;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
 };
 
@@ -354,7 +407,7 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
         cudaHostAlloc(&g->stage[s].h_fail, 3 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
       rc = fail(B200_E_CUDA, "stream/counter creation failed");
   }
-  for (int i = 0; i < 3 && rc == B200_OK; ++i)
+  for (int i = 0; i < 4 && rc == B200_OK; ++i)
     if (cudaEventCreate(&g->ev[i]) != cudaSuccess) rc = fail(B200_E_CUDA, "event creation failed");
   if (rc != B200_OK) {
     b200_grid_destroy(g);
@@ -382,7 +435,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
     if (h.h_fail) cudaFreeHost(h.h_fail);
     if (h.stream) cudaStreamDestroy(h.stream);
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;
 }
@@ -484,24 +537,66 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
                    bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
-  CU(ws.ensure(n));
+  const uint32_t nb = g->tr.n_cubes + g->tr.n_tets + 1;
+  CU(ws.ensure(n, nb, g->chunk));
   CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
+  // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
+  bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
+  if (cell && g->interp_path == 0 && n < 4 * (size_t)nb) cell = false;
+  uint32_t mpp = 0;
+  if (cell) {
+    mpp = cell_modes_per_pass(g->dd, g->chunk, 100 * 1024);
+    if (mpp == 0) cell = false;
+  }
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
   lo.tau = ws.tau;
+  if (cell) {
+    lo.key = ws.key;
+    lo.rank = ws.rank;
+    lo.cell_count = ws.cell_count;
+    CU(cudaMemsetAsync(ws.cell_count, 0, nb * sizeof(uint32_t), stream));
+  }
   if (g->timing) cudaEventRecord(g->ev[0], stream);
   CU(launch_locate(g->d_bz, g->tr, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
   g->launches += 1;
   if (g->timing) cudaEventRecord(g->ev[1], stream);
-  if (interp) {
-    CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream));
-    g->launches += 1;
+  if (interp && cell) {
+    CU(launch_bucket_sort(ws.bk, ws.key, ws.rank, n, g->sm_count, stream));
+    g->launches += 2;
     if (g->timing) cudaEventRecord(g->ev[2], stream);
+    CellArgs a{};
+    a.dd = g->dd;
+    a.cube_vertices = g->tr.cube_vertices;
+    a.tet_vertices = g->tr.tet_vertices;
+    a.n_cubes = g->tr.n_cubes;
+    a.bk = ws.bk;
+    a.weight = lo.weight;
+    a.q_ir = lo.q_ir;
+    a.ridx = lo.ridx;
+    a.invridx = lo.invridx;
+    a.vals_out = dvals;
+    a.vecs_out = dvecs;
+    a.ir = ir;
+    a.modes_per_pass = mpp;
+    CU(launch_interp_cell(a, n, stream));
+    // points that are not generic members of their cell (and failed points): general kernel over the last bucket
+    CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, ws.bk.order, ws.bk.n_items));
+    g->launches += 2;
+    if (g->timing) cudaEventRecord(g->ev[3], stream);
+  } else if (interp) {
+    if (g->timing) cudaEventRecord(g->ev[2], stream);
+    CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, nullptr, nullptr));
+    g->launches += 1;
+    if (g->timing) cudaEventRecord(g->ev[3], stream);
   }
   if (g->timing) {
-    cudaEventSynchronize(interp ? g->ev[2] : g->ev[1]);
+    cudaEventSynchronize(interp ? g->ev[3] : g->ev[1]);
     note_time(g, "locate", g->ev[0], g->ev[1]);
-    if (interp) note_time(g, "interpolate", g->ev[1], g->ev[2]);
+    if (interp) {
+      note_time(g, "sort", g->ev[1], g->ev[2]);
+      note_time(g, "interpolate", g->ev[2], g->ev[3]);
+    }
   }
   return B200_OK;
 }
@@ -688,6 +783,20 @@ extern "C" double b200_grid_kernel_ms(const b200_grid_t* g, const char* name) {
   auto it = g->kernel_ms.find(name);
   if (it == g->kernel_ms.end() || it->second.second == 0) return -1.0;
   return it->second.first / it->second.second;
+}
+extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double value) {
+  if (!g || !name) return fail(B200_E_INVALID, "NULL argument");
+  const std::string n(name);
+  if (n == "interp_path") {
+    if (value < 0 || value > 2) return fail(B200_E_INVALID, "interp_path must be 0 (auto), 1 (general) or 2 (cell-batched)");
+    g->interp_path = (int)value;
+  } else if (n == "chunk") {
+    if (value < 32 || value > 1024) return fail(B200_E_INVALID, "chunk must be in [32, 1024]");
+    g->chunk = (uint32_t)value;
+  } else {
+    return fail(B200_E_INVALID, "unknown option " + n);
+  }
+  return B200_OK;
 }
 extern "C" int b200_grid_row_bytes(const b200_grid_t* g, size_t* v, size_t* w) {
   if (!g || !g->has_data) return fail(B200_E_NODATA, "The interpolation data must be filled before interpolating.");

@@ -1,0 +1,353 @@
+// cellinterp.cu -- the cell-batched interpolation stage (the fast path of stage 2).
+//
+// Same arithmetic as interp.cu (interpolator_at.tpp:91-127 + interpolator_gamma.tpp:49-139), re-organised around the
+// observation that everything expensive in the reference's per-Q loop depends only on the CELL the point fell into:
+//   * which 4 (tetrahedron) or 8 (cube) vertex rows are gathered                       trellis_node.hpp:130-149,273-308
+//   * the permutation of the modes of every vertex relative to the pivot vertex          interpolatordual.hpp:374-382
+//   * the phase e^{-i arg<d_pivot|d_v>} that aligns every vertex' eigenvector to the pivot's   utilities.tpp:567-579
+// The locate stage therefore buckets the points by cell (counting sort: k_locate counts, k_bucket_scan scans,
+// k_bucket_scatter scatters).  One CTA then stages the cell's vertex rows ONCE in shared memory -- already permuted and
+// pre-multiplied by their alignment phase -- and streams up to `chunk` points of that cell through them: per point only
+// the barycentric/trilinear weights, the rotation matrix index and the per-atom Gamma phase differ.  The vertex table
+// is read from L2 once per (cell, chunk) instead of once per point, and the per-point work drops to
+// 2*n_v real-complex FMAs per element plus the 3x3 rotation.
+//
+// Points whose pivot is not the cell's first corner (some weight ~ 0: on a face/edge/vertex of the cell) and failed
+// points go to a last bucket that is processed by the general kernel of interp.cu.
+#include "device_tables.cuh"
+#include "brille_b200.h"
+
+namespace b200 {
+
+struct CellItem {
+  uint32_t key;    // bucket (cube c -> c, tetrahedron t -> n_cubes + t)
+  uint32_t start;  // first position in `order`
+  uint32_t len;    // number of points (<= chunk)
+};
+
+struct BucketDev {
+  uint32_t n_buckets;          // n_cubes + n_tets + 1
+  uint32_t chunk;              // points per CTA item
+  const uint32_t* cell_count;  // (n_buckets)
+  uint32_t* cell_offset;       // (n_buckets + 1) exclusive scan of cell_count
+  CellItem* items;             // (max_items)
+  uint32_t* n_items;           // [0] number of items, [1] start of the last (general) bucket, [2] its population
+  uint32_t* order;             // (n) point indices sorted by bucket
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// counting sort, part 2: single-CTA exclusive scan of the bucket populations + work-item table
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
+  __shared__ uint32_t s_pts[1024], s_its[1024];
+  __shared__ uint32_t carry_pts, carry_its;
+  const int tid = threadIdx.x;
+  if (tid == 0) carry_pts = carry_its = 0;
+  __syncthreads();
+  const uint32_t nb = b.n_buckets, last = nb - 1;
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t c = i < nb ? b.cell_count[i] : 0u;
+    const uint32_t it = (i < last) ? (c + b.chunk - 1) / b.chunk : 0u;  // the last bucket produces no cell items
+    s_pts[tid] = c;
+    s_its[tid] = it;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+      uint32_t a = tid >= off ? s_pts[tid - off] : 0u, d = tid >= off ? s_its[tid - off] : 0u;
+      __syncthreads();
+      s_pts[tid] += a;
+      s_its[tid] += d;
+      __syncthreads();
+    }
+    const uint32_t p0 = carry_pts + s_pts[tid] - c, i0 = carry_its + s_its[tid] - it;
+    if (i < nb) {
+      b.cell_offset[i] = p0;
+      for (uint32_t k = 0; k < it; ++k) {
+        CellItem ci;
+        ci.key = i;
+        ci.start = p0 + k * b.chunk;
+        ci.len = min(b.chunk, c - k * b.chunk);
+        b.items[i0 + k] = ci;
+      }
+      if (i == last) {
+        b.n_items[1] = p0;
+        b.n_items[2] = c;
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) {
+      carry_pts += s_pts[1023];
+      carry_its += s_its[1023];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    b.cell_offset[nb] = carry_pts;
+    b.n_items[0] = carry_its;
+  }
+}
+
+// counting sort, part 3
+__global__ void __launch_bounds__(256)
+k_bucket_scatter(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_offset,
+                 uint32_t* __restrict__ order, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    order[cell_offset[key[i]] + rank[i]] = (uint32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the cell kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct CellArgs {
+  DataDev dd;
+  const uint32_t* cube_vertices;
+  const uint32_t* tet_vertices;
+  uint32_t n_cubes;
+  BucketDev bk;
+  const double* weight;    // (n,8)
+  const double* q_ir;      // (n,3)
+  const int32_t* ridx;     // (n)
+  const int32_t* invridx;  // (n)
+  double* vals_out;
+  double* vecs_out;
+  int ir;
+  uint32_t modes_per_pass;  // modes staged per pass (<= branches)
+};
+
+struct cplx2 { double re, im; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dynamic shared memory carve-up (all offsets 16-byte aligned)
+struct SmemPlan {
+  size_t D, V, W, PH, RS, F0, QI, RI, total;
+};
+__host__ __device__ inline SmemPlan plan_smem(uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
+  SmemPlan p;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+  p.D = take((size_t)8 * mpp * S * 16);
+  p.V = take((size_t)8 * mpp * no0v * 8);
+  p.W = take((size_t)chunk * 8 * 8);
+  p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
+  p.RS = take((size_t)G * 9 * 8);
+  p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
+  p.QI = take((size_t)chunk * 4);
+  p.RI = take((size_t)chunk * 4);
+  p.total = o;
+  return p;
+}
+
+__global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (blockIdx.x >= a.bk.n_items[0]) return;
+  const CellItem item = a.bk.items[blockIdx.x];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const InterpDev& vals = a.dd.values;
+  const InterpDev& vecs = a.dd.vectors;
+  const uint32_t M = vecs.branches, S = vecs.span, NAT = vecs.no1, no0v = vals.span, G = a.dd.n_ops;
+  const int kind = a.ir ? vecs.rot_kind : -1;
+  const bool gamma = kind >= 3;
+  const bool is_cube = item.key < a.n_cubes;
+  const int NV = is_cube ? 8 : 4;
+  const uint32_t cellidx = is_cube ? item.key : item.key - a.n_cubes;
+  const uint32_t mpp = a.modes_per_pass;
+  const SmemPlan pl = plan_smem(mpp, S, no0v, a.bk.chunk, NAT, G, gamma);
+  double2* D = reinterpret_cast<double2*>(smem + pl.D);
+  double* V = reinterpret_cast<double*>(smem + pl.V);
+  double* W = reinterpret_cast<double*>(smem + pl.W);
+  double2* PH = reinterpret_cast<double2*>(smem + pl.PH);
+  double* RS = reinterpret_cast<double*>(smem + pl.RS);
+  uint32_t* F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
+  uint32_t* QI = reinterpret_cast<uint32_t*>(smem + pl.QI);
+  uint32_t* RI = reinterpret_cast<uint32_t*>(smem + pl.RI);
+  __shared__ uint32_t s_vtx[8], s_prow[8];
+
+  // ---- per-cell constants: vertices in emission order, permutation rows relative to the pivot ------------------
+  if (tid < NV) {
+    // emission order: cube corner 7-j (trellis_node.hpp:143-147), tetrahedron corner j (:285-287)
+    const uint32_t slot = is_cube ? 7u - tid : (uint32_t)tid;
+    s_vtx[tid] = is_cube ? a.cube_vertices[(size_t)cellidx * 8 + slot] : a.tet_vertices[(size_t)cellidx * 4 + slot];
+    uint32_t prow = 0;
+    if (a.dd.n_perm_rows > 1) {
+      const uint32_t pivot = is_cube ? 7u : 0u;
+      prow = is_cube ? a.dd.cube_perm[(size_t)cellidx * 64 + pivot * 8 + slot] : a.dd.tet_perm[(size_t)cellidx * 16 + pivot * 4 + slot];
+    }
+    s_prow[tid] = prow;
+  }
+  // rotation matrices used by this call, and the atom permutation table
+  {
+    const double* src = nullptr;
+    switch (kind) {
+      case 0: src = a.dd.rot_int; break;              // R
+      case 1: src = a.dd.rot_int + 9 * (size_t)G; break;  // R^T
+      case 2: src = a.dd.rot_int; break;              // R^-1 = R[invridx]
+      case 3: src = a.dd.rot_int; break;
+      case 4: src = a.dd.rot_cart; break;
+      default: break;
+    }
+    if (src)
+      for (uint32_t i = tid; i < G * 9; i += nthr) RS[i] = src[i];
+    if (gamma)
+      for (uint32_t i = tid; i < NAT * G; i += nthr) F0[i] = a.dd.gamma_F0[i];
+  }
+  // ---- per-point constants ------------------------------------------------------------------------------------------
+  for (uint32_t t = tid; t < item.len; t += nthr) {
+    const uint32_t q = a.bk.order[item.start + t];
+    QI[t] = q;
+    const int r = a.ridx[q], ri = a.invridx[q];
+    // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+    RI[t] = (uint32_t)((kind == 0 || kind == 1) ? r : ri) | ((uint32_t)r << 16);
+    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)q);
+    double2* ws = reinterpret_cast<double2*>(W + 8 * (size_t)t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ws[j] = wp[j];
+  }
+  __syncthreads();
+  if (gamma) {
+    // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
+    for (uint32_t p = tid; p < item.len * NAT; p += nthr) {
+      const uint32_t t = p / NAT, k = p - t * NAT;
+      const uint32_t q = QI[t], ri = RI[t] & 0xffffu;
+      const double* gv = a.dd.gamma_vectors + 3 * (size_t)a.dd.gamma_vidx[(size_t)k * G + ri];
+      const double dot = ((0.0 + a.q_ir[3 * (size_t)q] * gv[0]) + a.q_ir[3 * (size_t)q + 1] * gv[1]) + a.q_ir[3 * (size_t)q + 2] * gv[2];
+      double sn, cs;
+      sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
+      PH[p] = make_double2(cs, sn);
+    }
+  }
+
+  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
+  for (uint32_t b0 = 0; b0 < M; b0 += mpp) {
+    const uint32_t mb = min(mpp, M - b0);
+    __syncthreads();  // previous pass finished reading D / V
+    // ---- stage the permuted vertex rows ---------------------------------------------------------------------------
+    for (uint32_t idx = tid; idx < (uint32_t)NV * mb * S; idx += nthr) {
+      const uint32_t i = idx / (mb * S), r = idx - i * (mb * S), b = r / S, e = r - b * S;
+      const uint32_t pb = a.dd.n_perm_rows > 1 ? a.dd.perm_rows[(size_t)s_prow[i] * M + b0 + b] : b0 + b;
+      D[((size_t)i * mpp + b) * S + e] = reinterpret_cast<const double2*>(vecs.data)[(size_t)s_vtx[i] * wrow + (size_t)pb * S + e];
+    }
+    for (uint32_t idx = tid; idx < (uint32_t)NV * mb * no0v; idx += nthr) {
+      const uint32_t i = idx / (mb * no0v), r = idx - i * (mb * no0v), b = r / no0v, e = r - b * no0v;
+      const uint32_t pb = a.dd.n_perm_rows > 1 ? a.dd.perm_rows[(size_t)s_prow[i] * M + b0 + b] : b0 + b;
+      V[((size_t)i * mpp + b) * no0v + e] = vals.data[(size_t)s_vtx[i] * vrow + (size_t)pb * no0v + e];
+    }
+    __syncthreads();
+    // ---- align every vertex' eigenvector to the pivot's: one warp per (vertex, mode)  utilities.tpp:567-579 ----------
+    for (uint32_t pr = warp; pr < (uint32_t)(NV - 1) * mb; pr += nwarp) {
+      const uint32_t i = 1 + pr / mb, b = pr % mb;
+      const double2* d0 = D + (size_t)b * S;  // pivot (emission index 0) keeps its own branch
+      double2* dx = D + ((size_t)i * mpp + b) * S;
+      double re = 0.0, im = 0.0;
+      for (uint32_t s = lane; s < S; s += 32) {
+        const double2 p0 = d0[s], x = dx[s];
+        re += p0.x * x.x + p0.y * x.y;
+        im += p0.x * x.y - p0.y * x.x;
+      }
+      re = warp_sum(re);
+      im = warp_sum(im);
+      double sn, cs;
+      sincos(-atan2(im, re), &sn, &cs);
+      for (uint32_t s = lane; s < S; s += 32) {
+        const double2 x = dx[s];
+        dx[s] = make_double2(cs * x.x - sn * x.y, cs * x.y + sn * x.x);
+      }
+    }
+    __syncthreads();
+    // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
+    for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
+      const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
+      const double* w = W + 8 * (size_t)t;
+      double acc = 0.0;
+      for (int i = 0; i < NV; ++i) acc += w[i] * V[(size_t)i * mpp * no0v + r];
+      a.vals_out[(size_t)QI[t] * vrow + (size_t)b0 * no0v + r] = acc;
+    }
+    // ---- eigenvectors: weighted sum of pre-phased rows, rotation, atom permutation, Gamma phase ----------------------
+    const uint32_t per_q = mb * NAT;
+    for (uint32_t p = tid; p < item.len * per_q; p += nthr) {
+      const uint32_t t = p / per_q, r = p - t * per_q, b = r / NAT, k = r - b * NAT;
+      const double* w = W + 8 * (size_t)t;
+      const double2* src = D + (size_t)b * S + 3 * k;
+      double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0, acc2 = acc0;
+      for (int i = 0; i < NV; ++i) {
+        const double wi = w[i];
+        const double2* x = src + (size_t)i * mpp * S;
+        const double2 x0 = x[0], x1 = x[1], x2 = x[2];
+        acc0.x += wi * x0.x; acc0.y += wi * x0.y;
+        acc1.x += wi * x1.x; acc1.y += wi * x1.y;
+        acc2.x += wi * x2.x; acc2.y += wi * x2.y;
+      }
+      uint32_t dest = k;
+      double2 o0 = acc0, o1 = acc1, o2 = acc2;
+      if (kind >= 0) {
+        const uint32_t ri = RI[t] & 0xffffu;
+        const double* R = RS + 9 * ri;
+        o0.x = (R[0] * acc0.x + R[1] * acc1.x) + R[2] * acc2.x;  o0.y = (R[0] * acc0.y + R[1] * acc1.y) + R[2] * acc2.y;
+        o1.x = (R[3] * acc0.x + R[4] * acc1.x) + R[5] * acc2.x;  o1.y = (R[3] * acc0.y + R[4] * acc1.y) + R[5] * acc2.y;
+        o2.x = (R[6] * acc0.x + R[7] * acc1.x) + R[8] * acc2.x;  o2.y = (R[6] * acc0.y + R[7] * acc1.y) + R[8] * acc2.y;
+        if (gamma) {
+          dest = F0[k * G + ri];
+          const double2 ph = PH[(size_t)t * NAT + k];
+          double2 t0 = o0, t1 = o1, t2 = o2;
+          o0 = make_double2(ph.x * t0.x - ph.y * t0.y, ph.x * t0.y + ph.y * t0.x);
+          o1 = make_double2(ph.x * t1.x - ph.y * t1.y, ph.x * t1.y + ph.y * t1.x);
+          o2 = make_double2(ph.x * t2.x - ph.y * t2.y, ph.x * t2.y + ph.y * t2.x);
+        } else if (kind == 2) {
+          const double det = a.dd.rot_det[RI[t] >> 16];
+          o0.x *= det; o0.y *= det; o1.x *= det; o1.y *= det; o2.x *= det; o2.y *= det;
+        }
+      }
+      double2* out = reinterpret_cast<double2*>(a.vecs_out) + (size_t)QI[t] * wrow + (size_t)(b0 + b) * S + 3 * dest;
+      out[0] = o0;
+      out[1] = o1;
+      out[2] = o2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+bool cell_path_eligible(const DataDev& dd) {
+  const InterpDev& v = dd.values;
+  const InterpDev& w = dd.vectors;
+  return !v.is_complex && v.no1 == 0 && v.no2 == 0 && v.no0 >= 1 && w.is_complex && w.no0 == 0 && w.no2 == 0 && w.no1 >= 1 &&
+         v.rot_kind == -1;
+}
+
+// modes staged per pass so that the carve-up fits `budget` bytes of dynamic shared memory
+uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget) {
+  const bool gamma = dd.vectors.rot_kind >= 3;
+  for (uint32_t mpp = dd.vectors.branches; mpp >= 1; --mpp)
+    if (plan_smem(mpp, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) return mpp;
+  return 0;
+}
+
+cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
+                               cudaStream_t stream) {
+  k_bucket_scan<<<1, 1024, 0, stream>>>(bk);
+  size_t want = (n + 255) / 256, cap = (size_t)sm_count * 16;
+  k_bucket_scatter<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(key, rank, bk.cell_offset, bk.order, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream) {
+  const DataDev& dd = args.dd;
+  const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
+  const size_t smem = plan_smem(args.modes_per_pass, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_interp_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const size_t max_items = (n + args.bk.chunk - 1) / args.bk.chunk + (args.bk.n_buckets - 1);
+  k_interp_cell<<<(unsigned)max_items, 256, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

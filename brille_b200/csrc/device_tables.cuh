@@ -63,6 +63,11 @@ struct LocateOut {
   double* weight;    // (n,8)
   uint64_t* slots;   // (n) 8 packed corner slots (emission order), byte j = slot of emitted vertex j
   uint32_t* status;  // (n)
+  // bucketing for the cell-batched interpolation kernel (all optional: NULL => not bucketed)
+  uint32_t* key;         // (n) bucket of the point: cube c -> c, tetrahedron t -> n_cubes + t, everything that is not a
+                         //     full generic cell (some weight ~ 0, failed points) -> n_cubes + n_tets
+  uint32_t* rank;        // (n) arrival order of the point inside its bucket
+  uint32_t* cell_count;  // (n_cubes + n_tets + 1) bucket populations, zeroed before the launch
 };
 
 struct InterpDev {

@@ -268,7 +268,12 @@ __device__ __forceinline__ Rot make_rot(const InterpDev& id, const DataDev& dd, 
 
 template <int LANES>
 __global__ void __launch_bounds__(256)
-k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_out, double* __restrict__ vecs_out) {
+k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_out, double* __restrict__ vecs_out,
+         const uint32_t* __restrict__ order, const uint32_t* __restrict__ segment) {
+  // list mode (order != NULL): only the points order[segment[1] .. segment[1]+segment[2]) are processed -- the last
+  // bucket of the counting sort in cellinterp.cu, whose population is only known on the device
+  if (order) n = segment[2];
+  if (n == 0) return;
   const uint32_t B = dd.values.branches;
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = LANES >= 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
@@ -283,7 +288,7 @@ k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_ou
     size_t u = group + it * n_groups;
     const bool live = u < units;
     if (!live) u = units - 1;
-    const size_t q = u / B;
+    const size_t q = order ? (size_t)order[segment[1] + u / B] : u / B;
     const uint32_t b = (uint32_t)(u % B);
     const uint32_t st = in.status[q];
     const bool failed = (st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND)) != 0;
@@ -341,29 +346,29 @@ k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_ou
 
 template <int LANES>
 static cudaError_t launch_lanes(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs,
-                                int sm_count, cudaStream_t stream) {
+                                int sm_count, cudaStream_t stream, const uint32_t* order, const uint32_t* segment) {
   const int threads = 256;
   const size_t units = n * (size_t)dd.values.branches;
   size_t want = (units * LANES + threads - 1) / threads;
-  size_t cap = (size_t)sm_count * 32;
+  size_t cap = (size_t)sm_count * (order ? 2 : 32);  // list mode: the segment is normally (almost) empty
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  k_interp<LANES><<<blocks, threads, 0, stream>>>(dd, in, n, ir, vals, vecs);
+  k_interp<LANES><<<blocks, threads, 0, stream>>>(dd, in, n, ir, vals, vecs, order, segment);
   return cudaGetLastError();
 }
 
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment) {
   if (n == 0) return cudaSuccess;
   // lanes per (Q, mode) unit: enough to cover the items of the widest segment of the vectors' mode
   uint32_t items = dd.vectors.no1 > dd.vectors.no2 ? dd.vectors.no1 : dd.vectors.no2;
   if (dd.vectors.no0 > items) items = dd.vectors.no0;
-  if (items <= 1) return launch_lanes<1>(dd, in, n, ir, vals, vecs, sm_count, stream);
-  if (items <= 2) return launch_lanes<2>(dd, in, n, ir, vals, vecs, sm_count, stream);
-  if (items <= 4) return launch_lanes<4>(dd, in, n, ir, vals, vecs, sm_count, stream);
-  if (items <= 8) return launch_lanes<8>(dd, in, n, ir, vals, vecs, sm_count, stream);
-  if (items <= 16) return launch_lanes<16>(dd, in, n, ir, vals, vecs, sm_count, stream);
-  return launch_lanes<32>(dd, in, n, ir, vals, vecs, sm_count, stream);
+  if (items <= 1) return launch_lanes<1>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  if (items <= 2) return launch_lanes<2>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  if (items <= 4) return launch_lanes<4>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  if (items <= 8) return launch_lanes<8>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  if (items <= 16) return launch_lanes<16>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  return launch_lanes<32>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
 }
 
 }  // namespace b200

@@ -395,11 +395,12 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
     if (out.tau) { out.tau[3 * i] = tau[0]; out.tau[3 * i + 1] = tau[1]; out.tau[3 * i + 2] = tau[2]; }
     out.ridx[i] = ridx;
     out.invridx[i] = invridx;
+    uint32_t cell = 0xffffffffu;
+    int tet = -1, n_emit = 0;
     if (!(mode & MODE_NO_LOCATE)) {
       Emit e;
-      uint32_t cell;
-      int tet;
       st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
+      n_emit = e.n;
       out.cell[i] = cell;
       out.tet[i] = tet;
       out.n_vert[i] = e.n;
@@ -419,6 +420,17 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
       for (int j = 0; j < 4; ++j) wo[j] = make_double2(w[2 * j], w[2 * j + 1]);
     }
     out.status[i] = st;
+    if (out.key) {
+      // bucket for the cell-batched interpolation: only "generic" points (every corner of the cell carries weight, i.e.
+      // the pivot is the cell's first emitted corner) share a bucket with their cell
+      uint32_t key = tr.n_cubes + tr.n_tets;
+      if (!(mode & MODE_NO_LOCATE) && !(st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND))) {
+        if (tet >= 0 && n_emit == 4) key = tr.n_cubes + (uint32_t)tet;
+        else if (tet < 0 && n_emit == 8) key = tr.node_index[cell];
+      }
+      out.key[i] = key;
+      out.rank[i] = atomicAdd(out.cell_count + key, 1u);
+    }
     f_bz += (st & B200_ST_OUTSIDE_BZ) != 0;
     f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
     f_find += (st & B200_ST_NOT_FOUND) != 0;

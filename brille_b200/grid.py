@@ -232,6 +232,10 @@ class B200Grid:
     def enable_timing(self, on=True):
         capi.check(capi.lib().b200_grid_enable_timing(self._handle, 1 if on else 0))
 
+    def set_option(self, name, value):
+        """``interp_path``: 0 auto, 1 general kernel, 2 cell-batched kernel; ``chunk``: points per CTA item."""
+        capi.check(capi.lib().b200_grid_set_option(self._handle, name.encode(), float(value)))
+
     def kernel_ms(self, name):
         return float(capi.lib().b200_grid_kernel_ms(self._handle, name.encode()))
 

@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Profiling target: a few device-resident steps of the bench workload (C3, 1e7 Q) for ncu.
+
+    ncu --set full --clock-control none --import-source on -k regex:k_interp -s 1 -c 1 -o gpurun_out/prof python profiles/prof_target.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import brille_b200  # noqa: E402
+from bench import NQ, Q_SEED, build_workload  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+nq = int(float(sys.argv[2])) if len(sys.argv) > 2 else NQ
+wl = build_workload()
+grid = brille_b200.accelerate(wl.grid)
+dQ = torch.from_numpy(wl.make_q(nq, Q_SEED)).cuda()
+vals = torch.empty((nq, wl.modes, 1), dtype=torch.float64, device="cuda")
+vecs = torch.empty((nq, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
+for _ in range(steps):
+    grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
+torch.cuda.synchronize()
+print("done", steps, nq)

@@ -17,10 +17,12 @@ def probe_dict(pr):
     return {"tau": pr.tau, "q_ir": pr.q_ir, "ridx": pr.ridx, "invridx": pr.invridx, "n_vert": pr.n_vert, "vertex": pr.vertex, "weight": pr.weight}
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
 @pytest.mark.parametrize("name", FIXTURES)
-def test_golden_fixtures(name):
+def test_golden_fixtures(name, path):
     s, d, _, rest = load_golden(name)
     g = brille_b200.B200Grid(None, structure=s, data=d)
+    g.set_option("interp_path", path)
     vals, vecs, pr = g.ir_interpolate_at(rest["Q"], probe=True)
     assert_decisions_equal(pr, ref_decisions(rest), "cuda")
     assert_values_close(vals, rest["ref_values"])
@@ -52,6 +54,7 @@ def test_nacl_gamma_reference_golden_vectors():
     assert np.allclose(remove_mode_phase(br_vec, eu), eu)
     # Cartesian eigenvectors (LengthUnit::angstrom)
     g._set_data(d2)
+    g.set_option("interp_path", 2)
     vals2, vecs2 = g.ir_interpolate_at(rest["Q"])
     assert_values_close(vecs2, rest["ref2_vectors"])
     assert np.allclose(remove_mode_phase(vecs2.reshape(48, 24, 8, 3), eu), eu)
@@ -85,10 +88,12 @@ def test_errors_and_edge_cases():
     assert one[0].shape[0] == 1
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
 @pytest.mark.parametrize("builder,n", [("C1", 200000), ("C2", 100000), ("C3", 100000)])
-def test_against_oracle_and_reference(host, bridge, builder, n):
+def test_against_oracle_and_reference(host, bridge, builder, n, path):
     wl = W.BUILDERS[builder](host)
     g = brille_b200.accelerate(wl.grid)
+    g.set_option("interp_path", path)
     Q = wl.make_q(n, 11)
     vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
     orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
@@ -105,10 +110,12 @@ def test_against_oracle_and_reference(host, bridge, builder, n):
     assert_values_close(vecs[:m], rw)
 
 
-def test_sorted_permutations_against_reference(host, bridge):
+@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+def test_sorted_permutations_against_reference(host, bridge, path):
     wl = W.c3_p63mmc(host, density=150, seed=9)
     wl.grid.sort()
     g = brille_b200.accelerate(wl.grid)
+    g.set_option("interp_path", path)
     Q = wl.make_q(20000, 12)
     vals, vecs = g.ir_interpolate_at(Q)
     rv, rw = wl.grid.ir_interpolate_at(Q, True, 8)
@@ -139,6 +146,10 @@ def test_full_size_properties(host):
     assert np.array_equal(dv.cpu().numpy(), vals) and np.array_equal(dw.cpu().numpy(), vecs)
     v3, w3 = g.ir_interpolate_at(Q[: n // 3])
     assert np.array_equal(v3, vals[: n // 3]) and np.array_equal(w3, vecs[: n // 3])
+    g.set_option("interp_path", 1)  # the general kernel and the cell-batched kernel agree to rounding
+    v1, w1 = g.ir_interpolate_at(Q[:200000])
+    assert rel_close(v1, vals[:200000]) <= 1e-12 and rel_close(w1, vecs[:200000]) <= 1e-12
+    g.set_option("interp_path", 0)
     shift = np.random.default_rng(1).integers(-3, 4, (n, 3)).astype(float)
     v2, _ = g.ir_interpolate_at(Q + shift)
     assert rel_close(v2, vals) <= 1e-9
