@@ -792,7 +792,7 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
     g->interp_path = (int)value;
   } else if (n == "chunk") {
     if (value < 32 || value > 1024) return fail(B200_E_INVALID, "chunk must be in [32, 1024]");
-    g->chunk = (uint32_t)value;
+    g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
   } else {
     return fail(B200_E_INVALID, "unknown option " + n);
   }

@@ -196,16 +196,51 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       for (uint32_t i = tid; i < NAT * G; i += nthr) F0[i] = a.dd.gamma_F0[i];
   }
   // ---- per-point constants ------------------------------------------------------------------------------------------
-  for (uint32_t t = tid; t < item.len; t += nthr) {
-    const uint32_t q = a.bk.order[item.start + t];
-    QI[t] = q;
-    const int r = a.ridx[q], ri = a.invridx[q];
-    // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
-    RI[t] = (uint32_t)((kind == 0 || kind == 1) ? r : ri) | ((uint32_t)r << 16);
-    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)q);
-    double2* ws = reinterpret_cast<double2*>(W + 8 * (size_t)t);
+  // The points of the chunk are re-ordered by the index of the rotation matrix they need (a counting sort over <= 48
+  // bins in shared memory), so that the TQ consecutive points a thread works on almost always share the matrix.
+  const uint32_t CH = a.bk.chunk;  // row length of the transposed weight array W[corner][point]
+  __shared__ uint32_t s_hist[64];
+  if (tid < 64) s_hist[tid] = 0;
+  for (uint32_t t = tid; t < (uint32_t)NV * CH; t += nthr) W[t] = 0.0;  // padding points carry zero weight
+  __syncthreads();
+  uint32_t my_q[4], my_ri[4], my_rank[4];  // chunk <= 1024 and 256 threads: at most 4 points per thread
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ws[j] = wp[j];
+  for (int m = 0; m < 4; ++m) {
+    const uint32_t t = tid + m * nthr;
+    my_q[m] = my_ri[m] = my_rank[m] = 0;
+    if (t < item.len) {
+      const uint32_t q = a.bk.order[item.start + t];
+      const int r = a.ridx[q], ri = a.invridx[q];
+      // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+      const uint32_t mi = (uint32_t)((kind == 0 || kind == 1) ? r : ri);
+      my_q[m] = q;
+      my_ri[m] = mi | ((uint32_t)r << 16);
+      my_rank[m] = atomicAdd(&s_hist[mi], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive scan of <= 48 bins
+    uint32_t run = 0;
+    for (uint32_t j = 0; j < G; ++j) {
+      const uint32_t c = s_hist[j];
+      s_hist[j] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    if (tid + m * nthr >= item.len) break;
+    const uint32_t t = s_hist[my_ri[m] & 0xffffu] + my_rank[m];
+    const uint32_t q = my_q[m];
+    QI[t] = q;
+    RI[t] = my_ri[m];
+    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)q);
+    for (int j = 0; j < NV / 2; ++j) {
+      const double2 w2 = wp[j];
+      W[(size_t)(2 * j) * CH + t] = w2.x;
+      W[(size_t)(2 * j + 1) * CH + t] = w2.y;
+    }
   }
   __syncthreads();
   if (gamma) {
@@ -261,50 +296,75 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
     // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
     for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
       const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
-      const double* w = W + 8 * (size_t)t;
       double acc = 0.0;
-      for (int i = 0; i < NV; ++i) acc += w[i] * V[(size_t)i * mpp * no0v + r];
+      for (int i = 0; i < NV; ++i) acc += W[(size_t)i * CH + t] * V[(size_t)i * mpp * no0v + r];
       a.vals_out[(size_t)QI[t] * vrow + (size_t)b0 * no0v + r] = acc;
     }
     // ---- eigenvectors: weighted sum of pre-phased rows, rotation, atom permutation, Gamma phase ----------------------
+    // A task is one 3-vector (mode b, atom k) for TQ consecutive points: the three complex numbers of every corner are
+    // read from shared memory once and reused for the TQ points (register tile), which makes the loop FP64-bound
+    // instead of shared-memory-bound.
+    constexpr int TQ = 4;
     const uint32_t per_q = mb * NAT;
-    for (uint32_t p = tid; p < item.len * per_q; p += nthr) {
-      const uint32_t t = p / per_q, r = p - t * per_q, b = r / NAT, k = r - b * NAT;
-      const double* w = W + 8 * (size_t)t;
+    const uint32_t ntile = (item.len + TQ - 1) / TQ;
+    for (uint32_t task = tid; task < ntile * per_q; task += nthr) {
+      const uint32_t tile = task / per_q, r = task - tile * per_q, b = r / NAT, k = r - b * NAT;
+      const uint32_t t0 = tile * TQ;
       const double2* src = D + (size_t)b * S + 3 * k;
-      double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0, acc2 = acc0;
+      double2 acc[TQ][3];
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
       for (int i = 0; i < NV; ++i) {
-        const double wi = w[i];
         const double2* x = src + (size_t)i * mpp * S;
         const double2 x0 = x[0], x1 = x[1], x2 = x[2];
-        acc0.x += wi * x0.x; acc0.y += wi * x0.y;
-        acc1.x += wi * x1.x; acc1.y += wi * x1.y;
-        acc2.x += wi * x2.x; acc2.y += wi * x2.y;
-      }
-      uint32_t dest = k;
-      double2 o0 = acc0, o1 = acc1, o2 = acc2;
-      if (kind >= 0) {
-        const uint32_t ri = RI[t] & 0xffffu;
-        const double* R = RS + 9 * ri;
-        o0.x = (R[0] * acc0.x + R[1] * acc1.x) + R[2] * acc2.x;  o0.y = (R[0] * acc0.y + R[1] * acc1.y) + R[2] * acc2.y;
-        o1.x = (R[3] * acc0.x + R[4] * acc1.x) + R[5] * acc2.x;  o1.y = (R[3] * acc0.y + R[4] * acc1.y) + R[5] * acc2.y;
-        o2.x = (R[6] * acc0.x + R[7] * acc1.x) + R[8] * acc2.x;  o2.y = (R[6] * acc0.y + R[7] * acc1.y) + R[8] * acc2.y;
-        if (gamma) {
-          dest = F0[k * G + ri];
-          const double2 ph = PH[(size_t)t * NAT + k];
-          double2 t0 = o0, t1 = o1, t2 = o2;
-          o0 = make_double2(ph.x * t0.x - ph.y * t0.y, ph.x * t0.y + ph.y * t0.x);
-          o1 = make_double2(ph.x * t1.x - ph.y * t1.y, ph.x * t1.y + ph.y * t1.x);
-          o2 = make_double2(ph.x * t2.x - ph.y * t2.y, ph.x * t2.y + ph.y * t2.x);
-        } else if (kind == 2) {
-          const double det = a.dd.rot_det[RI[t] >> 16];
-          o0.x *= det; o0.y *= det; o1.x *= det; o1.y *= det; o2.x *= det; o2.y *= det;
+        const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
+        const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
+        const double w[TQ] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          acc[t][0].x += w[t] * x0.x; acc[t][0].y += w[t] * x0.y;
+          acc[t][1].x += w[t] * x1.x; acc[t][1].y += w[t] * x1.y;
+          acc[t][2].x += w[t] * x2.x; acc[t][2].y += w[t] * x2.y;
         }
       }
-      double2* out = reinterpret_cast<double2*>(a.vecs_out) + (size_t)QI[t] * wrow + (size_t)(b0 + b) * S + 3 * dest;
-      out[0] = o0;
-      out[1] = o1;
-      out[2] = o2;
+      uint32_t cur = 0xffffffffu;
+      double R[9];
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) {
+        const uint32_t qi = t0 + t;
+        if (qi >= item.len) break;
+        uint32_t dest = k;
+        double2 o0 = acc[t][0], o1 = acc[t][1], o2 = acc[t][2];
+        if (kind >= 0) {
+          const uint32_t rr = RI[qi];
+          const uint32_t ri = rr & 0xffffu;
+          if (ri != cur) {  // points are sorted by matrix index: this reload is rare
+            const double* Rs = RS + 9 * ri;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R[e] = Rs[e];
+            cur = ri;
+          }
+          const double2 a0 = o0, a1 = o1, a2 = o2;
+          o0.x = (R[0] * a0.x + R[1] * a1.x) + R[2] * a2.x;  o0.y = (R[0] * a0.y + R[1] * a1.y) + R[2] * a2.y;
+          o1.x = (R[3] * a0.x + R[4] * a1.x) + R[5] * a2.x;  o1.y = (R[3] * a0.y + R[4] * a1.y) + R[5] * a2.y;
+          o2.x = (R[6] * a0.x + R[7] * a1.x) + R[8] * a2.x;  o2.y = (R[6] * a0.y + R[7] * a1.y) + R[8] * a2.y;
+          if (gamma) {
+            dest = F0[k * G + ri];
+            const double2 ph = PH[(size_t)qi * NAT + k];
+            const double2 u0 = o0, u1 = o1, u2 = o2;
+            o0 = make_double2(ph.x * u0.x - ph.y * u0.y, ph.x * u0.y + ph.y * u0.x);
+            o1 = make_double2(ph.x * u1.x - ph.y * u1.y, ph.x * u1.y + ph.y * u1.x);
+            o2 = make_double2(ph.x * u2.x - ph.y * u2.y, ph.x * u2.y + ph.y * u2.x);
+          } else if (kind == 2) {
+            const double det = a.dd.rot_det[rr >> 16];
+            o0.x *= det; o0.y *= det; o1.x *= det; o1.y *= det; o2.x *= det; o2.y *= det;
+          }
+        }
+        double2* out = reinterpret_cast<double2*>(a.vecs_out) + (size_t)QI[qi] * wrow + (size_t)(b0 + b) * S + 3 * dest;
+        out[0] = o0;
+        out[1] = o1;
+        out[2] = o2;
+      }
     }
   }
 }
