@@ -11,59 +11,6 @@
 #include "brille_b200.h"
 #include "device_tables.cuh"
 
-namespace b200 {
-// locate.cu
-constexpr uint32_t MODE_NO_MOVE = 1u, MODE_IR = 2u, MODE_NO_LOCATE = 4u;
-cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
-                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
-                          cudaStream_t stream);
-// interp.cu
-struct LocateIn {
-  const double* q_ir;
-  const int32_t* ridx;
-  const int32_t* invridx;
-  const uint32_t* cell;
-  const int32_t* tet;
-  const int32_t* n_vert;
-  const uint32_t* vertex;
-  const double* weight;
-  const uint64_t* slots;
-  const uint32_t* status;
-  const uint8_t* node_type;
-  const uint32_t* node_index;
-};
-cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
-                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
-// cellinterp.cu
-struct CellItem { uint32_t key, start, len; };
-struct BucketDev {
-  uint32_t n_buckets, chunk;
-  const uint32_t* cell_count;
-  uint32_t* cell_offset;
-  CellItem* items;
-  uint32_t* n_items;
-  uint32_t* order;
-};
-struct CellArgs {
-  DataDev dd;
-  const uint32_t* cube_vertices;
-  const uint32_t* tet_vertices;
-  uint32_t n_cubes;
-  BucketDev bk;
-  const double* weight;
-  const double* q_ir;
-  const int32_t* ridx;
-  const int32_t* invridx;
-  double* vals_out;
-  double* vecs_out;
-  int ir;
-  uint32_t modes_per_pass;
-};
-bool cell_path_eligible(const DataDev& dd);
-uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget);
-cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count, cudaStream_t stream);
-cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
-}  // namespace b200
 
 using namespace b200;
 
@@ -131,8 +78,10 @@ struct Workspace {
     *p = static_cast<T*>(v);
     return e;
   }
-  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch) {
-    if (n <= capacity && nb == n_buckets && ch == chunk) return cudaSuccess;
+  uint32_t n_atoms_cap = 0;
+  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch, uint32_t n_atoms) {
+    if (n <= capacity && nb == n_buckets && ch == chunk && n_atoms == n_atoms_cap) return cudaSuccess;
+    n_atoms_cap = n_atoms;
     if (n < capacity) n = capacity;
     release();
     cudaError_t e;
@@ -538,7 +487,7 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
                    bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
   const uint32_t nb = g->tr.n_cubes + g->tr.n_tets + 1;
-  CU(ws.ensure(n, nb, g->chunk));
+  CU(ws.ensure(n, nb, g->chunk, (interp && g->dd.vectors.rot_kind >= 3) ? g->dd.vectors.no1 : 0u));
   CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
@@ -791,7 +740,7 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
     if (value < 0 || value > 2) return fail(B200_E_INVALID, "interp_path must be 0 (auto), 1 (general) or 2 (cell-batched)");
     g->interp_path = (int)value;
   } else if (n == "chunk") {
-    if (value < 32 || value > 1024) return fail(B200_E_INVALID, "chunk must be in [32, 1024]");
+    if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
   } else {
     return fail(B200_E_INVALID, "unknown option " + n);

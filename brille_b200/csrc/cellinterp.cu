@@ -19,22 +19,6 @@
 
 namespace b200 {
 
-struct CellItem {
-  uint32_t key;    // bucket (cube c -> c, tetrahedron t -> n_cubes + t)
-  uint32_t start;  // first position in `order`
-  uint32_t len;    // number of points (<= chunk)
-};
-
-struct BucketDev {
-  uint32_t n_buckets;          // n_cubes + n_tets + 1
-  uint32_t chunk;              // points per CTA item
-  const uint32_t* cell_count;  // (n_buckets)
-  uint32_t* cell_offset;       // (n_buckets + 1) exclusive scan of cell_count
-  CellItem* items;             // (max_items)
-  uint32_t* n_items;           // [0] number of items, [1] start of the last (general) bucket, [2] its population
-  uint32_t* order;             // (n) point indices sorted by bucket
-};
-
 // ---------------------------------------------------------------------------------------------------------------
 // counting sort, part 2: single-CTA exclusive scan of the bucket populations + work-item table
 // ---------------------------------------------------------------------------------------------------------------
@@ -87,7 +71,8 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
   }
 }
 
-// counting sort, part 3
+// counting sort, part 3.  Only the 4-byte point index is scattered (the 40 MB `order` array stays in L2); the
+// per-point records themselves are gathered by the cell kernel, early enough to be hidden behind the cell staging.
 __global__ void __launch_bounds__(256)
 k_bucket_scatter(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_offset,
                  uint32_t* __restrict__ order, size_t n) {
@@ -98,22 +83,6 @@ k_bucket_scatter(const uint32_t* __restrict__ key, const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 // the cell kernel
 // ---------------------------------------------------------------------------------------------------------------
-struct CellArgs {
-  DataDev dd;
-  const uint32_t* cube_vertices;
-  const uint32_t* tet_vertices;
-  uint32_t n_cubes;
-  BucketDev bk;
-  const double* weight;    // (n,8)
-  const double* q_ir;      // (n,3)
-  const int32_t* ridx;     // (n)
-  const int32_t* invridx;  // (n)
-  double* vals_out;
-  double* vecs_out;
-  int ir;
-  uint32_t modes_per_pass;  // modes staged per pass (<= branches)
-};
-
 struct cplx2 { double re, im; };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -195,64 +164,29 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
     if (gamma)
       for (uint32_t i = tid; i < NAT * G; i += nthr) F0[i] = a.dd.gamma_F0[i];
   }
-  // ---- per-point constants ------------------------------------------------------------------------------------------
-  // The points of the chunk are re-ordered by the index of the rotation matrix they need (a counting sort over <= 48
-  // bins in shared memory), so that the TQ consecutive points a thread works on almost always share the matrix.
+  // ---- per-point records: one point per thread (chunk <= blockDim) --------------------------------------------------
+  // The gathers are issued here and consumed only after the first staging pass below, so their latency (point index ->
+  // record, two dependent DRAM/L2 accesses) overlaps the staging and phase alignment of the cell's vertex rows.
   const uint32_t CH = a.bk.chunk;  // row length of the transposed weight array W[corner][point]
   __shared__ uint32_t s_hist[64];
   if (tid < 64) s_hist[tid] = 0;
   for (uint32_t t = tid; t < (uint32_t)NV * CH; t += nthr) W[t] = 0.0;  // padding points carry zero weight
-  __syncthreads();
-  uint32_t my_q[4], my_ri[4], my_rank[4];  // chunk <= 1024 and 256 threads: at most 4 points per thread
+  const bool has = (uint32_t)tid < item.len;
+  uint32_t my_q = 0;
+  int my_r = 0, my_inv = 0;
+  double2 my_w[4];
+  double my_qir[3] = {0.0, 0.0, 0.0};
+  if (has) {
+    my_q = a.bk.order[item.start + tid];
+    my_r = a.ridx[my_q];
+    my_inv = a.invridx[my_q];
+    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)my_q);
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const uint32_t t = tid + m * nthr;
-    my_q[m] = my_ri[m] = my_rank[m] = 0;
-    if (t < item.len) {
-      const uint32_t q = a.bk.order[item.start + t];
-      const int r = a.ridx[q], ri = a.invridx[q];
-      // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
-      const uint32_t mi = (uint32_t)((kind == 0 || kind == 1) ? r : ri);
-      my_q[m] = q;
-      my_ri[m] = mi | ((uint32_t)r << 16);
-      my_rank[m] = atomicAdd(&s_hist[mi], 1u);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {  // exclusive scan of <= 48 bins
-    uint32_t run = 0;
-    for (uint32_t j = 0; j < G; ++j) {
-      const uint32_t c = s_hist[j];
-      s_hist[j] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    if (tid + m * nthr >= item.len) break;
-    const uint32_t t = s_hist[my_ri[m] & 0xffffu] + my_rank[m];
-    const uint32_t q = my_q[m];
-    QI[t] = q;
-    RI[t] = my_ri[m];
-    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)q);
-    for (int j = 0; j < NV / 2; ++j) {
-      const double2 w2 = wp[j];
-      W[(size_t)(2 * j) * CH + t] = w2.x;
-      W[(size_t)(2 * j + 1) * CH + t] = w2.y;
-    }
-  }
-  __syncthreads();
-  if (gamma) {
-    // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
-    for (uint32_t p = tid; p < item.len * NAT; p += nthr) {
-      const uint32_t t = p / NAT, k = p - t * NAT;
-      const uint32_t q = QI[t], ri = RI[t] & 0xffffu;
-      const double* gv = a.dd.gamma_vectors + 3 * (size_t)a.dd.gamma_vidx[(size_t)k * G + ri];
-      const double dot = ((0.0 + a.q_ir[3 * (size_t)q] * gv[0]) + a.q_ir[3 * (size_t)q + 1] * gv[1]) + a.q_ir[3 * (size_t)q + 2] * gv[2];
-      double sn, cs;
-      sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
-      PH[p] = make_double2(cs, sn);
+    for (int j = 0; j < 4; ++j) my_w[j] = wp[j];
+    if (gamma) {
+      my_qir[0] = a.q_ir[3 * (size_t)my_q];
+      my_qir[1] = a.q_ir[3 * (size_t)my_q + 1];
+      my_qir[2] = a.q_ir[3 * (size_t)my_q + 2];
     }
   }
 
@@ -293,6 +227,48 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       }
     }
     __syncthreads();
+    if (b0 == 0) {
+      // ---- consume the per-point records --------------------------------------------------------------------------
+      // The points of the chunk are re-ordered by the index of the rotation matrix they need (a counting sort over <= 48
+      // bins in shared memory), so that the TQ consecutive points a thread works on almost always share the matrix.
+      // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+      const uint32_t mi = (uint32_t)((kind == 0 || kind == 1) ? my_r : my_inv);
+      uint32_t my_rank = 0;
+      if (has) my_rank = atomicAdd(&s_hist[mi], 1u);
+      __syncthreads();
+      if (tid == 0) {  // exclusive scan of <= 48 bins
+        uint32_t run = 0;
+        for (uint32_t j = 0; j < G; ++j) {
+          const uint32_t c = s_hist[j];
+          s_hist[j] = run;
+          run += c;
+        }
+      }
+      __syncthreads();
+      if (has) {
+        const uint32_t t = s_hist[mi] + my_rank;
+        QI[t] = my_q;
+        RI[t] = mi | ((uint32_t)my_r << 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (2 * j < NV) {
+            W[(size_t)(2 * j) * CH + t] = my_w[j].x;
+            W[(size_t)(2 * j + 1) * CH + t] = my_w[j].y;
+          }
+        }
+        if (gamma) {
+          // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
+          for (uint32_t k = 0; k < NAT; ++k) {
+            const double* gv = a.dd.gamma_vectors + 3 * (size_t)a.dd.gamma_vidx[(size_t)k * G + mi];
+            const double dot = ((0.0 + my_qir[0] * gv[0]) + my_qir[1] * gv[1]) + my_qir[2] * gv[2];
+            double sn, cs;
+            sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
+            PH[(size_t)t * NAT + k] = make_double2(cs, sn);
+          }
+        }
+      }
+      __syncthreads();
+    }
     // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
     for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
       const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
@@ -406,7 +382,8 @@ cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stre
     configured = smem;
   }
   const size_t max_items = (n + args.bk.chunk - 1) / args.bk.chunk + (args.bk.n_buckets - 1);
-  k_interp_cell<<<(unsigned)max_items, 256, smem, stream>>>(args);
+  const unsigned threads = args.bk.chunk <= 128 ? 128 : 256;  // one point per thread in the prologue: chunk <= threads
+  k_interp_cell<<<(unsigned)max_items, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -93,4 +93,70 @@ struct DataDev {
   const uint8_t* rot_is_identity;  // (G)
 };
 
+// per-Q record of the locate stage as the interpolation kernels read it
+struct LocateIn {
+  const double* q_ir;
+  const int32_t* ridx;
+  const int32_t* invridx;
+  const uint32_t* cell;
+  const int32_t* tet;
+  const int32_t* n_vert;
+  const uint32_t* vertex;
+  const double* weight;
+  const uint64_t* slots;
+  const uint32_t* status;
+  const uint8_t* node_type;    // trellis: type of node `cell`
+  const uint32_t* node_index;  // trellis: payload index of node `cell`
+};
+
+// ---- cell-batched interpolation (cellinterp.cu) ------------------------------------------------------------------
+struct CellItem {
+  uint32_t key;    // bucket (cube c -> c, tetrahedron t -> n_cubes + t)
+  uint32_t start;  // first position in the sorted arrays
+  uint32_t len;    // number of points (<= chunk)
+};
+
+struct BucketDev {
+  uint32_t n_buckets;          // n_cubes + n_tets + 1
+  uint32_t chunk;              // points per CTA item
+  const uint32_t* cell_count;  // (n_buckets)
+  uint32_t* cell_offset;       // (n_buckets + 1) exclusive scan of cell_count
+  CellItem* items;             // (max_items)
+  uint32_t* n_items;           // [0] number of items, [1] start of the last (general) bucket, [2] its population
+  uint32_t* order;             // (n) point indices in bucket order
+};
+
+struct CellArgs {
+  DataDev dd;
+  const uint32_t* cube_vertices;
+  const uint32_t* tet_vertices;
+  uint32_t n_cubes;
+  BucketDev bk;
+  const double* weight;    // (n,8) per-point records of the locate stage, gathered through `order`
+  const double* q_ir;      // (n,3)
+  const int32_t* ridx;     // (n)
+  const int32_t* invridx;  // (n)
+  double* vals_out;
+  double* vecs_out;
+  int ir;
+  uint32_t modes_per_pass;  // modes staged per pass (<= branches)
+};
+
+// mode bits of the locate kernel
+constexpr uint32_t MODE_NO_MOVE = 1u;    // skip moveinto/ir_moveinto (do_not_move_points)
+constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather than moveinto
+constexpr uint32_t MODE_NO_LOCATE = 4u;  // moveinto only (b200_moveinto)
+
+// launchers (one per .cu file)
+cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
+                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
+                          cudaStream_t stream);
+cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
+                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
+bool cell_path_eligible(const DataDev& dd);
+uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget);
+cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
+                               cudaStream_t stream);
+cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
+
 }  // namespace b200

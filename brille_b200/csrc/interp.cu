@@ -19,20 +19,6 @@ namespace b200 {
 struct cplx { double re, im; };
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 
-struct LocateIn {
-  const double* q_ir;
-  const int32_t* ridx;
-  const int32_t* invridx;
-  const uint32_t* cell;
-  const int32_t* tet;
-  const int32_t* n_vert;
-  const uint32_t* vertex;
-  const double* weight;
-  const uint64_t* slots;
-  const uint32_t* status;
-  const uint8_t* node_type;    // trellis: type of node `cell`
-  const uint32_t* node_index;  // trellis: payload index of node `cell`
-};
 
 // sum over the LANES lanes of one group; `mask` names exactly those lanes (groups of one warp may sit
 // in different loop iterations, so a full-warp mask would be wrong)

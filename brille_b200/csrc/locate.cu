@@ -339,10 +339,6 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   return st;
 }
 
-// mode bits
-constexpr uint32_t MODE_NO_MOVE = 1u;   // skip moveinto/ir_moveinto (do_not_move_points)
-constexpr uint32_t MODE_IR = 2u;        // ir_moveinto (wedge rotation) rather than moveinto
-constexpr uint32_t MODE_NO_LOCATE = 4u; // moveinto only (b200_moveinto)
 
 __global__ void __launch_bounds__(128)
 k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict__ Q, size_t n, uint32_t mode,
