@@ -93,7 +93,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // dynamic shared memory carve-up (all offsets 16-byte aligned)
 struct SmemPlan {
-  size_t D, V, W, PH, RS, F0, QI, RI, total;
+  size_t D, V, W, PH, RS, F0, QI, RI, PHI, total;
 };
 __host__ __device__ inline SmemPlan plan_smem(uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
   SmemPlan p;
@@ -107,6 +107,7 @@ __host__ __device__ inline SmemPlan plan_smem(uint32_t mpp, uint32_t S, uint32_t
   p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
   p.QI = take((size_t)chunk * 4);
   p.RI = take((size_t)chunk * 4);
+  p.PHI = take((size_t)7 * mpp * 16);
   p.total = o;
   return p;
 }
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
   uint32_t* F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
   uint32_t* QI = reinterpret_cast<uint32_t*>(smem + pl.QI);
   uint32_t* RI = reinterpret_cast<uint32_t*>(smem + pl.RI);
+  double2* PHI = reinterpret_cast<double2*>(smem + pl.PHI);
   __shared__ uint32_t s_vtx[8], s_prow[8];
 
   // ---- per-cell constants: vertices in emission order, permutation rows relative to the pivot ------------------
@@ -206,25 +208,35 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       V[((size_t)i * mpp + b) * no0v + e] = vals.data[(size_t)s_vtx[i] * vrow + (size_t)pb * no0v + e];
     }
     __syncthreads();
-    // ---- align every vertex' eigenvector to the pivot's: one warp per (vertex, mode)  utilities.tpp:567-579 ----------
-    for (uint32_t pr = warp; pr < (uint32_t)(NV - 1) * mb; pr += nwarp) {
-      const uint32_t i = 1 + pr / mb, b = pr % mb;
+    // ---- align every vertex' eigenvector to the pivot's (utilities.tpp:567-579) -------------------------------------
+    // One THREAD per (vertex, mode): z = <d_pivot|d_v>, factor e^{-i arg z} = conj(z)/|z| (the reference evaluates
+    // polar(1, -atan2(Im z, Re z)), the same number up to rounding; z == 0 gives 1 in both).  All threads then scale.
+    for (uint32_t pr = tid; pr < (uint32_t)(NV - 1) * mb; pr += nthr) {
+      const uint32_t i = 1 + pr / mb, b = pr - (i - 1) * mb;
       const double2* d0 = D + (size_t)b * S;  // pivot (emission index 0) keeps its own branch
-      double2* dx = D + ((size_t)i * mpp + b) * S;
+      const double2* dx = D + ((size_t)i * mpp + b) * S;
       double re = 0.0, im = 0.0;
-      for (uint32_t s = lane; s < S; s += 32) {
-        const double2 p0 = d0[s], x = dx[s];
+      for (uint32_t e = 0; e < S; ++e) {
+        const double2 p0 = d0[e], x = dx[e];
         re += p0.x * x.x + p0.y * x.y;
         im += p0.x * x.y - p0.y * x.x;
       }
-      re = warp_sum(re);
-      im = warp_sum(im);
-      double sn, cs;
-      sincos(-atan2(im, re), &sn, &cs);
-      for (uint32_t s = lane; s < S; s += 32) {
-        const double2 x = dx[s];
-        dx[s] = make_double2(cs * x.x - sn * x.y, cs * x.y + sn * x.x);
+      const double m = fmax(fabs(re), fabs(im));
+      double2 f = make_double2(1.0, 0.0);
+      if (m > 0.0) {
+        const double r = re / m, q = im / m;
+        const double n = 1.0 / sqrt(r * r + q * q);
+        f = make_double2(r * n, -q * n);
       }
+      PHI[pr] = f;
+    }
+    __syncthreads();
+    for (uint32_t idx = tid; idx < (uint32_t)(NV - 1) * mb * S; idx += nthr) {
+      const uint32_t pr = idx / S, e = idx - pr * S, i = 1 + pr / mb, b = pr - (i - 1) * mb;
+      const double2 f = PHI[pr];
+      double2* dx = D + ((size_t)i * mpp + b) * S + e;
+      const double2 x = *dx;
+      *dx = make_double2(f.x * x.x - f.y * x.y, f.x * x.y + f.y * x.x);
     }
     __syncthreads();
     if (b0 == 0) {
