@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       // The points of the chunk are re-ordered by the index of the rotation matrix they need (a counting sort over <= 48
       // bins in shared memory), so that the TQ consecutive points a thread works on almost always share the matrix.
       // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+      // (the empty volatile asm pins the first use of the gathered values here: without it the compiler schedules the
+      // trivial arithmetic on them right after the loads, i.e. before the staging that is meant to hide their latency)
+      asm volatile("" : "+r"(my_r), "+r"(my_inv), "+r"(my_q));
       const uint32_t mi = (uint32_t)((kind == 0 || kind == 1) ? my_r : my_inv);
       uint32_t my_rank = 0;
       if (has) my_rank = atomicAdd(&s_hist[mi], 1u);
