@@ -223,6 +223,22 @@ static int build_bz(const b200_bz_tables_t* t, BZDev* d, double* eps_w, double* 
       for (int b = 0; b < 3; ++b) d->Rt[j][a * 3 + b] = (double)t->rotations[9 * j + b * 3 + a];
     d->inverse_index[j] = t->inverse_index[j];
   }
+  // certified fast wedge test (locate.cu): covectors R_j (G* n_k) and the rounding bound of their dot with q
+  d->wedge_fast = (t->n_wedge > 0 && t->n_wedge <= MAX_WEDGE_FAST && t->no_ir_mirroring) ? 1 : 0;
+  d->eps_wedge = 0.0;
+  if (d->wedge_fast)
+    for (int j = 0; j < t->n_ops; ++j)
+      for (int k = 0; k < t->n_wedge; ++k) {
+        double bound = 0.0;
+        for (int a = 0; a < 3; ++a) {
+          double s = 0.0;
+          for (int b = 0; b < 3; ++b) s += (double)t->rotations[9 * j + a * 3 + b] * d->gw[k][b];
+          d->wc[j][k][a] = s;
+          bound += std::fabs(s) * 4.0;  // |q_i| <= 4 rlu inside any first Brillouin zone
+        }
+        d->eps_wedge = std::max(d->eps_wedge, 64.0 * DBL_EPSILON * bound);
+      }
+  for (int f = 0; f < t->n_faces; ++f) d->inv_tau_lens[f] = 1.0 / t->tau_lens[f];
   return B200_OK;
 }
 

@@ -9,6 +9,7 @@ constexpr int MAX_FACES = 32;  // faces of a first Brillouin zone (<= 14 for 3-D
 constexpr int MAX_OPS = 48;    // order of a crystallographic point group
 constexpr int MAX_WEDGE = 16;  // irreducible wedge normals
 constexpr int MAX_KNOTS = 1024;
+constexpr int MAX_WEDGE_FAST = 6;
 
 // Everything ir_moveinto needs, small enough (< 12 KB) to be staged in shared memory by every CTA.
 struct BZDev {
@@ -31,6 +32,12 @@ struct BZDev {
   double gw[MAX_WEDGE][3];  // (G* n_k) of same_lattice_dot, computed once in the reference's order
   double Rt[MAX_OPS][9];    // transposed rotations as doubles
   int inverse_index[MAX_OPS];
+  // certified fast wedge test: (G* n_k).(R_j^T q) == (R_j G* n_k).q =: wc[j][k].q ; used when n_wedge <= MAX_WEDGE_FAST
+  // and no_ir_mirroring; a value within eps_wedge of the tolerance threshold falls back to the reference arithmetic
+  int wedge_fast;
+  double eps_wedge;
+  double wc[MAX_OPS][MAX_WEDGE_FAST][3];
+  double inv_tau_lens[MAX_FACES];  // 1/|tau_j| for the certified fast rounding of d_j/|tau_j|
 };
 
 struct TrellisDev {

@@ -116,14 +116,20 @@ __device__ __forceinline__ uint32_t moveinto_one(const BZDev& bz, double eps_w, 
   }
   const int F = bz.n_faces;
   int count = 0;
-  while (count++ < F && !inside_planes(bz, true, q, eps_w)) {
+  bool ended_inside = false;
+  while (count++ < F && !(ended_inside = inside_planes(bz, true, q, eps_w))) {
     double tmp[3];
     matvec(tmp, bz.w_recip_metric, q);  // same_lattice_dot: (G q) . n
     int max_nm = 0, max_at = 0;
     double d_at = 0.0;
     for (int j = 0; j < F; ++j) {
       double d = ((0.0 + tmp[0] * bz.normals[j][0]) + tmp[1] * bz.normals[j][1]) + tmp[2] * bz.normals[j][2];
-      int N = (int)round(d / bz.tau_lens[j]);
+      // N = round(d/|tau_j|) (bz_move.cpp:30): multiply by the reciprocal, and divide exactly only when the quotient is
+      // within 1e-9 of a rounding boundary (half-integers) where the last bit could matter
+      double quo = d * bz.inv_tau_lens[j];
+      const double fr = quo - floor(quo);
+      if (fabs(fr - 0.5) < 1e-9) quo = d / bz.tau_lens[j];
+      int N = (int)round(quo);
       if (N > 0 && N >= max_nm) {
         bool ok = (0 == max_nm);
         if (!ok) {
@@ -158,7 +164,10 @@ __device__ __forceinline__ uint32_t moveinto_one(const BZDev& bz, double eps_w, 
       tauo[i] = tau[i];
     }
   }
-  // bz_move.cpp:149: every q is re-tested against the conventional-lattice planes
+  // bz_move.cpp:149: every q is re-tested against the conventional-lattice planes.  Without a primitive transform these
+  // are the very planes and the very q of the last test of the loop above, whose outcome is known when the loop ended
+  // because the point was inside.
+  if (!bz.transform_needed && ended_inside) return 0u;
   return inside_planes(bz, false, qo, eps_o) ? 0u : (uint32_t)B200_ST_OUTSIDE_BZ;
 }
 
@@ -217,15 +226,35 @@ __device__ __forceinline__ double tet_weights(const double* tp, const double* x,
   return 0.0;
 }
 
-struct Emit {
+// Result of the point location of one Q, written straight to the per-point output rows.  The common case (every
+// corner of the cell carries weight) is stored with vector stores from registers; only points on a face / edge / vertex
+// of their cell take the compacting path.
+struct EmitOut {
+  uint32_t* v;     // (8) vertex indices, emission order
+  double* w;       // (8) weights
+  uint64_t slots;  // byte j = cell corner of emitted vertex j
   int n;
-  uint32_t v[8];
-  double w[8];
-  uint64_t slots;
 };
 
+__device__ __noinline__ void emit_compact(EmitOut& e, const uint32_t* vi, const double* w, const bool* keep, int count, bool cube) {
+  e.n = 0;
+  e.slots = 0;
+  for (int i = 0; i < count; ++i)
+    if (keep[i]) {
+      const int slot = cube ? 7 - i : i;  // trellis_node.hpp:143-147 emits vertex_indices[7-i]
+      e.v[e.n] = vi[slot];
+      e.w[e.n] = w[i];
+      e.slots |= (uint64_t)slot << (8 * e.n);
+      ++e.n;
+    }
+  for (int j = e.n; j < 8; ++j) {
+    e.v[j] = 0xffffffffu;
+    e.w[j] = 0.0;
+  }
+}
+
 __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const TrellisDev& t, const double* knots, const double* x,
-                                                   Emit& e, uint32_t& cell, int& tet) {
+                                                   EmitOut& e, uint32_t& cell, int& tet) {
   uint32_t st = 0;
   e.n = 0;
   e.slots = 0;
@@ -268,28 +297,40 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   const int n0 = t.n_knots[0] - 1, n1 = t.n_knots[1] - 1;
   cell = (uint32_t)(sub[0] + n0 * (sub[1] + n1 * sub[2]));
   const uint32_t payload = t.node_index[cell];
+  uint4* vo = reinterpret_cast<uint4*>(e.v);
+  double2* wo = reinterpret_cast<double2*>(e.w);
   if (t.node_type[cell] == B200_NODE_CUBE) {
     // CubeNode::indices_weights (trellis_node.hpp:130-149)
-    const double* cp = t.cube_pack + 24 * (size_t)payload;
-    const uint32_t* vi = t.cube_vertices + 8 * (size_t)payload;
+    const double2* cp = reinterpret_cast<const double2*>(t.cube_pack + 24 * (size_t)payload);
+    const uint4* vip = reinterpret_cast<const uint4*>(t.cube_vertices + 8 * (size_t)payload);
     double c[24];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-      double2 v = reinterpret_cast<const double2*>(cp)[i];
+      const double2 v = cp[i];
       c[2 * i] = v.x;
       c[2 * i + 1] = v.y;
     }
     const double vol = (fabs(c[0] - c[21]) * fabs(c[1] - c[22])) * fabs(c[2] - c[23]);
+    double w[8];
+    bool keep[8];
+    bool all = true;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      double w = (fabs(x[0] - c[3 * i]) * fabs(x[1] - c[3 * i + 1])) * fabs(x[2] - c[3 * i + 2]);
-      w = w / vol;
-      if (!approx_eq(w, 0.0, bz.def_rel, bz.def_abs) && w > 0.0) {
-        e.v[e.n] = vi[7 - i];
-        e.w[e.n] = w;
-        e.slots |= (uint64_t)(7 - i) << (8 * e.n);
-        ++e.n;
-      }
+      w[i] = ((fabs(x[0] - c[3 * i]) * fabs(x[1] - c[3 * i + 1])) * fabs(x[2] - c[3 * i + 2])) / vol;
+      keep[i] = !approx_eq(w[i], 0.0, bz.def_rel, bz.def_abs) && w[i] > 0.0;  // w.is(gt, 0.)
+      all &= keep[i];
+    }
+    const uint4 va = vip[0], vb = vip[1];
+    if (all) {
+      vo[0] = make_uint4(vb.w, vb.z, vb.y, vb.x);  // vertex_indices[7], [6], [5], [4]
+      vo[1] = make_uint4(va.w, va.z, va.y, va.x);  // vertex_indices[3], [2], [1], [0]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wo[j] = make_double2(w[2 * j], w[2 * j + 1]);
+      e.n = 8;
+      e.slots = 0x0001020304050607ull;  // byte j = 7 - j
+    } else {
+      const uint32_t vi[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      emit_compact(e, vi, w, keep, 8, true);
     }
   } else {
     // PolyNode::indices_weights (trellis_node.hpp:273-308), should_contain == true
@@ -300,10 +341,10 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
     int found = -1;
     for (uint32_t k = t0; k < t1; ++k) {
       const double* tp = t.tet_pack + (size_t)TET_PACK * k;
-      double2 c01 = reinterpret_cast<const double2*>(tp)[0];
-      double2 c23 = reinterpret_cast<const double2*>(tp)[1];
-      double v0 = c01.x - x[0], v1 = c01.y - x[1], v2 = c23.x - x[2];
-      double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
+      const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+      const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+      const double v0 = c01.x - x[0], v1 = c01.y - x[1], v2 = c23.x - x[2];
+      const double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
       double mn;
       if (d2 < c23.y || approx_eq(d2, c23.y, bz.def_rel, bz.def_abs))
         mn = tet_weights(tp, x, w, bz.def_rel, bz.def_abs);
@@ -325,20 +366,31 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
       tet_weights(t.tet_pack + (size_t)TET_PACK * best_at, x, w, bz.def_rel, bz.def_abs);
     }
     tet = found;
-    const uint32_t* vi = t.tet_vertices + 4 * (size_t)found;
+    const uint4 vi4 = *reinterpret_cast<const uint4*>(t.tet_vertices + 4 * (size_t)found);
+    bool keep[4];
+    bool all = true;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (!approx_eq(w[j], 0.0, bz.def_rel, bz.def_abs)) {
-        e.v[e.n] = vi[j];
-        e.w[e.n] = w[j];
-        e.slots |= (uint64_t)j << (8 * e.n);
-        ++e.n;
-      }
+    for (int j = 0; j < 4; ++j) {
+      keep[j] = !approx_eq(w[j], 0.0, bz.def_rel, bz.def_abs);
+      all &= keep[j];
+    }
+    if (all) {
+      vo[0] = vi4;
+      vo[1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      wo[0] = make_double2(w[0], w[1]);
+      wo[1] = make_double2(w[2], w[3]);
+      wo[2] = make_double2(0.0, 0.0);
+      wo[3] = make_double2(0.0, 0.0);
+      e.n = 4;
+      e.slots = 0x03020100ull;
+    } else {
+      const uint32_t vi[4] = {vi4.x, vi4.y, vi4.z, vi4.w};
+      emit_compact(e, vi, w, keep, 4, false);
+    }
   }
   if (e.n < 1) st |= B200_ST_NOT_FOUND;
   return st;
 }
-
 
 __global__ void __launch_bounds__(128)
 k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict__ Q, size_t n, uint32_t mode,
@@ -369,9 +421,21 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
         // bz_move.cpp:262-285: first operation (storage order) whose transpose moves q into the wedge
         bool done = false;
         for (int j = 0; j < bz.n_ops && !done; ++j) {
+          int verdict = 2;  // 0 outside, 1 inside, 2 ask the reference arithmetic
+          if (bz.wedge_fast) {
+            // (G* n_k).(R_j^T q) evaluated as (R_j G* n_k).q; certain unless within eps_wedge of the threshold
+            verdict = 1;
+            const double lo = -bz.cfg_abs * (1.0 + 4.0 * bz.cfg_rel) - bz.eps_wedge, hi = -bz.cfg_abs + bz.eps_wedge;
+            for (int k = 0; k < bz.n_wedge; ++k) {
+              const double d = (bz.wc[j][k][0] * q[0] + bz.wc[j][k][1] * q[1]) + bz.wc[j][k][2] * q[2];
+              if (d < lo) { verdict = 0; break; }
+              if (d < hi) verdict = 2;
+            }
+          }
+          if (verdict == 0) continue;
           double qj[3];
           matvec(qj, bz.Rt[j], q);
-          if (inside_wedge(bz, qj)) {
+          if (verdict == 1 || inside_wedge(bz, qj)) {
             q[0] = qj[0]; q[1] = qj[1]; q[2] = qj[2];
             invridx = j;
             ridx = bz.inverse_index[j];
@@ -394,26 +458,21 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
     uint32_t cell = 0xffffffffu;
     int tet = -1, n_emit = 0;
     if (!(mode & MODE_NO_LOCATE)) {
-      Emit e;
+      EmitOut e;
+      e.v = out.vertex + 8 * i;
+      e.w = out.weight + 8 * i;
       st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
+      if (e.n == 0) {  // not found: defined contents for the row
+        for (int j = 0; j < 8; ++j) {
+          e.v[j] = 0xffffffffu;
+          e.w[j] = 0.0;
+        }
+      }
       n_emit = e.n;
       out.cell[i] = cell;
       out.tet[i] = tet;
       out.n_vert[i] = e.n;
       out.slots[i] = e.slots;
-      uint4* vo = reinterpret_cast<uint4*>(out.vertex + 8 * i);
-      double2* wo = reinterpret_cast<double2*>(out.weight + 8 * i);
-      uint32_t v[8];
-      double w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = j < e.n ? e.v[j] : 0xffffffffu;
-        w[j] = j < e.n ? e.w[j] : 0.0;
-      }
-      vo[0] = make_uint4(v[0], v[1], v[2], v[3]);
-      vo[1] = make_uint4(v[4], v[5], v[6], v[7]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wo[j] = make_double2(w[2 * j], w[2 * j + 1]);
     }
     out.status[i] = st;
     if (out.key) {
