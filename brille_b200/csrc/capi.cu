@@ -239,6 +239,51 @@ static int build_bz(const b200_bz_tables_t* t, BZDev* d, double* eps_w, double* 
         d->eps_wedge = std::max(d->eps_wedge, 64.0 * DBL_EPSILON * bound);
       }
   for (int f = 0; f < t->n_faces; ++f) d->inv_tau_lens[f] = 1.0 / t->tau_lens[f];
+  // sign-pattern lookup of the wedge operation
+  d->n_wplanes = 0;
+  if (d->wedge_fast) {
+    int pid[MAX_OPS][MAX_WEDGE_FAST], sgn[MAX_OPS][MAX_WEDGE_FAST];
+    int m = 0;
+    bool ok = true;
+    for (int j = 0; j < t->n_ops && ok; ++j)
+      for (int k = 0; k < t->n_wedge && ok; ++k) {
+        const double* c = d->wc[j][k];
+        const double nrm = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        if (nrm == 0.0) { ok = false; break; }
+        int found = -1, sg = 1;
+        for (int p = 0; p < m && found < 0; ++p)
+          for (int s = 1; s >= -1; s -= 2) {
+            double diff = 0.0;
+            for (int a = 0; a < 3; ++a) diff = std::max(diff, std::fabs(c[a] - s * d->wplane[p][a]));
+            if (diff <= 1e-9 * nrm) { found = p; sg = s; break; }
+          }
+        if (found < 0) {
+          if (m == MAX_WPLANES) { ok = false; break; }
+          for (int a = 0; a < 3; ++a) d->wplane[m][a] = c[a];
+          found = m++;
+          sg = 1;
+        }
+        pid[j][k] = found;
+        sgn[j][k] = sg;
+      }
+    if (ok) {
+      auto matches = [&](int j, unsigned s) {
+        for (int k = 0; k < t->n_wedge; ++k)
+          if ((((s >> pid[j][k]) & 1u) != 0) != (sgn[j][k] > 0)) return false;
+        return true;
+      };
+      for (unsigned s = 0; s < (1u << m); ++s) {
+        int pick = 0xff;
+        if (matches(t->identity_index, s)) pick = t->identity_index;  // bz_move.cpp:263-266 tests q itself first
+        for (int j = 0; j < t->n_ops && pick == 0xff; ++j)
+          if (matches(j, s)) pick = j;
+        d->wtable[s] = (uint8_t)pick;
+      }
+      d->n_wplanes = m;
+      // anything closer to a plane than this is decided by the reference arithmetic (1e-9 relative covers the plane merging)
+      d->wband = d->cfg_abs * (1.0 + 4.0 * d->cfg_rel) + d->eps_wedge * 1e3 + 1e-9 * d->cfg_abs;
+    }
+  }
   return B200_OK;
 }
 

@@ -10,6 +10,7 @@ constexpr int MAX_OPS = 48;    // order of a crystallographic point group
 constexpr int MAX_WEDGE = 16;  // irreducible wedge normals
 constexpr int MAX_KNOTS = 1024;
 constexpr int MAX_WEDGE_FAST = 6;
+constexpr int MAX_WPLANES = 12;
 
 // Everything ir_moveinto needs, small enough (< 12 KB) to be staged in shared memory by every CTA.
 struct BZDev {
@@ -38,6 +39,13 @@ struct BZDev {
   double eps_wedge;
   double wc[MAX_OPS][MAX_WEDGE_FAST][3];
   double inv_tau_lens[MAX_FACES];  // 1/|tau_j| for the certified fast rounding of d_j/|tau_j|
+  // sign-pattern wedge lookup: the wedge-bounding planes of all G images of the wedge reduce to n_wplanes distinct planes
+  // through the origin; the signs of q on them select the operation through wtable (0xff = none).  A point within wband
+  // of any plane takes the in-order scan with the reference arithmetic instead.
+  int n_wplanes;  // 0 => lookup not available
+  double wband;
+  double wplane[MAX_WPLANES][3];
+  uint8_t wtable[1 << MAX_WPLANES];
 };
 
 struct TrellisDev {

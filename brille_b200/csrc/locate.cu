@@ -338,25 +338,43 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
     double w[4];
     double best = 0.0;
     uint32_t best_at = t0;
+    bool have_best = false;
     int found = -1;
-    for (uint32_t k = t0; k < t1; ++k) {
-      const double* tp = t.tet_pack + (size_t)TET_PACK * k;
-      const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
-      const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
-      const double v0 = c01.x - x[0], v1 = c01.y - x[1], v2 = c23.x - x[2];
-      const double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
-      double mn;
-      if (d2 < c23.y || approx_eq(d2, c23.y, bz.def_rel, bz.def_abs))
-        mn = tet_weights(tp, x, w, bz.def_rel, bz.def_abs);
-      else
-        mn = -d2;
-      if (mn >= 0.0) {
-        found = (int)k;
-        break;
+    // Two phases per block of <= 64 tetrahedra, so that the expensive part is not executed once per loop trip of the
+    // slowest lane of the warp: (1) the cheap circumsphere test of tetrahedra_might_contain for every tetrahedron
+    // (:349-364), remembering the candidates in a bit mask; (2) the four weights of the candidates, in storage order,
+    // until one contains the point (first accepted wins, :284-290).  `best` keeps max_element's first-maximum rule.
+    for (uint32_t base = t0; base < t1 && found < 0; base += 64) {
+      const uint32_t nblk = min(64u, t1 - base);
+      unsigned long long cand = 0ull;
+      for (uint32_t k = 0; k < nblk; ++k) {
+        const double* tp = t.tet_pack + (size_t)TET_PACK * (base + k);
+        const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+        const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+        const double v0 = c01.x - x[0], v1 = c01.y - x[1], v2 = c23.x - x[2];
+        const double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
+        if (d2 < c23.y || approx_eq(d2, c23.y, bz.def_rel, bz.def_abs)) {
+          cand |= 1ull << k;
+        } else {
+          const double mn = -d2;
+          if (!have_best || mn > best || (mn == best && base + k < best_at)) {
+            best = mn;
+            best_at = base + k;
+            have_best = true;
+          }
+        }
       }
-      if (k == t0 || mn > best) {
-        best = mn;
-        best_at = k;
+      while (cand && found < 0) {
+        const uint32_t k = base + (uint32_t)(__ffsll((long long)cand) - 1);
+        cand &= cand - 1ull;
+        const double mn = tet_weights(t.tet_pack + (size_t)TET_PACK * k, x, w, bz.def_rel, bz.def_abs);
+        if (mn >= 0.0) {
+          found = (int)k;
+        } else if (!have_best || mn > best || (mn == best && k < best_at)) {
+          best = mn;
+          best_at = k;
+          have_best = true;
+        }
       }
     }
     if (found < 0) {
@@ -392,6 +410,34 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   return st;
 }
 
+// in-order scan with the reference arithmetic (bz_move.cpp:262-285); taken by points within tolerance of a wedge
+// plane and by Brillouin zones for which the sign-pattern lookup is not available
+__device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, int& invridx) {
+  for (int j = 0; j < bz.n_ops; ++j) {
+    int verdict = 2;  // 0 outside, 1 inside, 2 ask the reference arithmetic
+    if (bz.wedge_fast) {
+      // (G* n_k).(R_j^T q) evaluated as (R_j G* n_k).q; certain unless within eps_wedge of the threshold
+      verdict = 1;
+      const double lo = -bz.cfg_abs * (1.0 + 4.0 * bz.cfg_rel) - bz.eps_wedge, hi = -bz.cfg_abs + bz.eps_wedge;
+      for (int k = 0; k < bz.n_wedge; ++k) {
+        const double d = (bz.wc[j][k][0] * q[0] + bz.wc[j][k][1] * q[1]) + bz.wc[j][k][2] * q[2];
+        if (d < lo) { verdict = 0; break; }
+        if (d < hi) verdict = 2;
+      }
+    }
+    if (verdict == 0) continue;
+    double qj[3];
+    matvec(qj, bz.Rt[j], q);
+    if (verdict == 1 || inside_wedge(bz, qj)) {
+      q[0] = qj[0]; q[1] = qj[1]; q[2] = qj[2];
+      invridx = j;
+      ridx = bz.inverse_index[j];
+      return true;
+    }
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(128)
 k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict__ Q, size_t n, uint32_t mode,
          double eps_w, double eps_o, LocateOut out, unsigned long long* __restrict__ fail_count) {
@@ -417,30 +463,34 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
       q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
     } else {
       st = moveinto_one(bz, eps_w, eps_o, Qi, q, tau);
-      if ((mode & MODE_IR) && !inside_wedge(bz, q)) {
-        // bz_move.cpp:262-285: first operation (storage order) whose transpose moves q into the wedge
-        bool done = false;
-        for (int j = 0; j < bz.n_ops && !done; ++j) {
-          int verdict = 2;  // 0 outside, 1 inside, 2 ask the reference arithmetic
-          if (bz.wedge_fast) {
-            // (G* n_k).(R_j^T q) evaluated as (R_j G* n_k).q; certain unless within eps_wedge of the threshold
-            verdict = 1;
-            const double lo = -bz.cfg_abs * (1.0 + 4.0 * bz.cfg_rel) - bz.eps_wedge, hi = -bz.cfg_abs + bz.eps_wedge;
-            for (int k = 0; k < bz.n_wedge; ++k) {
-              const double d = (bz.wc[j][k][0] * q[0] + bz.wc[j][k][1] * q[1]) + bz.wc[j][k][2] * q[2];
-              if (d < lo) { verdict = 0; break; }
-              if (d < hi) verdict = 2;
-            }
+      if (mode & MODE_IR) {
+        // ---- wedge rotation: bz_move.cpp:257-285 ----
+        // fast path: signs of q on the distinct wedge-bounding planes -> operation index through a lookup table
+        int pick = -1;
+        if (bz.n_wplanes > 0) {
+          unsigned mask = 0;
+          bool ambiguous = false;
+          for (int p = 0; p < bz.n_wplanes; ++p) {
+            const double d = (bz.wplane[p][0] * q[0] + bz.wplane[p][1] * q[1]) + bz.wplane[p][2] * q[2];
+            ambiguous |= fabs(d) <= bz.wband;
+            mask |= (d > 0.0 ? 1u : 0u) << p;
           }
-          if (verdict == 0) continue;
-          double qj[3];
-          matvec(qj, bz.Rt[j], q);
-          if (verdict == 1 || inside_wedge(bz, qj)) {
+          if (!ambiguous) {
+            const int j = bz.wtable[mask];
+            if (j != 0xff) pick = j;
+          }
+        }
+        bool done = true;
+        if (pick >= 0) {
+          if (pick != bz.identity_index) {
+            double qj[3];
+            matvec(qj, bz.Rt[pick], q);  // exactly the reference's R_j^T q
             q[0] = qj[0]; q[1] = qj[1]; q[2] = qj[2];
-            invridx = j;
-            ridx = bz.inverse_index[j];
-            done = true;
+            invridx = pick;
+            ridx = bz.inverse_index[pick];
           }
+        } else if (!inside_wedge(bz, q)) {
+          done = wedge_scan(bz, q, ridx, invridx);
         }
         if (!done) {
           st |= B200_ST_OUTSIDE_WEDGE;
