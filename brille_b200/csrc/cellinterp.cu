@@ -91,6 +91,28 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// out = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
+// that finishes a point produces the same bits (the result must not depend on which path a point happens to take)
+__device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
+                                                   const double2 ph, bool use_phase, double2* out) {
+  double2 u0, u1, u2;
+  u0.x = __fma_rn(R[2], a2.x, __fma_rn(R[1], a1.x, __dmul_rn(R[0], a0.x)));
+  u0.y = __fma_rn(R[2], a2.y, __fma_rn(R[1], a1.y, __dmul_rn(R[0], a0.y)));
+  u1.x = __fma_rn(R[5], a2.x, __fma_rn(R[4], a1.x, __dmul_rn(R[3], a0.x)));
+  u1.y = __fma_rn(R[5], a2.y, __fma_rn(R[4], a1.y, __dmul_rn(R[3], a0.y)));
+  u2.x = __fma_rn(R[8], a2.x, __fma_rn(R[7], a1.x, __dmul_rn(R[6], a0.x)));
+  u2.y = __fma_rn(R[8], a2.y, __fma_rn(R[7], a1.y, __dmul_rn(R[6], a0.y)));
+  if (use_phase) {
+    out[0] = make_double2(__fma_rn(-ph.y, u0.y, __dmul_rn(ph.x, u0.x)), __fma_rn(ph.y, u0.x, __dmul_rn(ph.x, u0.y)));
+    out[1] = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
+    out[2] = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
+  } else {
+    out[0] = u0;
+    out[1] = u1;
+    out[2] = u2;
+  }
+}
+
 // dynamic shared memory carve-up (all offsets 16-byte aligned)
 struct SmemPlan {
   size_t D, V, W, PH, RS, F0, QI, RI, PHI, total;
@@ -318,43 +340,57 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
           acc[t][2].x += w[t] * x2.x; acc[t][2].y += w[t] * x2.y;
         }
       }
-      uint32_t cur = 0xffffffffu;
-      double R[9];
+      // ---- finish: rotation, atom permutation, Gamma phase, store ------------------------------------------------------
+      const uint32_t nt = min((uint32_t)TQ, item.len - t0);
+      const uint4 rr4 = *reinterpret_cast<const uint4*>(RI + t0);
+      const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
+      const uint32_t rrs[TQ] = {rr4.x, rr4.y, rr4.z, rr4.w}, qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
+      double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + (size_t)(b0 + b) * S;
+      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu)) {
+        // the four points share the rotation (the chunk is sorted by it): one matrix, one destination atom, no branches
+        const uint32_t ri = rr4.x & 0xffffu;
+        double R[9];
+        {
+          const double* Rs = RS + 9 * ri;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = Rs[e];
+        }
+        const uint32_t dest = F0[k * G + ri];
+        const double2* php = PH + (size_t)t0 * NAT + k;
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          rotate_phase_store(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true,
+                             out_base + (size_t)qis[t] * wrow + 3 * dest);
+        }
+        continue;
+      }
 #pragma unroll
       for (int t = 0; t < TQ; ++t) {
+        if ((uint32_t)t >= nt) break;
         const uint32_t qi = t0 + t;
-        if (qi >= item.len) break;
         uint32_t dest = k;
-        double2 o0 = acc[t][0], o1 = acc[t][1], o2 = acc[t][2];
+        double2* out = out_base + (size_t)qis[t] * wrow;
         if (kind >= 0) {
-          const uint32_t rr = RI[qi];
+          const uint32_t rr = rrs[t];
           const uint32_t ri = rr & 0xffffu;
-          if (ri != cur) {  // points are sorted by matrix index: this reload is rare
-            const double* Rs = RS + 9 * ri;
-#pragma unroll
-            for (int e = 0; e < 9; ++e) R[e] = Rs[e];
-            cur = ri;
-          }
-          const double2 a0 = o0, a1 = o1, a2 = o2;
-          o0.x = (R[0] * a0.x + R[1] * a1.x) + R[2] * a2.x;  o0.y = (R[0] * a0.y + R[1] * a1.y) + R[2] * a2.y;
-          o1.x = (R[3] * a0.x + R[4] * a1.x) + R[5] * a2.x;  o1.y = (R[3] * a0.y + R[4] * a1.y) + R[5] * a2.y;
-          o2.x = (R[6] * a0.x + R[7] * a1.x) + R[8] * a2.x;  o2.y = (R[6] * a0.y + R[7] * a1.y) + R[8] * a2.y;
+          double2 ph = make_double2(1.0, 0.0);
           if (gamma) {
             dest = F0[k * G + ri];
-            const double2 ph = PH[(size_t)qi * NAT + k];
-            const double2 u0 = o0, u1 = o1, u2 = o2;
-            o0 = make_double2(ph.x * u0.x - ph.y * u0.y, ph.x * u0.y + ph.y * u0.x);
-            o1 = make_double2(ph.x * u1.x - ph.y * u1.y, ph.x * u1.y + ph.y * u1.x);
-            o2 = make_double2(ph.x * u2.x - ph.y * u2.y, ph.x * u2.y + ph.y * u2.x);
-          } else if (kind == 2) {
-            const double det = a.dd.rot_det[rr >> 16];
-            o0.x *= det; o0.y *= det; o1.x *= det; o1.y *= det; o2.x *= det; o2.y *= det;
+            ph = PH[(size_t)qi * NAT + k];
           }
+          out += 3 * dest;
+          rotate_phase_store(RS + 9 * ri, acc[t][0], acc[t][1], acc[t][2], ph, gamma, out);
+          if (kind == 2) {  // axial: det(R) R^-1 v
+            const double det = a.dd.rot_det[rr >> 16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out[c] = make_double2(out[c].x * det, out[c].y * det);
+          }
+        } else {
+          out += 3 * dest;
+          out[0] = acc[t][0];
+          out[1] = acc[t][1];
+          out[2] = acc[t][2];
         }
-        double2* out = reinterpret_cast<double2*>(a.vecs_out) + (size_t)QI[qi] * wrow + (size_t)(b0 + b) * S + 3 * dest;
-        out[0] = o0;
-        out[1] = o1;
-        out[2] = o2;
       }
     }
   }
