@@ -74,6 +74,19 @@ struct Access {
 };
 struct LeafCR { using type = std::array<double, 4> NestLeaf::*; friend type get(LeafCR); };
 template struct Access<LeafCR, &NestLeaf::centre_radius>;
+template <class T, class R>
+struct NestRoot { using type = NestNode Nest<T, R, double, Array2>::*; friend type get(NestRoot); };
+template struct Access<NestRoot<double, double>, &Nest<double, double, double, Array2>::root_>;
+template struct Access<NestRoot<double, cplx>, &Nest<double, cplx, double, Array2>::root_>;
+template struct Access<NestRoot<cplx, cplx>, &Nest<cplx, cplx, double, Array2>::root_>;
+struct TetTriLayers { using type = std::vector<TetTriLayer> TetTri::*; friend type get(TetTriLayers); };
+template struct Access<TetTriLayers, &TetTri::layers>;
+struct TetTriConns { using type = std::vector<std::vector<std::vector<ind_t>>> TetTri::*; friend type get(TetTriConns); };
+template struct Access<TetTriConns, &TetTri::connections>;
+template <class T, class R>
+struct MeshSpy : Mesh3<T, R, double, Array2> {
+  static const TetTri& mesh_of(const Mesh3<T, R, double, Array2>& m) { return m.*(&MeshSpy::mesh); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // numpy helpers (always own a copy: tables must outlive the host objects)
@@ -358,6 +371,154 @@ static py::dict flatten_trellis_data(const BrillouinZoneTrellis3<T, R, S>& g) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Nest (nest.hpp): the tree flattened breadth-first, children of a node contiguous and in storage order,
+// i.e. exactly the order in which NestNode::indices_weights' deque visits them (nest.hpp:163-192)
+// ---------------------------------------------------------------------------------------------
+template <class T, class R>
+static py::dict flatten_nest(const BrillouinZoneNest3<T, R, double>& g) {
+  py::dict d;
+  d["kind"] = "nest";
+  d["bz"] = flatten_bz(g.get_brillouinzone());
+  const Nest<T, R, double, Array2>& nest = g;
+  const NestNode& root = nest.*get(NestRoot<T, R>());
+  std::vector<unsigned> vi, cbeg, cend;
+  std::vector<double> cr, vol;
+  std::vector<uint8_t> leaf;
+  std::deque<const NestNode*> work;
+  auto push = [&](const NestNode& n, bool is_root) {
+    const auto& lf = n.boundary();
+    for (auto v : lf.vertices()) vi.push_back(v);
+    const auto& c = lf.*get(LeafCR());
+    for (auto x : c) cr.push_back(x);
+    vol.push_back(lf.volume());
+    leaf.push_back((!is_root && n.is_leaf()) ? 1 : 0);
+    cbeg.push_back(0);
+    cend.push_back(0);
+  };
+  push(root, true);  // node 0 = root (its own boundary is unused)
+  work.push_back(&root);
+  size_t at = 0;
+  while (!work.empty()) {
+    const NestNode* n = work.front();
+    work.pop_front();
+    cbeg[at] = static_cast<unsigned>(vol.size());
+    for (const auto& b : n->branches()) {
+      push(b, false);
+      work.push_back(&b);
+    }
+    cend[at] = static_cast<unsigned>(vol.size());
+    ++at;
+  }
+  d["node_vertices"] = np2(vi, 4);
+  d["node_circum"] = np2(cr, 4);
+  d["node_volume"] = np1(vol);
+  d["node_is_leaf"] = np1(leaf);
+  d["child_begin"] = np1(cbeg);
+  d["child_end"] = np1(cend);
+  d["vertices"] = np_from_a2<double>(g.all_vertices());
+  auto cfg = g.approx_config();
+  d["approx_digit"] = cfg.digit();
+  d["approx_direct"] = cfg.template direct<double>();
+  d["approx_reciprocal"] = cfg.template reciprocal<double>();
+  return d;
+}
+
+// per-tetrahedron pair -> permutation row for tetrahedral grids (nest: per node, mesh: per finest-layer tetrahedron)
+template <class T, class R>
+static void flatten_tet_perms(const DualInterpolator<T, R>& data, const std::vector<unsigned>& tets, py::dict& d) {
+  bool any = false;
+  flatten_perm_rows(data, d, any);
+  d["perm_nonidentity"] = any ? 1 : 0;
+  if (!any) return;
+  PermLookup look(DualSpy<T, R>::table(data));
+  std::vector<unsigned> tp;
+  tp.reserve(tets.size() * 4);
+  for (size_t t = 0; t < tets.size() / 4; ++t)
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) tp.push_back(look.row(tets[4 * t + a], tets[4 * t + b]));
+  d["tet_perm"] = np2(tp, 16);
+  d["cube_perm"] = np2(std::vector<unsigned>(), 64);
+}
+
+template <class T, class R>
+static py::dict flatten_nest_data(const BrillouinZoneNest3<T, R, double>& g) {
+  py::dict d;
+  flatten_data_common(g, d);
+  py::dict s = flatten_nest(g);
+  auto nv = s["node_vertices"].cast<py::array_t<unsigned>>();
+  std::vector<unsigned> tets(nv.data(), nv.data() + nv.size());
+  flatten_tet_perms(g.data(), tets, d);
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mesh (mesh.hpp, triangulation_layers.hpp): layers of tetrahedral meshes + layer-to-layer candidate lists
+// ---------------------------------------------------------------------------------------------
+template <class T, class R>
+static py::dict flatten_mesh(const BrillouinZoneMesh3<T, R, double>& g) {
+  py::dict d;
+  d["kind"] = "mesh";
+  d["bz"] = flatten_bz(g.get_brillouinzone());
+  const TetTri& tt = MeshSpy<T, R>::mesh_of(g);
+  const auto& layers = tt.*get(TetTriLayers());
+  const auto& conns = tt.*get(TetTriConns());
+  std::vector<unsigned> tet_off{0u}, vert_off{0u}, tets, conn_off{0u}, conn_idx;
+  std::vector<double> centres, radii, vol6, verts;
+  for (size_t l = 0; l < layers.size(); ++l) {
+    const auto& L = layers[l];
+    const auto& vpt = L.get_vertices_per_tetrahedron();
+    const auto& cc = L.get_circum_centres();
+    const auto& rr = L.get_circum_radii();
+    const auto& vp = L.get_vertex_positions();
+    for (ind_t t = 0; t < L.number_of_tetrahedra(); ++t) {
+      for (ind_t j = 0; j < 4; ++j) tets.push_back(vpt.val(t, j));
+      for (ind_t j = 0; j < 3; ++j) centres.push_back(cc.val(t, j));
+      radii.push_back(rr[t]);
+      vol6.push_back(6.0 * L.volume(t));  // triangulation_layers.hpp:267
+    }
+    for (ind_t v = 0; v < L.number_of_vertices(); ++v)
+      for (ind_t j = 0; j < 3; ++j) verts.push_back(vp.val(v, j));
+    tet_off.push_back(static_cast<unsigned>(radii.size()));
+    vert_off.push_back(static_cast<unsigned>(verts.size() / 3));
+    if (l + 1 < layers.size()) {
+      const auto& map = conns[l];
+      for (const auto& lst : map) {
+        for (auto x : lst) conn_idx.push_back(x);
+        conn_off.push_back(static_cast<unsigned>(conn_idx.size()));
+      }
+    }
+  }
+  d["n_layers"] = layers.size();
+  d["tet_offset"] = np1(tet_off);
+  d["vert_offset"] = np1(vert_off);
+  d["tets"] = np2(tets, 4);
+  d["centres"] = np2(centres, 3);
+  d["radii"] = np1(radii);
+  d["vol6"] = np1(vol6);
+  d["vertices"] = np2(verts, 3);
+  d["conn_offset"] = np1(conn_off);
+  d["conn_index"] = np1(conn_idx);
+  auto cfg = g.approx_config();
+  d["approx_digit"] = cfg.digit();
+  d["approx_direct"] = cfg.template direct<double>();
+  d["approx_reciprocal"] = cfg.template reciprocal<double>();
+  return d;
+}
+
+template <class T, class R>
+static py::dict flatten_mesh_data(const BrillouinZoneMesh3<T, R, double>& g) {
+  py::dict d;
+  flatten_data_common(g, d);
+  const TetTri& tt = MeshSpy<T, R>::mesh_of(g);
+  const auto& vpt = tt.get_vertices_per_tetrahedron();  // finest layer
+  std::vector<unsigned> tets;
+  for (ind_t t = 0; t < vpt.size(0); ++t)
+    for (ind_t j = 0; j < 4; ++j) tets.push_back(vpt.val(t, j));
+  flatten_tet_perms(g.data(), tets, d);
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // module
 // ---------------------------------------------------------------------------------------------
 template <class T, class R>
@@ -369,10 +530,23 @@ static void def_trellis(py::module& m) {
         "Data tables (values, vectors, permutations, gamma table) of a BZTrellisQ* object");
 }
 
+template <class T, class R>
+static void def_nest_mesh(py::module& m) {
+  using N = BrillouinZoneNest3<T, R, double>;
+  using M = BrillouinZoneMesh3<T, R, double>;
+  m.def("flatten", [](const N& g) { return flatten_nest(g); }, py::arg("grid"));
+  m.def("flatten_data", [](const N& g) { return flatten_nest_data(g); }, py::arg("grid"));
+  m.def("flatten", [](const M& g) { return flatten_mesh(g); }, py::arg("grid"));
+  m.def("flatten_data", [](const M& g) { return flatten_mesh_data(g); }, py::arg("grid"));
+}
+
 PYBIND11_MODULE(_bridge, m) {
   m.doc() = "brille_b200 bridge: flatten brille host objects into SoA tables";
   m.def("flatten_bz", &flatten_bz, py::arg("bz"));
   def_trellis<double, double>(m);
   def_trellis<double, cplx>(m);
   def_trellis<cplx, cplx>(m);
+  def_nest_mesh<double, double>(m);
+  def_nest_mesh<double, cplx>(m);
+  def_nest_mesh<cplx, cplx>(m);
 }

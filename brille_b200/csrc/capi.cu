@@ -132,7 +132,8 @@ struct b200_grid {
   BZDev h_bz;
   BZDev* d_bz = nullptr;
   double eps_w = 0, eps_o = 0;
-  TrellisDev tr{};
+  GridDev gd{};
+  uint32_t n_vertices = 0;
   DevPool structure_pool, data_pool;
   DataDev dd{};
   bool has_data = false;
@@ -288,7 +289,7 @@ static int build_bz(const b200_bz_tables_t* t, BZDev* d, double* eps_w, double* 
 }
 
 static int build_trellis(b200_grid* g, const b200_trellis_tables_t* t) {
-  TrellisDev& d = g->tr;
+  TrellisDev& d = g->gd.tr;
   DevPool& pool = g->structure_pool;
   std::vector<double> knots;
   for (int i = 0; i < 3; ++i) {
@@ -332,6 +333,85 @@ static int build_trellis(b200_grid* g, const b200_trellis_tables_t* t) {
   CU(pool.upload(t->poly_offsets, (size_t)t->n_polys + 1, &d.poly_offsets));
   CU(pool.upload(t->tet_vertices, (size_t)t->n_tets * 4, &d.tet_vertices));
   CU(pool.upload(tet_pack.data(), tet_pack.size(), &d.tet_pack));
+  g->n_vertices = t->n_vertices;
+  g->gd.cells.n_cubes = t->n_cubes;
+  g->gd.cells.n_tets = t->n_tets;
+  g->gd.cells.cube_vertices = d.cube_vertices;
+  g->gd.cells.tet_vertices = d.tet_vertices;
+  g->gd.cells.node_index = d.node_index;
+  return B200_OK;
+}
+
+// pack one tetrahedron: cx cy cz c3 | v0 v1 v2 v3 | vol6 | pad     (c3 = r^2 for trellis/nest, r for mesh)
+static void pack_tet(double* p, const double* c, double c3, const double* verts, const uint32_t* vi, double vol6) {
+  p[0] = c[0]; p[1] = c[1]; p[2] = c[2]; p[3] = c3;
+  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 3; ++k) p[4 + 3 * j + k] = verts[3 * (size_t)vi[j] + k];
+  p[16] = vol6;
+  p[17] = 0.0;
+}
+
+static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
+  NestDev& d = g->gd.ne;
+  DevPool& pool = g->structure_pool;
+  if (t->n_nodes < 1) return fail(B200_E_INVALID, "empty nest");
+  std::vector<double> pack((size_t)t->n_nodes * TET_PACK, 0.0);
+  for (size_t n = 1; n < t->n_nodes; ++n) {
+    const uint32_t* vi = t->node_vertices + 4 * n;
+    for (int j = 0; j < 4; ++j)
+      if (vi[j] >= t->n_vertices) return fail(B200_E_INVALID, "nest vertex index out of range");
+    const double* cr = t->node_circum + 4 * n;
+    pack_tet(&pack[n * TET_PACK], cr, cr[3] * cr[3], t->vertices, vi, t->node_volume[n] * 6.0);  // nest.hpp:81,119
+  }
+  for (size_t n = 0; n < t->n_nodes; ++n)
+    if (t->child_begin[n] > t->child_end[n] || t->child_end[n] > t->n_nodes) return fail(B200_E_INVALID, "nest child range out of bounds");
+  d.n_nodes = t->n_nodes;
+  d.n_vertices = t->n_vertices;
+  tol_pair(t->tolerance, t->digit, &d.rel, &d.abs_);
+  CU(pool.upload(pack.data(), pack.size(), &d.node_pack));
+  CU(pool.upload(t->node_vertices, (size_t)t->n_nodes * 4, &d.node_vertices));
+  CU(pool.upload(t->node_is_leaf, (size_t)t->n_nodes, &d.node_is_leaf));
+  CU(pool.upload(t->child_begin, (size_t)t->n_nodes, &d.child_begin));
+  CU(pool.upload(t->child_end, (size_t)t->n_nodes, &d.child_end));
+  g->n_vertices = t->n_vertices;
+  g->gd.cells.n_cubes = 0;
+  g->gd.cells.n_tets = t->n_nodes;  // bucket key = node index (only leaves ever receive points)
+  g->gd.cells.tet_vertices = d.node_vertices;
+  return B200_OK;
+}
+
+static int build_mesh(b200_grid* g, const b200_mesh_tables_t* t) {
+  MeshDev& d = g->gd.me;
+  DevPool& pool = g->structure_pool;
+  if (t->n_layers < 1) return fail(B200_E_INVALID, "Can not locate without triangulation");
+  const uint32_t L = t->n_layers, ntot = t->tet_offset[L];
+  std::vector<double> pack((size_t)ntot * TET_PACK, 0.0);
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t nvl = t->vert_offset[l + 1] - t->vert_offset[l];
+    const double* verts = t->vertices + 3 * (size_t)t->vert_offset[l];
+    for (uint32_t k = t->tet_offset[l]; k < t->tet_offset[l + 1]; ++k) {
+      const uint32_t* vi = t->tets + 4 * (size_t)k;
+      for (int j = 0; j < 4; ++j)
+        if (vi[j] >= nvl) return fail(B200_E_INVALID, "mesh vertex index out of range");
+      pack_tet(&pack[(size_t)k * TET_PACK], t->centres + 3 * (size_t)k, t->radii[k], verts, vi, t->vol6[k]);
+    }
+  }
+  const uint32_t nconn = L > 1 ? t->tet_offset[L - 1] : 0;
+  for (uint32_t l = 0; l + 1 < L; ++l)
+    for (uint32_t k = t->tet_offset[l]; k < t->tet_offset[l + 1]; ++k)
+      for (uint32_t c = t->conn_offset[k]; c < t->conn_offset[k + 1]; ++c)
+        if (t->conn_index[c] >= t->tet_offset[l + 2] - t->tet_offset[l + 1]) return fail(B200_E_INVALID, "mesh connection out of range");
+  d.n_layers = L;
+  d.n_tets_last = t->tet_offset[L] - t->tet_offset[L - 1];
+  CU(pool.upload(t->tet_offset, (size_t)L + 1, &d.tet_offset));
+  CU(pool.upload(pack.data(), pack.size(), &d.tet_pack));
+  CU(pool.upload(t->tets, (size_t)ntot * 4, &d.tets));
+  CU(pool.upload(t->conn_offset, (size_t)nconn + (L > 1 ? 1 : 0), &d.conn_offset));
+  CU(pool.upload(t->conn_index, L > 1 ? (size_t)t->conn_offset[nconn] : 0, &d.conn_index));
+  g->n_vertices = t->vert_offset[L] - t->vert_offset[L - 1];  // data live on the finest layer's vertices
+  g->gd.cells.n_cubes = 0;
+  g->gd.cells.n_tets = d.n_tets_last;
+  g->gd.cells.tet_vertices = d.tets + 4 * (size_t)t->tet_offset[L - 1];
   return B200_OK;
 }
 
@@ -390,7 +470,7 @@ static int fill_interp(b200_grid* g, const b200_interp_desc_t& s, uint32_t n_ver
 // ----------------------------------------------------------------------------------------------------
 extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void* structure, int device, b200_grid_t** out) {
   if (!bz || !structure || !out) return fail(B200_E_INVALID, "NULL argument");
-  if (kind != B200_GRID_TRELLIS) return fail(B200_E_UNSUPPORTED, "only trellis grids are implemented so far");
+  if (kind != B200_GRID_TRELLIS && kind != B200_GRID_NEST && kind != B200_GRID_MESH) return fail(B200_E_INVALID, "unknown grid kind");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -400,6 +480,7 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
   b200_grid* g = new b200_grid();
   g->device = device;
   g->kind = kind;
+  g->gd.kind = kind;
   cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
   int rc = build_bz(bz, &g->h_bz, &g->eps_w, &g->eps_o);
   if (rc == B200_OK) {
@@ -408,7 +489,11 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
     g->d_bz = const_cast<BZDev*>(p);
     if (ce != cudaSuccess) rc = fail(B200_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(ce));
   }
-  if (rc == B200_OK) rc = build_trellis(g, static_cast<const b200_trellis_tables_t*>(structure));
+  if (rc == B200_OK) {
+    if (kind == B200_GRID_TRELLIS) rc = build_trellis(g, static_cast<const b200_trellis_tables_t*>(structure));
+    else if (kind == B200_GRID_NEST) rc = build_nest(g, static_cast<const b200_nest_tables_t*>(structure));
+    else rc = build_mesh(g, static_cast<const b200_mesh_tables_t*>(structure));
+  }
   if (rc == B200_OK && cudaMalloc(&g->d_fail, 3 * sizeof(unsigned long long)) != cudaSuccess)
     rc = fail(B200_E_CUDA, "cudaMalloc failed");
   for (int s = 0; s < 2 && rc == B200_OK; ++s) {
@@ -456,8 +541,8 @@ extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
   CU(cudaDeviceSynchronize());
   g->data_pool.release();
   g->has_data = false;
-  if (t->n_vertices != g->tr.n_vertices)
-    return fail(B200_E_INVALID, "Provided " + std::to_string(t->n_vertices) + " arrays but " + std::to_string(g->tr.n_vertices) + " were expected!");
+  if (t->n_vertices != g->n_vertices)
+    return fail(B200_E_INVALID, "Provided " + std::to_string(t->n_vertices) + " arrays but " + std::to_string(g->n_vertices) + " were expected!");
   if (t->values.branches != t->vectors.branches)
     return fail(B200_E_INVALID, "Inconsistent values and vectors provided to DualInterpolator");  // interpolatordual.hpp:90-91
   DataDev d{};
@@ -469,12 +554,12 @@ extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
   d.n_perm_rows = t->n_perm_rows;
   if (t->n_perm_rows > 1) {
     if (!t->perm_rows || !t->cube_perm || !t->tet_perm) {
-      if (!t->perm_rows || (g->tr.n_cubes && !t->cube_perm) || (g->tr.n_tets && !t->tet_perm))
+      if (!t->perm_rows || (g->gd.cells.n_cubes && !t->cube_perm) || (g->gd.cells.n_tets && !t->tet_perm))
         return fail(B200_E_INVALID, "permutation rows given without the per-cell pair tables");
     }
     CU(g->data_pool.upload(t->perm_rows, (size_t)t->n_perm_rows * B, &d.perm_rows));
-    CU(g->data_pool.upload(t->cube_perm, (size_t)g->tr.n_cubes * 64, &d.cube_perm));
-    CU(g->data_pool.upload(t->tet_perm, (size_t)g->tr.n_tets * 16, &d.tet_perm));
+    CU(g->data_pool.upload(t->cube_perm, (size_t)g->gd.cells.n_cubes * 64, &d.cube_perm));
+    CU(g->data_pool.upload(t->tet_perm, (size_t)g->gd.cells.n_tets * 16, &d.tet_perm));
   }
   const int G = g->h_bz.n_ops;
   d.n_ops = (uint32_t)G;
@@ -530,8 +615,8 @@ static LocateIn as_input(const b200_grid* g, const LocateOut& lo) {
   LocateIn in{};
   in.q_ir = lo.q_ir; in.ridx = lo.ridx; in.invridx = lo.invridx; in.cell = lo.cell; in.tet = lo.tet;
   in.n_vert = lo.n_vert; in.vertex = lo.vertex; in.weight = lo.weight; in.slots = lo.slots; in.status = lo.status;
-  in.node_type = g->tr.node_type;
-  in.node_index = g->tr.node_index;
+  in.node_type = g->gd.tr.node_type;
+  in.node_index = g->gd.cells.node_index;
   return in;
 }
 
@@ -547,7 +632,7 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
                    bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
-  const uint32_t nb = g->tr.n_cubes + g->tr.n_tets + 1;
+  const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
   CU(ws.ensure(n, nb, g->chunk, (interp && g->dd.vectors.rot_kind >= 3) ? g->dd.vectors.no1 : 0u));
   CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
@@ -568,7 +653,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     CU(cudaMemsetAsync(ws.cell_count, 0, nb * sizeof(uint32_t), stream));
   }
   if (g->timing) cudaEventRecord(g->ev[0], stream);
-  CU(launch_locate(g->d_bz, g->tr, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
+  CU(launch_locate(g->d_bz, g->gd, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
   g->launches += 1;
   if (g->timing) cudaEventRecord(g->ev[1], stream);
   if (interp && cell) {
@@ -577,9 +662,9 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     if (g->timing) cudaEventRecord(g->ev[2], stream);
     CellArgs a{};
     a.dd = g->dd;
-    a.cube_vertices = g->tr.cube_vertices;
-    a.tet_vertices = g->tr.tet_vertices;
-    a.n_cubes = g->tr.n_cubes;
+    a.cube_vertices = g->gd.cells.cube_vertices;
+    a.tet_vertices = g->gd.cells.tet_vertices;
+    a.n_cubes = g->gd.cells.n_cubes;
     a.bk = ws.bk;
     a.weight = lo.weight;
     a.q_ir = lo.q_ir;

@@ -64,6 +64,43 @@ struct TrellisDev {
 };
 constexpr int TET_PACK = 18;
 
+// Nest: breadth-first flattened tetrahedron tree (nest.hpp); node 0 = root
+struct NestDev {
+  uint32_t n_nodes, n_vertices;
+  const double* node_pack;        // (n_nodes, 18): cx cy cz r^2 | v0 v1 v2 v3 (xyz) | 6*vol | pad
+  const uint32_t* node_vertices;  // (n_nodes, 4)
+  const uint8_t* node_is_leaf;
+  const uint32_t* child_begin;
+  const uint32_t* child_end;
+  double rel, abs_;               // approx tolerance pair of (approx_.reciprocal, approx_.digit)
+};
+
+// Mesh: layered tetrahedral meshes (triangulation_layers.hpp)
+struct MeshDev {
+  uint32_t n_layers, n_tets_last;
+  const uint32_t* tet_offset;     // (n_layers+1)
+  const double* tet_pack;         // (all tets, 18): cx cy cz radius | v0 v1 v2 v3 (xyz) | 6*vol | pad
+  const uint32_t* tets;           // (all tets, 4) layer-local vertex indices
+  const uint32_t* conn_offset;
+  const uint32_t* conn_index;
+};
+
+// what the bucketing / cell kernel needs to know about the cells of any grid kind
+struct CellsDev {
+  uint32_t n_cubes, n_tets;        // trellis: cubes + tetrahedra; nest: 0 + nodes; mesh: 0 + finest-layer tetrahedra
+  const uint32_t* cube_vertices;   // (n_cubes, 8)
+  const uint32_t* tet_vertices;    // (n_tets, 4)
+  const uint32_t* node_index;      // trellis only: payload index of a node
+};
+
+struct GridDev {
+  int kind;  // b200_grid_kind
+  TrellisDev tr;
+  NestDev ne;
+  MeshDev me;
+  CellsDev cells;
+};
+
 // per-Q result of the locate stage, consumed by the interpolation stage (SoA, all device pointers)
 struct LocateOut {
   double* q_ir;      // (n,3)
@@ -163,7 +200,7 @@ constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather 
 constexpr uint32_t MODE_NO_LOCATE = 4u;  // moveinto only (b200_moveinto)
 
 // launchers (one per .cu file)
-cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
+cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
                           double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
                           cudaStream_t stream);
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,

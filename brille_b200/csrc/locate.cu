@@ -410,6 +410,208 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   return st;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// orient3d of the vendored TetGen (lib/tetgen/predicates.cxx:1997-2050): the floating-point determinant in the
+// reference's operation order, returned as is when |det| > o3derrboundA*permanent; otherwise (the point is within
+// ~1e-15 of the plane) re-evaluated in double-double arithmetic where the reference switches to exact expansions.
+// ---------------------------------------------------------------------------------------------------
+struct dd_t { double hi, lo; };
+__device__ __forceinline__ dd_t dd_two_sum(double a, double b) { double s = a + b, bb = s - a; return {s, (a - (s - bb)) + (b - bb)}; }
+__device__ __forceinline__ dd_t dd_two_diff(double a, double b) { double s = a - b, bb = s - a; return {s, (a - (s - bb)) - (b + bb)}; }
+__device__ __forceinline__ dd_t dd_norm(double hi, double lo) { double s = hi + lo; return {s, lo - (s - hi)}; }
+__device__ __forceinline__ dd_t dd_add(dd_t a, dd_t b) {
+  dd_t s = dd_two_sum(a.hi, b.hi), t = dd_two_sum(a.lo, b.lo);
+  s.lo += t.hi;
+  s = dd_norm(s.hi, s.lo);
+  s.lo += t.lo;
+  return dd_norm(s.hi, s.lo);
+}
+__device__ __forceinline__ dd_t dd_neg(dd_t a) { return {-a.hi, -a.lo}; }
+__device__ __forceinline__ dd_t dd_mul(dd_t a, dd_t b) {
+  double p = a.hi * b.hi;
+  dd_t r = {p, __fma_rn(a.hi, b.hi, -p)};
+  r.lo += a.hi * b.lo + a.lo * b.hi;
+  return dd_norm(r.hi, r.lo);
+}
+__device__ __noinline__ double orient3d_dd(const double* pa, const double* pb, const double* pc, const double* pd) {
+  dd_t ax = dd_two_diff(pa[0], pd[0]), ay = dd_two_diff(pa[1], pd[1]), az = dd_two_diff(pa[2], pd[2]);
+  dd_t bx = dd_two_diff(pb[0], pd[0]), by = dd_two_diff(pb[1], pd[1]), bz = dd_two_diff(pb[2], pd[2]);
+  dd_t cx = dd_two_diff(pc[0], pd[0]), cy = dd_two_diff(pc[1], pd[1]), cz = dd_two_diff(pc[2], pd[2]);
+  dd_t t1 = dd_mul(az, dd_add(dd_mul(bx, cy), dd_neg(dd_mul(cx, by))));
+  dd_t t2 = dd_mul(bz, dd_add(dd_mul(cx, ay), dd_neg(dd_mul(ax, cy))));
+  dd_t t3 = dd_mul(cz, dd_add(dd_mul(ax, by), dd_neg(dd_mul(bx, ay))));
+  dd_t r = dd_add(dd_add(t1, t2), t3);
+  return r.hi + r.lo;
+}
+__device__ __forceinline__ double orient3d_tetgen(const double* pa, const double* pb, const double* pc, const double* pd) {
+  const double eps = 1.1102230246251565e-16;  // 2^-53 (exactinit, predicates.cxx:380-443)
+  const double o3derrboundA = (7.0 + 56.0 * eps) * eps;
+  const double adx = pa[0] - pd[0], ady = pa[1] - pd[1], adz = pa[2] - pd[2];
+  const double bdx = pb[0] - pd[0], bdy = pb[1] - pd[1], bdz = pb[2] - pd[2];
+  const double cdx = pc[0] - pd[0], cdy = pc[1] - pd[1], cdz = pc[2] - pd[2];
+  const double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, cdxady = cdx * ady, adxcdy = adx * cdy, adxbdy = adx * bdy, bdxady = bdx * ady;
+  const double det = adz * (bdxcdy - cdxbdy) + bdz * (cdxady - adxcdy) + cdz * (adxbdy - bdxady);
+  const double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * fabs(adz) + (fabs(cdxady) + fabs(adxcdy)) * fabs(bdz) +
+                           (fabs(adxbdy) + fabs(bdxady)) * fabs(cdz);
+  const double errbound = o3derrboundA * permanent;
+  if (det > errbound || -det > errbound) return det;
+  return orient3d_dd(pa, pb, pc, pd);
+}
+// the four barycentric weights of x in a packed tetrahedron (NestLeaf::weights nest.hpp:78-88, TetTriLayer::weights
+// triangulation_layers.hpp:265-288)
+__device__ __forceinline__ void tetgen_weights(const double* tp, const double* x, double* w) {
+  const double *p0 = tp + 4, *p1 = tp + 7, *p2 = tp + 10, *p3 = tp + 13;
+  const double vol6 = tp[16];
+  w[0] = orient3d_tetgen(x, p1, p2, p3) / vol6;
+  w[1] = orient3d_tetgen(p0, x, p2, p3) / vol6;
+  w[2] = orient3d_tetgen(p0, p1, x, p3) / vol6;
+  w[3] = orient3d_tetgen(p0, p1, p2, x) / vol6;
+}
+
+// emit the weights that are not ~0, tetrahedron corner order
+__device__ __forceinline__ void emit_tet(EmitOut& e, const uint32_t* vip, const double* w, double rel, double abs_) {
+  const uint4 vi4 = *reinterpret_cast<const uint4*>(vip);
+  bool keep[4];
+  bool all = true;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    keep[j] = !approx_eq(w[j], 0.0, rel, abs_);
+    all &= keep[j];
+  }
+  if (all) {
+    reinterpret_cast<uint4*>(e.v)[0] = vi4;
+    reinterpret_cast<uint4*>(e.v)[1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    double2* wo = reinterpret_cast<double2*>(e.w);
+    wo[0] = make_double2(w[0], w[1]);
+    wo[1] = make_double2(w[2], w[3]);
+    wo[2] = make_double2(0.0, 0.0);
+    wo[3] = make_double2(0.0, 0.0);
+    e.n = 4;
+    e.slots = 0x03020100ull;
+  } else {
+    const uint32_t vi[4] = {vi4.x, vi4.y, vi4.z, vi4.w};
+    emit_compact(e, vi, w, keep, 4, false);
+  }
+}
+
+// Nest::indices_weights (nest.hpp:163-222): breadth-first over the nodes that contain x; among the containing
+// leaves the LAST one whose weights are all > 0 wins, else the first; ~0 weights are folded into the largest one
+__device__ __forceinline__ uint32_t nest_locate(const NestDev& t, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  cell = 0xffffffffu;
+  constexpr int QCAP = 32;  // ranges of children waiting to be visited (one per containing inner node)
+  uint32_t qb[QCAP], qe[QCAP];
+  int head = 0, tail = 0;
+  qb[0] = t.child_begin[0];
+  qe[0] = t.child_end[0];
+  tail = 1;
+  int nsol = 0;
+  bool have_best = false, overflow = false;
+  uint32_t first_node = 0, best_node = 0;
+  double fw[4], bw[4], w[4];
+  while (head < tail) {
+    const uint32_t b = qb[head % QCAP], en = qe[head % QCAP];
+    ++head;
+    for (uint32_t node = b; node < en; ++node) {
+      const double* tp = t.node_pack + (size_t)TET_PACK * node;
+      const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+      const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+      const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
+      const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
+      if (!(d2 < c23.y || approx_eq(d2, c23.y, t.rel, t.abs_))) continue;  // might_contain (:114-122) -> weights -1
+      tetgen_weights(tp, x, w);
+      bool ok = true;  // none_negative (:43-48)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok &= !(w[j] < 0.0 && !approx_eq(w[j], 0.0, t.rel, t.abs_));
+      if (!ok) continue;
+      if (t.node_is_leaf[node]) {
+        if (nsol == 0) {
+          first_node = node;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fw[j] = w[j];
+        }
+        if (w[0] > 0.0 && w[1] > 0.0 && w[2] > 0.0 && w[3] > 0.0) {
+          best_node = node;
+          have_best = true;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bw[j] = w[j];
+        }
+        ++nsol;
+      } else {
+        if (tail - head >= QCAP) { overflow = true; continue; }
+        qb[tail % QCAP] = t.child_begin[node];
+        qe[tail % QCAP] = t.child_end[node];
+        ++tail;
+      }
+    }
+  }
+  if (nsol == 0 || overflow) return B200_ST_NOT_FOUND;
+  uint32_t node = first_node;
+  double sw[4] = {fw[0], fw[1], fw[2], fw[3]};
+  if (nsol > 1 && have_best) {
+    node = best_node;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sw[j] = bw[j];
+  }
+  for (int i = 0; i < 4; ++i)  // fold (:203-217)
+    if (approx_eq(sw[i], 0.0, t.rel, t.abs_)) {
+      int max_at = 0;
+      for (int j = 0; j < 4; ++j)
+        if (!approx_eq(sw[j], 0.0, t.rel, t.abs_) && sw[j] > sw[max_at]) max_at = j;
+      sw[max_at] += sw[i];
+    }
+  emit_tet(e, t.node_vertices + 4 * (size_t)node, sw, t.rel, t.abs_);
+  cell = node;
+  tet = (int)node;
+  return e.n < 1 ? (uint32_t)B200_ST_NOT_FOUND : 0u;
+}
+
+// TetTri::locate (triangulation_layers.hpp:401-417): first containing tetrahedron of the coarsest layer, then of the
+// candidate list connections[l-1][idx] in every finer layer
+__device__ __forceinline__ bool mesh_try(const BZDev& bz, const double* tp, const double* x, double* w) {
+  const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+  const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+  const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
+  const double nrm = sqrt(((0.0 + d0 * d0) + d1 * d1) + d2v * d2v);  // unsafe_might_contain (:254-256)
+  if (!(approx_eq(nrm, c23.y, bz.def_rel, bz.def_abs) || nrm < c23.y)) return false;
+  tetgen_weights(tp, x, w);
+  bool ok = true;  // unsafe_contains (:261-264)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ok &= (w[j] > 0.0 || approx_eq(w[j], 0.0, bz.def_rel, bz.def_abs));
+  return ok;
+}
+__device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const MeshDev& t, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  cell = 0xffffffffu;
+  double w[4];
+  uint32_t idx = 0xffffffffu;
+  for (uint32_t layer = 0; layer < t.n_layers; ++layer) {
+    uint32_t found = 0xffffffffu;
+    const uint32_t base = t.tet_offset[layer];
+    if (layer == 0) {
+      const uint32_t nt = t.tet_offset[1] - base;
+      for (uint32_t k = 0; k < nt; ++k)
+        if (mesh_try(bz, t.tet_pack + (size_t)TET_PACK * (base + k), x, w)) { found = k; break; }
+    } else {
+      const uint32_t c = t.tet_offset[layer - 1] + idx;
+      for (uint32_t k = t.conn_offset[c]; k < t.conn_offset[c + 1]; ++k) {
+        const uint32_t cand = t.conn_index[k];
+        if (mesh_try(bz, t.tet_pack + (size_t)TET_PACK * (base + cand), x, w)) { found = cand; break; }
+      }
+    }
+    if (found == 0xffffffffu) return B200_ST_NOT_FOUND;
+    idx = found;
+  }
+  emit_tet(e, t.tets + 4 * (size_t)(t.tet_offset[t.n_layers - 1] + idx), w, bz.def_rel, bz.def_abs);
+  cell = idx;
+  tet = (int)idx;
+  return e.n < 1 ? (uint32_t)B200_ST_NOT_FOUND : 0u;
+}
+
 // in-order scan with the reference arithmetic (bz_move.cpp:262-285); taken by points within tolerance of a wedge
 // plane and by Brillouin zones for which the sign-pattern lookup is not available
 __device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, int& invridx) {
@@ -438,9 +640,11 @@ __device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, i
   return false;
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(128)
-k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict__ Q, size_t n, uint32_t mode,
+k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q, size_t n, uint32_t mode,
          double eps_w, double eps_o, LocateOut out, unsigned long long* __restrict__ fail_count) {
+  const TrellisDev& tr = gd.tr;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BZDev& bz = *reinterpret_cast<BZDev*>(smem_raw);
   double* knots = reinterpret_cast<double*>(smem_raw + ((sizeof(BZDev) + 15) / 16) * 16);
@@ -448,7 +652,7 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
     const uint32_t* src = reinterpret_cast<const uint32_t*>(bzg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&bz);
     for (int i = threadIdx.x; i < (int)(sizeof(BZDev) / 4); i += blockDim.x) dst[i] = src[i];
-    const int nk = (mode & MODE_NO_LOCATE) ? 0 : tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2];
+    const int nk = (KIND != B200_GRID_TRELLIS || (mode & MODE_NO_LOCATE)) ? 0 : tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2];
     for (int i = threadIdx.x; i < nk; i += blockDim.x) knots[i] = tr.knots[i];
   }
   __syncthreads();
@@ -511,7 +715,9 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
       EmitOut e;
       e.v = out.vertex + 8 * i;
       e.w = out.weight + 8 * i;
-      st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
+      if (KIND == B200_GRID_TRELLIS) st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
+      else if (KIND == B200_GRID_NEST) st |= nest_locate(gd.ne, x, e, cell, tet);
+      else st |= mesh_locate(bz, gd.me, x, e, cell, tet);
       if (e.n == 0) {  // not found: defined contents for the row
         for (int j = 0; j < 8; ++j) {
           e.v[j] = 0xffffffffu;
@@ -528,10 +734,10 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
     if (out.key) {
       // bucket for the cell-batched interpolation: only "generic" points (every corner of the cell carries weight, i.e.
       // the pivot is the cell's first emitted corner) share a bucket with their cell
-      uint32_t key = tr.n_cubes + tr.n_tets;
+      uint32_t key = gd.cells.n_cubes + gd.cells.n_tets;
       if (!(mode & MODE_NO_LOCATE) && !(st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND))) {
-        if (tet >= 0 && n_emit == 4) key = tr.n_cubes + (uint32_t)tet;
-        else if (tet < 0 && n_emit == 8) key = tr.node_index[cell];
+        if (tet >= 0 && n_emit == 4) key = gd.cells.n_cubes + (uint32_t)tet;
+        else if (tet < 0 && n_emit == 8) key = gd.cells.node_index[cell];
       }
       out.key[i] = key;
       out.rank[i] = atomicAdd(out.cell_count + key, 1u);
@@ -546,27 +752,39 @@ k_locate(const BZDev* __restrict__ bzg, TrellisDev tr, const double* __restrict_
   if (f_find) atomicAdd(fail_count + 2, f_find);
 }
 
-size_t locate_smem_bytes(const TrellisDev& tr, uint32_t mode) {
-  size_t nk = (mode & MODE_NO_LOCATE) ? 0 : (size_t)(tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2]);
+static size_t locate_smem_bytes(const GridDev& gd, uint32_t mode) {
+  const TrellisDev& tr = gd.tr;
+  size_t nk = (gd.kind != B200_GRID_TRELLIS || (mode & MODE_NO_LOCATE)) ? 0 : (size_t)(tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2]);
   return ((sizeof(BZDev) + 15) / 16) * 16 + nk * sizeof(double);
 }
 
-cudaError_t launch_locate(const BZDev* bzg, const TrellisDev& tr, const double* Q, size_t n, uint32_t mode, double eps_w,
-                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
-                          cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
+template <int KIND>
+static cudaError_t launch_kind(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
+                               double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
+                               cudaStream_t stream) {
   const int threads = 128;
-  size_t smem = locate_smem_bytes(tr, mode);
+  const size_t smem = locate_smem_bytes(gd, mode);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_locate<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
   size_t want = (n + threads - 1) / threads;
   size_t cap = (size_t)sm_count * 16;  // grid-stride: a multiple of the SM count
   int blocks = (int)(want < cap ? want : cap);
-  k_locate<<<blocks, threads, smem, stream>>>(bzg, tr, Q, n, mode, eps_w, eps_o, out, fail_count);
+  k_locate<KIND><<<blocks, threads, smem, stream>>>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count);
   return cudaGetLastError();
+}
+
+cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
+                          double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
+                          cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  switch (gd.kind) {
+    case B200_GRID_TRELLIS: return launch_kind<B200_GRID_TRELLIS>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    case B200_GRID_NEST: return launch_kind<B200_GRID_NEST>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    default: return launch_kind<B200_GRID_MESH>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+  }
 }
 
 }  // namespace b200

@@ -71,12 +71,8 @@ class B200Grid:
         if structure is None:
             structure = _bridge().flatten(host_grid)
         self._structure = structure
-        self._kind = self._KINDS[str(structure["kind"])]
         self._bz_tables = T.pack_bz(structure["bz"])
-        if self._kind == T.GRID_TRELLIS:
-            self._struct_tables = T.pack_trellis(structure)
-        else:
-            raise capi.B200Error(T.E_UNSUPPORTED, f"grid kind {structure['kind']!r} not implemented")
+        self._kind, self._struct_tables = T.pack_structure(structure)
         h = C.c_void_p()
         capi.check(
             capi.lib().b200_grid_create(

@@ -82,6 +82,37 @@ class TrellisTables(C.Structure):
     ]
 
 
+class NestTables(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint32),
+        ("node_vertices", c_uint32_p),
+        ("node_circum", c_double_p),
+        ("node_volume", c_double_p),
+        ("node_is_leaf", c_uint8_p),
+        ("child_begin", c_uint32_p),
+        ("child_end", c_uint32_p),
+        ("n_vertices", C.c_uint32),
+        ("vertices", c_double_p),
+        ("tolerance", C.c_double),
+        ("digit", C.c_int32),
+    ]
+
+
+class MeshTables(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_uint32),
+        ("tet_offset", c_uint32_p),
+        ("vert_offset", c_uint32_p),
+        ("tets", c_uint32_p),
+        ("centres", c_double_p),
+        ("radii", c_double_p),
+        ("vol6", c_double_p),
+        ("vertices", c_double_p),
+        ("conn_offset", c_uint32_p),
+        ("conn_index", c_uint32_p),
+    ]
+
+
 class InterpDesc(C.Structure):
     _fields_ = [
         ("data", C.c_void_p),
@@ -214,6 +245,69 @@ def pack_trellis(d) -> TrellisTables:
     return t
 
 
+def pack_nest(d) -> NestTables:
+    """bridge ``flatten`` dictionary (kind == 'nest') -> ``b200_nest_tables_t``"""
+    t = NestTables()
+    nv = _arr(d["node_vertices"], np.uint32).reshape(-1, 4)
+    nc = _arr(d["node_circum"], np.float64).reshape(-1, 4)
+    vol = _arr(d["node_volume"], np.float64)
+    leaf = _arr(d["node_is_leaf"], np.uint8)
+    cb = _arr(d["child_begin"], np.uint32)
+    ce = _arr(d["child_end"], np.uint32)
+    vx = _arr(d["vertices"], np.float64).reshape(-1, 3)
+    t.n_nodes = int(vol.size)
+    t.node_vertices = _ptr(nv, c_uint32_p)
+    t.node_circum = _ptr(nc, c_double_p)
+    t.node_volume = _ptr(vol, c_double_p)
+    t.node_is_leaf = _ptr(leaf, c_uint8_p)
+    t.child_begin = _ptr(cb, c_uint32_p)
+    t.child_end = _ptr(ce, c_uint32_p)
+    t.n_vertices = int(vx.shape[0])
+    t.vertices = _ptr(vx, c_double_p)
+    t.tolerance = float(d["approx_reciprocal"])
+    t.digit = int(d["approx_digit"])
+    t._keep = [nv, nc, vol, leaf, cb, ce, vx]
+    return t
+
+
+def pack_mesh(d) -> MeshTables:
+    """bridge ``flatten`` dictionary (kind == 'mesh') -> ``b200_mesh_tables_t``"""
+    t = MeshTables()
+    to = _arr(d["tet_offset"], np.uint32)
+    vo = _arr(d["vert_offset"], np.uint32)
+    tets = _arr(d["tets"], np.uint32).reshape(-1, 4)
+    cen = _arr(d["centres"], np.float64).reshape(-1, 3)
+    rad = _arr(d["radii"], np.float64)
+    vol6 = _arr(d["vol6"], np.float64)
+    vx = _arr(d["vertices"], np.float64).reshape(-1, 3)
+    co = _arr(d["conn_offset"], np.uint32)
+    ci = _arr(d["conn_index"], np.uint32)
+    t.n_layers = int(d["n_layers"])
+    t.tet_offset = _ptr(to, c_uint32_p)
+    t.vert_offset = _ptr(vo, c_uint32_p)
+    t.tets = _ptr(tets, c_uint32_p)
+    t.centres = _ptr(cen, c_double_p)
+    t.radii = _ptr(rad, c_double_p)
+    t.vol6 = _ptr(vol6, c_double_p)
+    t.vertices = _ptr(vx, c_double_p)
+    t.conn_offset = _ptr(co, c_uint32_p)
+    t.conn_index = _ptr(ci, c_uint32_p)
+    t._keep = [to, vo, tets, cen, rad, vol6, vx, co, ci]
+    return t
+
+
+def pack_structure(d):
+    """dispatch on the bridge dictionary's ``kind`` -> (grid kind, packed structure tables)"""
+    kind = str(d["kind"])
+    if kind == "trellis":
+        return GRID_TRELLIS, pack_trellis(d)
+    if kind == "nest":
+        return GRID_NEST, pack_nest(d)
+    if kind == "mesh":
+        return GRID_MESH, pack_mesh(d)
+    raise ValueError(f"unknown grid kind {kind!r}")
+
+
 def _pack_interp(desc: InterpDesc, d, prefix, keep):
     data = np.asarray(d[f"{prefix}_data"])
     is_complex = np.iscomplexobj(data)
@@ -245,6 +339,8 @@ def pack_data(d) -> DataTables:
     t.perm_rows = _ptr(rows, c_uint32_p)
     if int(d.get("perm_nonidentity", 0)):
         for name in ("cube_perm", "tet_perm"):
+            if name not in d:
+                continue
             a = _arr(d[name], np.uint32)
             keep.append(a)
             setattr(t, name, _ptr(a, c_uint32_p))

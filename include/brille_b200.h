@@ -116,6 +116,41 @@ typedef struct b200_trellis_tables {
   const double* vertices;       /* (n_vertices,3) Cartesian                                                       */
 } b200_trellis_tables_t;
 
+/* ---- tables: Nest structure (nest.hpp) ------------------------------------------------------------------------
+ * The tetrahedron tree flattened breadth-first: node 0 is the root (no tetrahedron of its own); the children of
+ * node i are the nodes [child_begin[i], child_end[i]) in the order NestNode::branches() holds them.                */
+typedef struct b200_nest_tables {
+  uint32_t n_nodes;
+  const uint32_t* node_vertices; /* (n_nodes,4) NestLeaf::vi                          nest.hpp:61                  */
+  const double* node_circum;     /* (n_nodes,4) NestLeaf::centre_radius (xyz + radius) nest.hpp:62                  */
+  const double* node_volume;     /* (n_nodes)   NestLeaf::volume_                      nest.hpp:63                  */
+  const uint8_t* node_is_leaf;   /* (n_nodes)   NestNode::is_leaf()                    nest.hpp:143                 */
+  const uint32_t* child_begin;   /* (n_nodes) */
+  const uint32_t* child_end;     /* (n_nodes) */
+  uint32_t n_vertices;
+  const double* vertices;        /* (n_vertices,3) Nest::vertices_ (all vertices), Cartesian                        */
+  double tolerance;              /* approx_.reciprocal<double>()                       nest.hpp:343-345,399-400     */
+  int32_t digit;                 /* approx_.digit()                                                                 */
+} b200_nest_tables_t;
+
+/* ---- tables: Mesh structure (mesh.hpp, triangulation_layers.hpp) ----------------------------------------------
+ * TetTri: n_layers tetrahedral meshes, coarse to fine; tetrahedron t of layer l is row tet_offset[l]+t of the
+ * per-tetrahedron arrays and its vertex indices are local to layer l (row vert_offset[l]+v of `vertices`).
+ * connections[l][t] (candidate tetrahedra of layer l+1 for tetrahedron t of layer l) is
+ * conn_index[conn_offset[c] .. conn_offset[c+1]) with c = tet_offset[l]+t for l < n_layers-1.                     */
+typedef struct b200_mesh_tables {
+  uint32_t n_layers;
+  const uint32_t* tet_offset;    /* (n_layers+1) */
+  const uint32_t* vert_offset;   /* (n_layers+1) */
+  const uint32_t* tets;          /* (tet_offset[n_layers],4) vertices_per_tetrahedron   triangulation_layers.hpp:51 */
+  const double* centres;         /* (.,3) circum_centres                                                            */
+  const double* radii;           /* (.)   circum_radii                                                              */
+  const double* vol6;            /* (.)   6.0*volume(tet)                               triangulation_layers.hpp:267 */
+  const double* vertices;        /* (vert_offset[n_layers],3) vertex_positions of every layer                       */
+  const uint32_t* conn_offset;   /* (tet_offset[n_layers-1]+1) CSR offsets                                          */
+  const uint32_t* conn_index;    /* layer-local tetrahedron indices of the next finer layer                         */
+} b200_mesh_tables_t;
+
 /* ---- tables: interpolation data (DualInterpolator, PermutationTable, GammaTable) ---------------------- */
 typedef struct b200_interp_desc {
   const void* data;       /* (n_vertices, branches*span) row-major; double or complex<double> (re,im pairs)       */

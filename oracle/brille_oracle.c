@@ -430,6 +430,221 @@ static uint32_t trellis_locate(const b200_trellis_tables_t* t, const double* x, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * orient3d of the vendored TetGen (lib/tetgen/predicates.cxx:1997-2050, Shewchuk's adaptive predicate).
+ * Fast path: the reference's floating-point determinant in its own operation order, returned as is when
+ * |det| > o3derrboundA * permanent (predicates.cxx:436-443: o3derrboundA = (7 + 56 eps) eps with eps = 2^-53).
+ * Slow path: the reference refines the value in exact expansion arithmetic (orient3dadapt).  Here the determinant
+ * is re-evaluated in double-double arithmetic (error ~1e-31 * permanent, far below every tolerance brille
+ * applies to the result: the weights are only ever compared through approx_float with |w| <= 5e-15).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { double hi, lo; } dd_t;
+static dd_t dd_two_sum(double a, double b) {
+  double s = a + b, bb = s - a;
+  dd_t r = {s, (a - (s - bb)) + (b - bb)};
+  return r;
+}
+static dd_t dd_two_diff(double a, double b) {
+  double s = a - b, bb = s - a;
+  dd_t r = {s, (a - (s - bb)) - (b + bb)};
+  return r;
+}
+static dd_t dd_two_prod(double a, double b) {
+  double p = a * b;
+  dd_t r = {p, fma(a, b, -p)};
+  return r;
+}
+static dd_t dd_norm(double hi, double lo) {
+  double s = hi + lo;
+  dd_t r = {s, lo - (s - hi)};
+  return r;
+}
+static dd_t dd_add(dd_t a, dd_t b) {
+  dd_t s = dd_two_sum(a.hi, b.hi), t = dd_two_sum(a.lo, b.lo);
+  s.lo += t.hi;
+  s = dd_norm(s.hi, s.lo);
+  s.lo += t.lo;
+  return dd_norm(s.hi, s.lo);
+}
+static dd_t dd_neg(dd_t a) { dd_t r = {-a.hi, -a.lo}; return r; }
+static dd_t dd_mul(dd_t a, dd_t b) {
+  dd_t p = dd_two_prod(a.hi, b.hi);
+  p.lo += a.hi * b.lo + a.lo * b.hi;
+  return dd_norm(p.hi, p.lo);
+}
+static double orient3d_tetgen(const double* pa, const double* pb, const double* pc, const double* pd) {
+  const double eps = 1.1102230246251565e-16; /* 2^-53, exactinit(): predicates.cxx:380-443 */
+  const double o3derrboundA = (7.0 + 56.0 * eps) * eps;
+  double adx = pa[0] - pd[0], ady = pa[1] - pd[1], adz = pa[2] - pd[2];
+  double bdx = pb[0] - pd[0], bdy = pb[1] - pd[1], bdz = pb[2] - pd[2];
+  double cdx = pc[0] - pd[0], cdy = pc[1] - pd[1], cdz = pc[2] - pd[2];
+  double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, cdxady = cdx * ady, adxcdy = adx * cdy, adxbdy = adx * bdy, bdxady = bdx * ady;
+  double det = adz * (bdxcdy - cdxbdy) + bdz * (cdxady - adxcdy) + cdz * (adxbdy - bdxady);
+  double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * fabs(adz) + (fabs(cdxady) + fabs(adxcdy)) * fabs(bdz) +
+                     (fabs(adxbdy) + fabs(bdxady)) * fabs(cdz);
+  double errbound = o3derrboundA * permanent;
+  if (det > errbound || -det > errbound) return det;
+  /* double-double re-evaluation on the exact differences */
+  dd_t ax = dd_two_diff(pa[0], pd[0]), ay = dd_two_diff(pa[1], pd[1]), az = dd_two_diff(pa[2], pd[2]);
+  dd_t bx = dd_two_diff(pb[0], pd[0]), by = dd_two_diff(pb[1], pd[1]), bzz = dd_two_diff(pb[2], pd[2]);
+  dd_t cx = dd_two_diff(pc[0], pd[0]), cy = dd_two_diff(pc[1], pd[1]), cz = dd_two_diff(pc[2], pd[2]);
+  dd_t t1 = dd_mul(az, dd_add(dd_mul(bx, cy), dd_neg(dd_mul(cx, by))));
+  dd_t t2 = dd_mul(bzz, dd_add(dd_mul(cx, ay), dd_neg(dd_mul(ax, cy))));
+  dd_t t3 = dd_mul(cz, dd_add(dd_mul(ax, by), dd_neg(dd_mul(bx, ay))));
+  dd_t r = dd_add(dd_add(t1, t2), t3);
+  return r.hi + r.lo;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Nest point location  (nest.hpp:59-123 NestLeaf, :163-222 NestNode::indices_weights)
+ * ---------------------------------------------------------------------------------------------- */
+static int nest_weights(const b200_nest_tables_t* t, uint32_t node, const double* x, tol_t tol, double* w) {
+  /* NestLeaf::weights (:78-88): {-1,-1,-1,-1} unless might_contain (:114-122) */
+  const double* cr = t->node_circum + 4 * (size_t)node;
+  double d[3] = {x[0] - cr[0], x[1] - cr[1], x[2] - cr[2]};
+  double d2 = 0.0, r2 = cr[3] * cr[3];
+  for (int i = 0; i < 3; ++i) d2 += d[i] * d[i];
+  w[0] = w[1] = w[2] = w[3] = -1.0;
+  if (d2 < r2 || approx(d2, r2, tol)) {
+    const uint32_t* vi = t->node_vertices + 4 * (size_t)node;
+    const double* p0 = t->vertices + 3 * (size_t)vi[0];
+    const double* p1 = t->vertices + 3 * (size_t)vi[1];
+    const double* p2 = t->vertices + 3 * (size_t)vi[2];
+    const double* p3 = t->vertices + 3 * (size_t)vi[3];
+    double vol6 = t->node_volume[node] * 6.0;
+    w[0] = orient3d_tetgen(x, p1, p2, p3) / vol6;
+    w[1] = orient3d_tetgen(p0, x, p2, p3) / vol6;
+    w[2] = orient3d_tetgen(p0, p1, x, p3) / vol6;
+    w[3] = orient3d_tetgen(p0, p1, p2, x) / vol6;
+  }
+  /* none_negative (:43-48) */
+  for (int j = 0; j < 4; ++j)
+    if (w[j] < 0 && !approx(w[j], 0.0, tol)) return 0;
+  return 1;
+}
+
+static uint32_t nest_locate(const b200_nest_tables_t* t, const double* x, iw_t* iw) {
+  tol_t tol = make_tol(t->tolerance, t->digit);
+  iw->n = 0;
+  iw->tet = -1;
+  iw->cell = 0xffffffffu;
+  /* breadth-first over containing nodes (the reference's std::deque, :175-192) */
+  uint32_t cap = 64, head = 0, tail = 0;
+  uint32_t* queue = (uint32_t*)malloc(sizeof(uint32_t) * cap);
+  for (uint32_t c = t->child_begin[0]; c < t->child_end[0]; ++c) {
+    if (tail == cap) queue = (uint32_t*)realloc(queue, sizeof(uint32_t) * (cap *= 2));
+    queue[tail++] = c;
+  }
+  int nsol = 0;
+  uint32_t first_node = 0, best_node = 0;
+  double first_w[4], best_w[4], w[4];
+  int have_best = 0;
+  while (head < tail) {
+    uint32_t node = queue[head++];
+    if (nest_weights(t, node, x, tol, w)) {
+      if (t->node_is_leaf[node]) {
+        if (nsol == 0) { first_node = node; memcpy(first_w, w, sizeof(w)); }
+        /* "best": the LAST solution whose weights are all > 0, else the first (:195-201) */
+        int all_pos = 1;
+        for (int j = 0; j < 4; ++j) if (w[j] <= 0) all_pos = 0;
+        if (all_pos) { best_node = node; memcpy(best_w, w, sizeof(w)); have_best = 1; }
+        ++nsol;
+      } else {
+        for (uint32_t c = t->child_begin[node]; c < t->child_end[node]; ++c) {
+          if (tail == cap) queue = (uint32_t*)realloc(queue, sizeof(uint32_t) * (cap *= 2));
+          queue[tail++] = c;
+        }
+      }
+    }
+  }
+  free(queue);
+  if (nsol == 0) return B200_ST_NOT_FOUND;
+  uint32_t node = first_node;
+  double sw[4];
+  memcpy(sw, first_w, sizeof(sw));
+  if (nsol > 1 && have_best) { node = best_node; memcpy(sw, best_w, sizeof(sw)); }
+  /* fold ~0 weights into the largest (:203-217) */
+  for (int i = 0; i < 4; ++i)
+    if (approx(sw[i], 0.0, tol)) {
+      int max_at = 0;
+      for (int j = 0; j < 4; ++j)
+        if (!approx(sw[j], 0.0, tol) && sw[j] > sw[max_at]) max_at = j;
+      sw[max_at] += sw[i];
+    }
+  const uint32_t* vi = t->node_vertices + 4 * (size_t)node;
+  for (int i = 0; i < 4; ++i)
+    if (!approx(sw[i], 0.0, tol)) {
+      iw->vertex[iw->n] = vi[i];
+      iw->weight[iw->n] = sw[i];
+      iw->slot[iw->n] = (uint8_t)i;
+      ++iw->n;
+    }
+  iw->cell = node;
+  iw->tet = (int32_t)node;
+  return iw->n < 1 ? B200_ST_NOT_FOUND : 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Mesh point location  (triangulation_layers.hpp:177-189 unsafe_locate, :254-288, :401-417 TetTri::locate)
+ * ---------------------------------------------------------------------------------------------- */
+static int mesh_try(const b200_mesh_tables_t* t, uint32_t layer, uint32_t tet, const double* x, double* w) {
+  tol_t def = make_tol(0.0, 1);
+  size_t g = (size_t)t->tet_offset[layer] + tet;
+  /* unsafe_might_contain (:254-256): norm(x - centre) <= radius with the default tolerance */
+  const double* c = t->centres + 3 * g;
+  double d[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
+  double s = 0.0;
+  for (int i = 0; i < 3; ++i) s += d[i] * d[i];
+  double nrm = sqrt(s), r = t->radii[g];
+  if (!(approx(nrm, r, def) || nrm < r)) return 0;
+  const uint32_t* vi = t->tets + 4 * g;
+  const double* vb = t->vertices + 3 * (size_t)t->vert_offset[layer];
+  const double *p0 = vb + 3 * (size_t)vi[0], *p1 = vb + 3 * (size_t)vi[1], *p2 = vb + 3 * (size_t)vi[2], *p3 = vb + 3 * (size_t)vi[3];
+  double vol6 = t->vol6[g];
+  w[0] = orient3d_tetgen(x, p1, p2, p3) / vol6; /* weights (:265-288) */
+  w[1] = orient3d_tetgen(p0, x, p2, p3) / vol6;
+  w[2] = orient3d_tetgen(p0, p1, x, p3) / vol6;
+  w[3] = orient3d_tetgen(p0, p1, p2, x) / vol6;
+  for (int j = 0; j < 4; ++j)
+    if (!(w[j] > 0.0 || approx(w[j], 0.0, def))) return 0; /* unsafe_contains (:261-264) */
+  return 1;
+}
+
+static uint32_t mesh_locate(const b200_mesh_tables_t* t, const double* x, iw_t* iw) {
+  tol_t def = make_tol(0.0, 1);
+  iw->n = 0;
+  iw->tet = -1;
+  iw->cell = 0xffffffffu;
+  double w[4];
+  uint32_t idx = 0xffffffffu;
+  for (uint32_t layer = 0; layer < t->n_layers; ++layer) {
+    uint32_t found = 0xffffffffu;
+    if (layer == 0) {
+      uint32_t nt = t->tet_offset[1] - t->tet_offset[0];
+      for (uint32_t k = 0; k < nt && found == 0xffffffffu; ++k)
+        if (mesh_try(t, 0, k, x, w)) found = k;
+    } else {
+      size_t c = (size_t)t->tet_offset[layer - 1] + idx;
+      for (uint32_t k = t->conn_offset[c]; k < t->conn_offset[c + 1] && found == 0xffffffffu; ++k)
+        if (mesh_try(t, layer, t->conn_index[k], x, w)) found = t->conn_index[k];
+    }
+    if (found == 0xffffffffu) return B200_ST_NOT_FOUND; /* the reference indexes connections[..][nTetrahedra]: undefined */
+    idx = found;
+  }
+  uint32_t last = t->n_layers - 1;
+  const uint32_t* vi = t->tets + 4 * ((size_t)t->tet_offset[last] + idx);
+  for (int i = 0; i < 4; ++i)
+    if (!approx(w[i], 0.0, def)) {
+      iw->vertex[iw->n] = vi[i];
+      iw->weight[iw->n] = w[i];
+      iw->slot[iw->n] = (uint8_t)i;
+      ++iw->n;
+    }
+  iw->cell = idx;
+  iw->tet = (int32_t)idx;
+  return iw->n < 1 ? B200_ST_NOT_FOUND : 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * interpolation  (interpolatordual.hpp:149-155,374-382; interpolator_at.tpp:91-127)
  * ---------------------------------------------------------------------------------------------- */
 static uint32_t span_of(const b200_interp_desc_t* d) { return d->elements[0] + d->elements[1] + d->elements[2]; }
@@ -717,7 +932,6 @@ int oracle_moveinto(const b200_bz_tables_t* bz, const double* Q, size_t nQ, int 
 int oracle_interpolate_at(int kind, const b200_bz_tables_t* bz, const void* structure, const b200_data_tables_t* data,
                           const double* Q, size_t nQ, uint32_t flags, int ir, void* vals_out, void* vecs_out,
                           b200_probe_t* probe) {
-  if (kind != B200_GRID_TRELLIS) return B200_E_UNSUPPORTED;
   const b200_trellis_tables_t* tr = (const b200_trellis_tables_t*)structure;
   const size_t vrow = (size_t)data->values.branches * span_of(&data->values) * (data->values.is_complex ? 2 : 1);
   const size_t wrow = (size_t)data->vectors.branches * span_of(&data->vectors) * (data->vectors.is_complex ? 2 : 1);
@@ -736,7 +950,10 @@ int oracle_interpolate_at(int kind, const b200_bz_tables_t* bz, const void* stru
     }
     matvec_dd(x, bz->to_xyz, q);
     iw_t iw;
-    st |= trellis_locate(tr, x, &iw);
+    if (kind == B200_GRID_TRELLIS) st |= trellis_locate(tr, x, &iw);
+    else if (kind == B200_GRID_NEST) st |= nest_locate((const b200_nest_tables_t*)structure, x, &iw);
+    else if (kind == B200_GRID_MESH) st |= mesh_locate((const b200_mesh_tables_t*)structure, x, &iw);
+    else return B200_E_UNSUPPORTED;
     probe_store(probe, i, q, x, tau, r, ri, &iw, st);
     double* vo = (double*)vals_out + i * vrow;
     double* wo = (double*)vecs_out + i * wrow;
@@ -746,7 +963,7 @@ int oracle_interpolate_at(int kind, const b200_bz_tables_t* bz, const void* stru
       memset(wo, 0, wrow * sizeof(double));
       continue;
     }
-    int is_cube = tr->node_type[iw.cell] == B200_NODE_CUBE;
+    int is_cube = kind == B200_GRID_TRELLIS && tr->node_type[iw.cell] == B200_NODE_CUBE;
     uint32_t cellidx = is_cube ? tr->node_index[iw.cell] : (uint32_t)iw.tet;
     interpolate_one(&data->values, data, &iw, is_cube, cellidx, 0, vo);
     interpolate_one(&data->vectors, data, &iw, is_cube, cellidx, 1, wo);

@@ -46,9 +46,8 @@ class Oracle:
     """The oracle over one set of flat tables (bridge dictionaries)."""
 
     def __init__(self, structure, data=None):
-        self.kind = {"trellis": T.GRID_TRELLIS, "nest": T.GRID_NEST, "mesh": T.GRID_MESH}[str(structure["kind"])]
         self.bz = T.pack_bz(structure["bz"])
-        self.structure = {T.GRID_TRELLIS: T.pack_trellis}[self.kind](structure)
+        self.kind, self.structure = T.pack_structure(structure)
         self.data = T.pack_data(data) if data is not None else None
 
     def set_data(self, data):

@@ -101,6 +101,35 @@ static py::tuple indices_weights(const G& g, py::array_t<double, py::array::c_st
   return py::make_tuple(cnt, idx, wgt);
 }
 
+// Mesh3 keeps its TetTri protected and offers no per-point accessor: reach it through a derived class
+template <class T, class R>
+struct MeshProbe : Mesh3<T, R, double, Array2> {
+  static const TetTri& mesh_of(const Mesh3<T, R, double, Array2>& m) { return m.*(&MeshProbe::mesh); }
+};
+template <class T, class R>
+static py::tuple mesh_indices_weights(const BrillouinZoneMesh3<T, R, double>& g, py::array_t<double, py::array::c_style | py::array::forcecast> X) {
+  auto a = to_a2(X);
+  ind_t n = a.size(0);
+  const TetTri& tt = MeshProbe<T, R>::mesh_of(g);
+  py::array_t<int> cnt((py::ssize_t)n);
+  py::array_t<unsigned> idx({(py::ssize_t)n, (py::ssize_t)8});
+  py::array_t<double> wgt({(py::ssize_t)n, (py::ssize_t)8});
+  for (ind_t i = 0; i < n; ++i) {
+    std::vector<std::pair<ind_t, double>> iw;
+    try {
+      iw = tt.locate(a.view(i));
+    } catch (const std::exception&) {
+      iw.clear();
+    }
+    cnt.mutable_at(i) = static_cast<int>(iw.size());
+    for (size_t j = 0; j < 8; ++j) {
+      idx.mutable_at(i, j) = j < iw.size() ? iw[j].first : 0xffffffffu;
+      wgt.mutable_at(i, j) = j < iw.size() ? iw[j].second : 0.;
+    }
+  }
+  return py::make_tuple(cnt, idx, wgt);
+}
+
 template <class G>
 static py::array_t<unsigned> node_index(const G& g, py::array_t<double, py::array::c_style | py::array::forcecast> X) {
   auto a = to_a2(X);
@@ -122,6 +151,7 @@ static void def_all(py::module& m) {
   m.def("indices_weights", &indices_weights<Tr>, py::arg("grid"), py::arg("x_xyz"));
   m.def("indices_weights", &indices_weights<Ne>, py::arg("grid"), py::arg("x_xyz"));
   m.def("node_index", &node_index<Tr>, py::arg("grid"), py::arg("x_xyz"));
+  m.def("indices_weights", &mesh_indices_weights<T, R>, py::arg("grid"), py::arg("x_xyz"));
   m.def("permutation", &permutation<Tr>);
   m.def("permutation", &permutation<Ne>);
 }

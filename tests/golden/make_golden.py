@@ -133,7 +133,30 @@ def p1_trellis():
     print("p1_trellis_dd.npz", os.path.getsize(os.path.join(HERE, "p1_trellis_dd.npz")))
 
 
+def tet_grid(name, cls, args, nq, seed, sort=False):
+    """Nest / Mesh grids on the P6_3/mmc lattice (BZNestQdc: nest.hpp, BZMeshQdc: mesh.hpp)."""
+    lat = W.p63mmc_lattice(b)
+    bz = b.BrillouinZone(lat)
+    g = getattr(b, cls)(bz, *[a(bz) if callable(a) else a for a in args])
+    W._gamma_fill(g, 12, 4, seed)
+    if sort:
+        g.sort()
+    out = {}
+    flat("s.", br.flatten(g), out)
+    flat("d.", br.flatten_data(g), out)
+    Q = np.vstack([special_points(), np.random.default_rng(seed).uniform(-3, 3, (nq, 3))])
+    out["Q"] = Q
+    out.update(reference_run(g, bz, Q))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, os.path.getsize(os.path.join(HERE, name)))
+
+
 def main():
+    tet_grid("p63mmc_nest.npz", "BZNestQdc", (lambda bz: bz.ir_polyhedron.volume / 40, 5), 300, 41)
+    tet_grid("p63mmc_nest_sorted.npz", "BZNestQdc", (lambda bz: bz.ir_polyhedron.volume / 30, 5), 200, 42, sort=True)
+    tet_grid("p63mmc_mesh.npz", "BZMeshQdc", (lambda bz: bz.ir_polyhedron.volume / 60, 3), 300, 43)
+    if "--tet-only" in sys.argv:
+        return
     nacl_gamma()
     p1_trellis()
     small_trellis("nacl_prim_trellis.npz", W.c2_nacl(b, density=150, seed=5), 400, 21, extra_q=special_points())

@@ -10,7 +10,12 @@ from helpers import RTOL, assert_decisions_equal, assert_values_close, load_gold
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scalar_trellis.npz", "p63mmc_trellis.npz", "p1_trellis_dd.npz"]
+FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scalar_trellis.npz", "p63mmc_trellis.npz", "p1_trellis_dd.npz",
+            "p63mmc_nest.npz", "p63mmc_nest_sorted.npz", "p63mmc_mesh.npz"]
+
+
+def rel_close(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
 
 
 def probe_dict(pr):
@@ -24,7 +29,7 @@ def test_golden_fixtures(name, path):
     g = brille_b200.B200Grid(None, structure=s, data=d)
     g.set_option("interp_path", path)
     vals, vecs, pr = g.ir_interpolate_at(rest["Q"], probe=True)
-    assert_decisions_equal(pr, ref_decisions(rest), "cuda")
+    assert_decisions_equal(pr, ref_decisions(rest), "cuda", adaptive_ulps=4 if str(s["kind"]) in ("nest", "mesh") else 0)
     assert_values_close(vals, rest["ref_values"])
     assert_values_close(vecs, rest["ref_vectors"])
     assert g.launch_count >= 2
@@ -111,6 +116,44 @@ def test_against_oracle_and_reference(host, bridge, builder, n, path):
 
 
 @pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+@pytest.mark.parametrize("cls,args", [("BZNestQdc", (5,)), ("BZMeshQdc", (3,))])
+def test_nest_and_mesh_against_oracle_and_reference(host, bridge, cls, args, path):
+    """BZNestQdc (nest.hpp) and BZMeshQdc (mesh.hpp, triangulation_layers.hpp) on the C3 lattice."""
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    hg = getattr(host, cls)(bz, bz.ir_polyhedron.volume / 1000, *args)
+    W._gamma_fill(hg, 12, 4, 17)
+    g = brille_b200.accelerate(hg)
+    g.set_option("interp_path", path)
+    Q = np.random.default_rng(5).uniform(-3, 3, (100000, 3))
+    vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+    orc = Oracle(bridge.flatten(hg), bridge.flatten_data(hg))
+    rc, ov, ow, opr = orc.interpolate_at(Q)
+    assert rc == 0
+    assert_decisions_equal(pr, probe_dict(opr), "cuda vs oracle")
+    assert np.array_equal(pr.tet, opr.tet)
+    assert_values_close(vals, ov)
+    assert_values_close(vecs, ow)
+    rv, rw = hg.ir_interpolate_at(Q[:20000], True, 8)
+    assert_values_close(vals[:20000], rv)
+    assert_values_close(vecs[:20000], rw)
+
+
+def test_c4_p21c_nest_72_modes(host, bridge):
+    """BASELINE config 4: P2_1/c, 24 atoms, 72 modes, BZNestQdc (mode-tiled staging in the cell kernel)."""
+    wl = W.c4_p21c_nest(host, density=300)
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(20000, 21)
+    vals, vecs = g.ir_interpolate_at(Q)
+    g.set_option("interp_path", 1)
+    v1, w1 = g.ir_interpolate_at(Q[:4000])
+    assert rel_close(v1, vals[:4000]) <= 1e-12 and rel_close(w1, vecs[:4000]) <= 1e-12
+    rv, rw = wl.grid.ir_interpolate_at(Q[:4000], True, 8)
+    assert_values_close(vals[:4000], rv)
+    assert_values_close(vecs[:4000], rw)
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
 def test_sorted_permutations_against_reference(host, bridge, path):
     wl = W.c3_p63mmc(host, density=150, seed=9)
     wl.grid.sort()
@@ -121,10 +164,6 @@ def test_sorted_permutations_against_reference(host, bridge, path):
     rv, rw = wl.grid.ir_interpolate_at(Q, True, 8)
     assert_values_close(vals, rv)
     assert_values_close(vecs, rw)
-
-
-def rel_close(a, b):
-    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
 
 
 def test_full_size_properties(host):

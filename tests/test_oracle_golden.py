@@ -6,7 +6,8 @@ import pytest
 from oracle.oracle import Oracle
 from helpers import RTOL, assert_decisions_equal, assert_values_close, load_golden, ref_decisions, remove_mode_phase
 
-FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scalar_trellis.npz", "p63mmc_trellis.npz", "p1_trellis_dd.npz"]
+FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scalar_trellis.npz", "p63mmc_trellis.npz", "p1_trellis_dd.npz",
+            "p63mmc_nest.npz", "p63mmc_nest_sorted.npz", "p63mmc_mesh.npz"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -15,10 +16,14 @@ def test_oracle_matches_reference_outputs(name):
     orc = Oracle(s, d)
     rc, vals, vecs, pr = orc.interpolate_at(rest["Q"])
     assert rc == 0
-    assert_decisions_equal(pr, ref_decisions(rest))
-    # the oracle keeps the reference's operation order: results are bit-identical
-    assert np.array_equal(vals, rest["ref_values"].reshape(vals.shape))
-    assert np.array_equal(vecs, rest["ref_vectors"].reshape(vecs.shape))
+    tet_grid = str(s["kind"]) in ("nest", "mesh")
+    assert_decisions_equal(pr, ref_decisions(rest), adaptive_ulps=4 if tet_grid else 0)
+    # the oracle keeps the reference's operation order: results are bit-identical (for points off the cell faces)
+    ok = np.ones(len(rest["Q"]), bool) if not tet_grid else np.asarray(rest["ref_n_vert"]) == 4
+    assert np.array_equal(vals[ok], rest["ref_values"].reshape(vals.shape)[ok])
+    assert np.array_equal(vecs[ok], rest["ref_vectors"].reshape(vecs.shape)[ok])
+    assert_values_close(vals, rest["ref_values"])
+    assert_values_close(vecs, rest["ref_vectors"])
 
 
 def test_oracle_interpolate_at_no_rotation():

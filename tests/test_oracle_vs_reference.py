@@ -45,3 +45,17 @@ def test_powder_q_large_tau(host, probe, bridge):
     B = np.asarray(bridge.flatten_bz(wl.bz)["to_xyz"])
     wl.make_q = lambda n, seed: W.powder_q(B, n, seed)
     _compare(host, probe, bridge, wl, 10000, 6)
+
+
+@pytest.mark.parametrize("cls,args", [("BZNestQdc", (5,)), ("BZMeshQdc", (3,)), ("BZMeshQdc", (1,))])
+def test_nest_and_mesh(host, probe, bridge, cls, args):
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    g = getattr(host, cls)(bz, bz.ir_polyhedron.volume / 300, *args)
+    W._gamma_fill(g, 12, 4, 9)
+    wl = W.Workload(cls, g, bz, 12, 4, lambda n, seed: np.random.default_rng(seed).uniform(-3, 3, (n, 3)))
+    _compare(host, probe, bridge, wl, 10000, 8)
+
+
+def test_c4_nest_low_symmetry(host, probe, bridge):
+    _compare(host, probe, bridge, W.c4_p21c_nest(host, density=200), 3000, 9)
