@@ -217,12 +217,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # sampled from the warm-up on: the timed region of 10 steps is shorter than one 200 ms sample
     for i in range(max(args.warmup, 3)):
         step(check=(i == 0))  # the first warm-up step also verifies that every Q was placed
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = grid.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
