@@ -633,16 +633,19 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
                    bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
   const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
-  CU(ws.ensure(n, nb, g->chunk, (interp && g->dd.vectors.rot_kind >= 3) ? g->dd.vectors.no1 : 0u));
-  CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
   if (cell && g->interp_path == 0 && n < 4 * (size_t)nb) cell = false;
-  uint32_t mpp = 0;
+  uint32_t mpp = 0, chunk = g->chunk;
   if (cell) {
-    mpp = cell_modes_per_pass(g->dd, g->chunk, 100 * 1024);
-    if (mpp == 0) cell = false;
+    chunk = cell_pick_chunk(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 100 * 1024, &mpp);
+    if (chunk == 0 || mpp == 0) {
+      cell = false;
+      chunk = g->chunk;
+    }
   }
+  CU(ws.ensure(n, nb, chunk, 0u));
+  CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
   lo.tau = ws.tau;

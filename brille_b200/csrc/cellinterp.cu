@@ -117,19 +117,19 @@ __device__ __forceinline__ void rotate_phase_store(const double* R, const double
 struct SmemPlan {
   size_t D, V, W, PH, RS, F0, QI, RI, PHI, total;
 };
-__host__ __device__ inline SmemPlan plan_smem(uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
+__host__ __device__ inline SmemPlan plan_smem(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
   SmemPlan p;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
-  p.D = take((size_t)8 * mpp * S * 16);
-  p.V = take((size_t)8 * mpp * no0v * 8);
+  p.D = take((size_t)nvmax * mpp * S * 16);  // nvmax = 8 when the grid has cube cells, else 4
+  p.V = take((size_t)nvmax * mpp * no0v * 8);
   p.W = take((size_t)chunk * 8 * 8);
   p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
   p.RS = take((size_t)G * 9 * 8);
   p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
   p.QI = take((size_t)chunk * 4);
   p.RI = take((size_t)chunk * 4);
-  p.PHI = take((size_t)7 * mpp * 16);
+  p.PHI = take((size_t)(nvmax - 1) * mpp * 16);
   p.total = o;
   return p;
 }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
   const int NV = is_cube ? 8 : 4;
   const uint32_t cellidx = is_cube ? item.key : item.key - a.n_cubes;
   const uint32_t mpp = a.modes_per_pass;
-  const SmemPlan pl = plan_smem(mpp, S, no0v, a.bk.chunk, NAT, G, gamma);
+  const SmemPlan pl = plan_smem(a.n_cubes ? 8u : 4u, mpp, S, no0v, a.bk.chunk, NAT, G, gamma);
   double2* D = reinterpret_cast<double2*>(smem + pl.D);
   double* V = reinterpret_cast<double*>(smem + pl.V);
   double* W = reinterpret_cast<double*>(smem + pl.W);
@@ -407,11 +407,26 @@ bool cell_path_eligible(const DataDev& dd) {
 }
 
 // modes staged per pass so that the carve-up fits `budget` bytes of dynamic shared memory
-uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget) {
+uint32_t cell_modes_per_pass(const DataDev& dd, bool has_cubes, uint32_t chunk, size_t budget) {
   const bool gamma = dd.vectors.rot_kind >= 3;
   for (uint32_t mpp = dd.vectors.branches; mpp >= 1; --mpp)
-    if (plan_smem(mpp, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) return mpp;
+    if (plan_smem(has_cubes ? 8u : 4u, mpp, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) return mpp;
   return 0;
+}
+
+// Points per work item: the per-point tables (weights, per-atom Gamma phases) grow with chunk * n_atoms, the staged rows with
+// modes_per_pass * span.  Take the largest chunk that still leaves room for at least a quarter of the modes per pass.
+uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out) {
+  uint32_t best_chunk = 0, best_mpp = 0;
+  for (uint32_t chunk = preferred; chunk >= 32; chunk /= 2) {
+    const uint32_t mpp = cell_modes_per_pass(dd, has_cubes, chunk, budget);
+    if (mpp == 0) continue;
+    if (best_chunk == 0) { best_chunk = chunk; best_mpp = mpp; }
+    if (4 * mpp >= dd.vectors.branches || mpp == dd.vectors.branches) { best_chunk = chunk; best_mpp = mpp; break; }
+    if (mpp > best_mpp) { best_chunk = chunk; best_mpp = mpp; }
+  }
+  *mpp_out = best_mpp;
+  return best_chunk;
 }
 
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
@@ -425,7 +440,7 @@ cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const u
 cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream) {
   const DataDev& dd = args.dd;
   const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
-  const size_t smem = plan_smem(args.modes_per_pass, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
+  const size_t smem = plan_smem(args.n_cubes ? 8u : 4u, args.modes_per_pass, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_interp_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

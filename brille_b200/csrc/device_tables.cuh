@@ -206,7 +206,8 @@ cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, 
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
                           cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
 bool cell_path_eligible(const DataDev& dd);
-uint32_t cell_modes_per_pass(const DataDev& dd, uint32_t chunk, size_t budget);
+uint32_t cell_modes_per_pass(const DataDev& dd, bool has_cubes, uint32_t chunk, size_t budget);
+uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
                                cudaStream_t stream);
 cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);

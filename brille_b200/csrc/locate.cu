@@ -514,36 +514,45 @@ __device__ __forceinline__ uint32_t nest_locate(const NestDev& t, const double* 
   while (head < tail) {
     const uint32_t b = qb[head % QCAP], en = qe[head % QCAP];
     ++head;
-    for (uint32_t node = b; node < en; ++node) {
-      const double* tp = t.node_pack + (size_t)TET_PACK * node;
-      const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
-      const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
-      const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
-      const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
-      if (!(d2 < c23.y || approx_eq(d2, c23.y, t.rel, t.abs_))) continue;  // might_contain (:114-122) -> weights -1
-      tetgen_weights(tp, x, w);
-      bool ok = true;  // none_negative (:43-48)
+    // two phases per block of <= 64 children (cf. the trellis): circumsphere mask first, then the weights of the candidates
+    for (uint32_t base = b; base < en; base += 64) {
+      const uint32_t nblk = min(64u, en - base);
+      unsigned long long cand = 0ull;
+      for (uint32_t k = 0; k < nblk; ++k) {
+        const double* tp = t.node_pack + (size_t)TET_PACK * (base + k);
+        const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+        const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+        const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
+        const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
+        if (d2 < c23.y || approx_eq(d2, c23.y, t.rel, t.abs_)) cand |= 1ull << k;  // might_contain (:114-122)
+      }
+      while (cand) {
+        const uint32_t node = base + (uint32_t)(__ffsll((long long)cand) - 1);
+        cand &= cand - 1ull;
+        tetgen_weights(t.node_pack + (size_t)TET_PACK * node, x, w);
+        bool ok = true;  // none_negative (:43-48)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ok &= !(w[j] < 0.0 && !approx_eq(w[j], 0.0, t.rel, t.abs_));
-      if (!ok) continue;
-      if (t.node_is_leaf[node]) {
-        if (nsol == 0) {
-          first_node = node;
+        for (int j = 0; j < 4; ++j) ok &= !(w[j] < 0.0 && !approx_eq(w[j], 0.0, t.rel, t.abs_));
+        if (!ok) continue;
+        if (t.node_is_leaf[node]) {
+          if (nsol == 0) {
+            first_node = node;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) fw[j] = w[j];
+            for (int j = 0; j < 4; ++j) fw[j] = w[j];
+          }
+          if (w[0] > 0.0 && w[1] > 0.0 && w[2] > 0.0 && w[3] > 0.0) {
+            best_node = node;
+            have_best = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bw[j] = w[j];
+          }
+          ++nsol;
+        } else {
+          if (tail - head >= QCAP) { overflow = true; continue; }
+          qb[tail % QCAP] = t.child_begin[node];
+          qe[tail % QCAP] = t.child_end[node];
+          ++tail;
         }
-        if (w[0] > 0.0 && w[1] > 0.0 && w[2] > 0.0 && w[3] > 0.0) {
-          best_node = node;
-          have_best = true;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bw[j] = w[j];
-        }
-        ++nsol;
-      } else {
-        if (tail - head >= QCAP) { overflow = true; continue; }
-        qb[tail % QCAP] = t.child_begin[node];
-        qe[tail % QCAP] = t.child_end[node];
-        ++tail;
       }
     }
   }
@@ -570,12 +579,14 @@ __device__ __forceinline__ uint32_t nest_locate(const NestDev& t, const double* 
 
 // TetTri::locate (triangulation_layers.hpp:401-417): first containing tetrahedron of the coarsest layer, then of the
 // candidate list connections[l-1][idx] in every finer layer
-__device__ __forceinline__ bool mesh_try(const BZDev& bz, const double* tp, const double* x, double* w) {
+__device__ __forceinline__ bool mesh_sphere(const BZDev& bz, const double* tp, const double* x) {
   const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
   const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
   const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
   const double nrm = sqrt(((0.0 + d0 * d0) + d1 * d1) + d2v * d2v);  // unsafe_might_contain (:254-256)
-  if (!(approx_eq(nrm, c23.y, bz.def_rel, bz.def_abs) || nrm < c23.y)) return false;
+  return approx_eq(nrm, c23.y, bz.def_rel, bz.def_abs) || nrm < c23.y;
+}
+__device__ __forceinline__ bool mesh_contains(const BZDev& bz, const double* tp, const double* x, double* w) {
   tetgen_weights(tp, x, w);
   bool ok = true;  // unsafe_contains (:261-264)
 #pragma unroll
@@ -592,15 +603,22 @@ __device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const MeshDev& 
   for (uint32_t layer = 0; layer < t.n_layers; ++layer) {
     uint32_t found = 0xffffffffu;
     const uint32_t base = t.tet_offset[layer];
-    if (layer == 0) {
-      const uint32_t nt = t.tet_offset[1] - base;
-      for (uint32_t k = 0; k < nt; ++k)
-        if (mesh_try(bz, t.tet_pack + (size_t)TET_PACK * (base + k), x, w)) { found = k; break; }
-    } else {
-      const uint32_t c = t.tet_offset[layer - 1] + idx;
-      for (uint32_t k = t.conn_offset[c]; k < t.conn_offset[c + 1]; ++k) {
-        const uint32_t cand = t.conn_index[k];
-        if (mesh_try(bz, t.tet_pack + (size_t)TET_PACK * (base + cand), x, w)) { found = cand; break; }
+    // candidate list of this layer: all tetrahedra (layer 0) or connections[layer-1][idx]; scanned in blocks of 64 with the
+    // cheap circumsphere test first and the four weights only for the survivors, in list order (first match wins)
+    const uint32_t c = layer ? t.tet_offset[layer - 1] + idx : 0u;
+    const uint32_t k0 = layer ? t.conn_offset[c] : 0u, k1 = layer ? t.conn_offset[c + 1] : t.tet_offset[1] - base;
+    for (uint32_t kb = k0; kb < k1 && found == 0xffffffffu; kb += 64) {
+      const uint32_t nblk = min(64u, k1 - kb);
+      unsigned long long cand = 0ull;
+      for (uint32_t k = 0; k < nblk; ++k) {
+        const uint32_t ti = layer ? t.conn_index[kb + k] : kb + k;
+        if (mesh_sphere(bz, t.tet_pack + (size_t)TET_PACK * (base + ti), x)) cand |= 1ull << k;
+      }
+      while (cand) {
+        const uint32_t k = (uint32_t)(__ffsll((long long)cand) - 1);
+        cand &= cand - 1ull;
+        const uint32_t ti = layer ? t.conn_index[kb + k] : kb + k;
+        if (mesh_contains(bz, t.tet_pack + (size_t)TET_PACK * (base + ti), x, w)) { found = ti; break; }
       }
     }
     if (found == 0xffffffffu) return B200_ST_NOT_FOUND;

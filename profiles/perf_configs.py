@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Device-resident throughput of the BASELINE.json configurations (and the Nest/Mesh variants of C3) on one GPU."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import brille_b200  # noqa: E402
+from brille_b200 import workloads as W  # noqa: E402
+from oracle import ref  # noqa: E402
+
+b = ref.host()
+which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C1", "C2", "C3", "C3nest", "C3mesh", "C4"]
+
+
+def build(name):
+    if name in W.BUILDERS:
+        wl = W.BUILDERS[name](b)
+        return wl, {"C1": 10_000_000, "C2": 10_000_000, "C3": 10_000_000, "C4": 500_000}[name]
+    lat = W.p63mmc_lattice(b)
+    bz = b.BrillouinZone(lat)
+    g = b.BZNestQdc(bz, bz.ir_polyhedron.volume / 2000, 5) if name == "C3nest" else b.BZMeshQdc(bz, bz.ir_polyhedron.volume / 2000, 3)
+    args = W._gamma_fill(g, 12, 4, 3)
+    return W.Workload(name, g, bz, 12, 4, W._uniform_q(-3, 3), args), 10_000_000
+
+
+for name in which:
+    wl, nq = build(name)
+    grid = brille_b200.accelerate(wl.grid)
+    dQ = torch.from_numpy(wl.make_q(nq, 3)).cuda()
+    vals, vecs = grid.ir_interpolate_at_device(dQ)
+    for _ in range(2):
+        grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record()
+    for _ in range(steps):
+        grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    grid.enable_timing(True)
+    grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
+    t = {k: grid.kernel_ms(k) for k in ("locate", "sort", "interpolate")}
+    grid.enable_timing(False)
+    bpq = grid.bytes_per_q
+    print(f"{name:7s} nQ={nq:.0e} bytes/Q={bpq:6d} step {ms:8.3f} ms  {nq/ms/1e3:.3e} Q/s  {bpq*nq/ms/1e6:7.1f} GB/s algorithmic | "
+          + " ".join(f"{k} {v:.3f}" for k, v in t.items()), flush=True)
+    del vals, vecs, dQ
+    grid.close()
+    torch.cuda.empty_cache()
