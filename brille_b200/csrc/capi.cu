@@ -142,6 +142,7 @@ struct b200_grid {
   Workspace ws;                 // device-pointer API
   unsigned long long* d_fail = nullptr;
   HostStage stage[2];
+  size_t host_chunk = 0;   // max points per chunk of the host-buffer pipeline (0 = sized from free memory)
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
   uint64_t launches = 0;
@@ -631,11 +632,12 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
-                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream) {
+                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call) {
   const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
-  if (cell && g->interp_path == 0 && n < 4 * (size_t)nb) cell = false;
+  // (decided on the size of the whole call, not of the chunk, so that chunking never changes which kernel a point sees)
+  if (cell && g->interp_path == 0 && n_call < 4 * (size_t)nb) cell = false;
   uint32_t mpp = 0, chunk = g->chunk;
   if (cell) {
     chunk = cell_pick_chunk(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 100 * 1024, &mpp);
@@ -725,7 +727,7 @@ static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_
   if (g->timing) g->kernel_ms.clear();
   uint32_t mode = (flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u;
   if (ir) mode |= MODE_IR;
-  rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, ir, static_cast<double*>(dvals), static_cast<double*>(dvecs), stream);
+  rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, ir, static_cast<double*>(dvals), static_cast<double*>(dvecs), stream, nQ);
   if (rc) return rc;
   if (dprobe) {
     const LocateOut& lo = g->ws.lo;
@@ -762,6 +764,7 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
   size_t budget = std::min<size_t>(free_b / 4, (size_t)6 << 30);  // both stages together
   size_t chunk = std::max<size_t>(1024, budget / 2 / per_q);
   chunk = std::min(chunk, (size_t)1 << 22);
+  if (g->host_chunk) chunk = std::min(chunk, g->host_chunk);
   if (chunk > nQ) chunk = std::max<size_t>(nQ, 1);
   unsigned long long total[3] = {0, 0, 0};
   bool pending[2] = {false, false};
@@ -791,7 +794,7 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
     }
     CU(cudaMemcpyAsync(h.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h.stream));
-    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream);
+    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ);
     if (rc) return rc;
     if (interp) {
       CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
@@ -891,6 +894,9 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   } else if (n == "chunk") {
     if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
+  } else if (n == "host_chunk") {
+    if (value < 0) return fail(B200_E_INVALID, "host_chunk must be >= 0");
+    g->host_chunk = (size_t)value;
   } else {
     return fail(B200_E_INVALID, "unknown option " + n);
   }

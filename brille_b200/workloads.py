@@ -136,3 +136,49 @@ def powder_q(lat_to_xyz, n, seed):
 
 
 BUILDERS = {"C1": c1_fd3m_scalar, "C2": c2_nacl, "C3": c3_p63mmc, "C4": c4_p21c_nest}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# "lattice zoo": small grids over lattices / settings that exercise the remaining branches of the path (centred lattices
+# with a primitive transform, time-reversal symmetry added to a non-centrosymmetric group, rhombohedral and triclinic
+# cells) with data that transform like real/reciprocal vectors, pseudovectors and matrices (dd and cc classes)
+# ---------------------------------------------------------------------------------------------------------------------
+ZOO = {
+    "P3_timereversal": dict(lengths=(4.0, 4.0, 5.0), angles=(90, 90, 120), sg="P 3", tr=True),
+    "I4_timereversal": dict(lengths=(4.0, 4.0, 5.0), angles=(90, 90, 90), sg="I 4", tr=True),
+    "F23": dict(lengths=(5.0, 5.0, 5.0), angles=(90, 90, 90), sg="F 2 2 3", tr=False),
+    "R-3m_hex": dict(lengths=(4.0, 4.0, 12.0), angles=(90, 90, 120), sg='-R 3 2"', tr=False),
+    "P-1": dict(lengths=(4.0, 5.0, 6.0), angles=(80, 85, 95), sg="-P 1", tr=False),
+    "Im-3m": dict(lengths=(2.87, 2.87, 2.87), angles=(90, 90, 90), sg="Im-3m", tr=False),
+}
+
+
+def zoo_grid(b, name, cls="BZTrellisQcc", density=60, seed=1):
+    """values: complex, per mode 1 scalar + one pseudovector (real_lattice); vectors: complex, per mode 2 scalars + one
+    reciprocal-lattice vector ... or, for the dd class, real vectors + one 3x3 matrix."""
+    z = ZOO[name]
+    lat = b.Lattice(z["lengths"], z["angles"], z["sg"])
+    bz = b.BrillouinZone(lat, True, 1, z["tr"])
+    g = getattr(b, cls)(bz, bz.ir_polyhedron.volume / density)
+    nv = g.rlu.shape[0]
+    rng = np.random.default_rng(seed)
+    modes = 3
+
+    def rnd(shape, cplx):
+        a = rng.normal(size=shape)
+        return a + 1j * rng.normal(size=shape) if cplx else a
+
+    if cls.endswith("cc"):
+        vals = rnd((nv, modes, 1 + 3), True)       # scalar + pseudovector
+        vecs = rnd((nv, modes, 2 + 3), True)       # 2 scalars + reciprocal-lattice vector
+        args = (vals, (1, 3, 0, 1, 3), vecs, (2, 3, 0, 0, 4))
+    elif cls.endswith("dd"):
+        vals = rnd((nv, modes, 3), False)          # real-lattice vector
+        vecs = rnd((nv, modes, 1 + 9), False)      # scalar + matrix
+        args = (vals, (0, 3, 0, 0, 3), vecs, (1, 0, 9, 0, 3))
+    else:  # dc: real eigenvalue-like scalars, complex pseudovector + matrix
+        vals = rnd((nv, modes, 2), False)
+        vecs = rnd((nv, modes, 3 + 9), True)
+        args = (vals, (2, 0, 0, 0, 3), vecs, (0, 3, 9, 1, 3))
+    g.fill(*args)
+    return Workload(f"zoo {name} {cls}", g, bz, modes, 0, _uniform_q(-2, 2), args)

@@ -139,6 +139,46 @@ def test_nest_and_mesh_against_oracle_and_reference(host, bridge, cls, args, pat
     assert_values_close(vecs[:20000], rw)
 
 
+SPECIAL = np.array([[0, 0, 0], [0.5, 0, 0], [0.5, 0.5, 0], [0.5, 0.5, 0.5], [1, 0, 0], [0.25, 0.25, 0], [1 / 3, 1 / 3, 0], [0, 0, 0.5],
+                    [-0.5, 0, 0], [2, 1, 0], [0.1, 0.1, 0.1], [-1.5, 2.5, 0.5], [0.75, 0.25, 0.5]], dtype=float)
+
+
+@pytest.mark.parametrize("cls", ["BZTrellisQcc", "BZTrellisQdd", "BZTrellisQdc"])
+@pytest.mark.parametrize("name", sorted(W.ZOO))
+def test_lattice_zoo(host, bridge, name, cls):
+    """centred / rhombohedral / triclinic lattices, added time reversal; complex values, pseudovector, reciprocal-vector
+    and matrix data (rip_axial, rip_recip, rip_real with matrices) through the general kernel"""
+    wl = W.zoo_grid(host, name, cls)
+    g = brille_b200.accelerate(wl.grid)
+    Q = np.vstack([SPECIAL, wl.make_q(20000, 5)])
+    vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rc, ov, ow, opr = orc.interpolate_at(Q)
+    assert rc == 0
+    assert_decisions_equal(pr, probe_dict(opr), "cuda vs oracle")
+    assert_values_close(vals, ov)
+    assert_values_close(vecs, ow)
+    rv, rw = wl.grid.ir_interpolate_at(Q[:2000], False, 1)
+    assert_values_close(vals[:2000], rv)
+    assert_values_close(vecs[:2000], rw)
+
+
+def test_host_pipeline_chunking_is_invisible(host):
+    """many small chunks through the two-stream host pipeline give the same bits as one chunk"""
+    wl = W.c2_nacl(host, density=300)
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(300001, 4)
+    v1, w1 = g.ir_interpolate_at(Q)
+    g.set_option("host_chunk", 7001)
+    v2, w2 = g.ir_interpolate_at(Q, pinned=True)
+    assert np.array_equal(v1, v2) and np.array_equal(w1, w2)
+    # a failing point anywhere fails the whole call, like the reference
+    Qbad = Q.copy()
+    Qbad[123456] = 7.3  # far outside the gridded irreducible zone when points are not moved
+    with pytest.raises(RuntimeError):
+        g.ir_interpolate_at(Qbad, do_not_move_points=True)
+
+
 def test_c4_p21c_nest_72_modes(host, bridge):
     """BASELINE config 4: P2_1/c, 24 atoms, 72 modes, BZNestQdc (mode-tiled staging in the cell kernel)."""
     wl = W.c4_p21c_nest(host, density=300)

@@ -59,3 +59,17 @@ def test_nest_and_mesh(host, probe, bridge, cls, args):
 
 def test_c4_nest_low_symmetry(host, probe, bridge):
     _compare(host, probe, bridge, W.c4_p21c_nest(host, density=200), 3000, 9)
+
+
+SPECIAL = np.array([[0, 0, 0], [0.5, 0, 0], [0.5, 0.5, 0], [0.5, 0.5, 0.5], [1, 0, 0], [0.25, 0.25, 0], [1 / 3, 1 / 3, 0], [0, 0, 0.5],
+                    [-0.5, 0, 0], [2, 1, 0], [0.1, 0.1, 0.1], [-1.5, 2.5, 0.5], [0.75, 0.25, 0.5]], dtype=float)
+
+
+@pytest.mark.parametrize("cls", ["BZTrellisQcc", "BZTrellisQdd", "BZTrellisQdc"])
+@pytest.mark.parametrize("name", sorted(W.ZOO))
+def test_lattice_zoo(host, probe, bridge, name, cls):
+    """centred / rhombohedral / triclinic lattices, added time reversal; pseudovector, reciprocal-vector and matrix data"""
+    wl = W.zoo_grid(host, name, cls)
+    base = wl.make_q
+    wl.make_q = lambda n, seed: np.vstack([SPECIAL, base(n, seed)])
+    _compare(host, probe, bridge, wl, 3000, 5)
