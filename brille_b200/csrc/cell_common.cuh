@@ -1,0 +1,176 @@
+// cell_common.cuh -- pieces shared by the two cell-batched interpolation kernels (cellinterp.cu, cellinterp_ws.cu)
+#pragma once
+#include "device_tables.cuh"
+#include "brille_b200.h"
+
+namespace b200 {
+
+// out = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
+// that finishes a point produces the same bits (the result must not depend on which path a point happens to take)
+__device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
+                                                   const double2 ph, bool use_phase, double2* out) {
+  double2 u0, u1, u2;
+  u0.x = __fma_rn(R[2], a2.x, __fma_rn(R[1], a1.x, __dmul_rn(R[0], a0.x)));
+  u0.y = __fma_rn(R[2], a2.y, __fma_rn(R[1], a1.y, __dmul_rn(R[0], a0.y)));
+  u1.x = __fma_rn(R[5], a2.x, __fma_rn(R[4], a1.x, __dmul_rn(R[3], a0.x)));
+  u1.y = __fma_rn(R[5], a2.y, __fma_rn(R[4], a1.y, __dmul_rn(R[3], a0.y)));
+  u2.x = __fma_rn(R[8], a2.x, __fma_rn(R[7], a1.x, __dmul_rn(R[6], a0.x)));
+  u2.y = __fma_rn(R[8], a2.y, __fma_rn(R[7], a1.y, __dmul_rn(R[6], a0.y)));
+  if (use_phase) {
+    out[0] = make_double2(__fma_rn(-ph.y, u0.y, __dmul_rn(ph.x, u0.x)), __fma_rn(ph.y, u0.x, __dmul_rn(ph.x, u0.y)));
+    out[1] = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
+    out[2] = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
+  } else {
+    out[0] = u0;
+    out[1] = u1;
+    out[2] = u2;
+  }
+}
+
+// dynamic shared memory carve-up (all offsets 16-byte aligned)
+struct SmemPlan {
+  size_t D, V, W, PH, RS, F0, QI, RI, PHI, total;
+};
+__host__ __device__ inline SmemPlan plan_smem(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
+  SmemPlan p;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+  p.D = take((size_t)nvmax * mpp * S * 16);  // nvmax = 8 when the grid has cube cells, else 4
+  p.V = take((size_t)nvmax * mpp * no0v * 8);
+  p.W = take((size_t)chunk * 8 * 8);
+  p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
+  p.RS = take((size_t)G * 9 * 8);
+  p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
+  p.QI = take((size_t)chunk * 4);
+  p.RI = take((size_t)chunk * 4);
+  p.PHI = take((size_t)(nvmax - 1) * mpp * 16);
+  p.total = o;
+  return p;
+}
+
+
+// Everything one pass (a block of `mb` modes starting at b0) of one work item needs; all pointers are shared memory
+// except the outputs.  `tid`/`nthr` are the index and count of the threads that execute the pass together.
+struct CellPass {
+  const double2* D;   // [NV][mpp][S] permuted, phase-aligned vertex rows
+  const double* V;    // [NV][mpp][no0v] permuted eigenvalue rows
+  const double* W;    // [NV][CH] weights, transposed
+  const double2* PH;  // [CH][NAT] Gamma phases
+  const double* RS;   // [G][9] rotation matrices applied to the vectors
+  const uint32_t* F0; // [NAT][G] atom permutation
+  const uint32_t* QI; // [CH] point index
+  const uint32_t* RI; // [CH] matrix index | Ridx << 16
+  uint32_t CH, mpp, mb, b0, len, M, S, NAT, no0v, G;
+  int NV, kind;
+  bool gamma;
+  const double* rot_det;
+  double* vals_out;
+  double* vecs_out;
+};
+
+__device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, int nthr) {
+  const double2* D = c.D;
+  const double* V = c.V;
+  const double* W = c.W;
+  const double2* PH = c.PH;
+  const double* RS = c.RS;
+  const uint32_t* F0 = c.F0;
+  const uint32_t* QI = c.QI;
+  const uint32_t* RI = c.RI;
+  const uint32_t CH = c.CH, mpp = c.mpp, mb = c.mb, b0 = c.b0, M = c.M, S = c.S, NAT = c.NAT, no0v = c.no0v, G = c.G;
+  const int NV = c.NV, kind = c.kind;
+  const bool gamma = c.gamma;
+  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
+  struct { uint32_t len; } item = {c.len};
+  struct { const double* rot_det; } dd_ = {c.rot_det};
+  struct { double* vals_out; double* vecs_out; decltype(dd_) dd; } a = {c.vals_out, c.vecs_out, dd_};
+    // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
+    for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
+      const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
+      double acc = 0.0;
+      for (int i = 0; i < NV; ++i) acc += W[(size_t)i * CH + t] * V[(size_t)i * mpp * no0v + r];
+      a.vals_out[(size_t)QI[t] * vrow + (size_t)b0 * no0v + r] = acc;
+    }
+    // ---- eigenvectors: weighted sum of pre-phased rows, rotation, atom permutation, Gamma phase ----------------------
+    // A task is one 3-vector (mode b, atom k) for TQ consecutive points: the three complex numbers of every corner are
+    // read from shared memory once and reused for the TQ points (register tile), which makes the loop FP64-bound
+    // instead of shared-memory-bound.
+    constexpr int TQ = 4;
+    const uint32_t per_q = mb * NAT;
+    const uint32_t ntile = (item.len + TQ - 1) / TQ;
+    for (uint32_t task = tid; task < ntile * per_q; task += nthr) {
+      const uint32_t tile = task / per_q, r = task - tile * per_q, b = r / NAT, k = r - b * NAT;
+      const uint32_t t0 = tile * TQ;
+      const double2* src = D + (size_t)b * S + 3 * k;
+      double2 acc[TQ][3];
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
+      for (int i = 0; i < NV; ++i) {
+        const double2* x = src + (size_t)i * mpp * S;
+        const double2 x0 = x[0], x1 = x[1], x2 = x[2];
+        const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
+        const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
+        const double w[TQ] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          acc[t][0].x += w[t] * x0.x; acc[t][0].y += w[t] * x0.y;
+          acc[t][1].x += w[t] * x1.x; acc[t][1].y += w[t] * x1.y;
+          acc[t][2].x += w[t] * x2.x; acc[t][2].y += w[t] * x2.y;
+        }
+      }
+      // ---- finish: rotation, atom permutation, Gamma phase, store ------------------------------------------------------
+      const uint32_t nt = min((uint32_t)TQ, item.len - t0);
+      const uint4 rr4 = *reinterpret_cast<const uint4*>(RI + t0);
+      const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
+      const uint32_t rrs[TQ] = {rr4.x, rr4.y, rr4.z, rr4.w}, qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
+      double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + (size_t)(b0 + b) * S;
+      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu)) {
+        // the four points share the rotation (the chunk is sorted by it): one matrix, one destination atom, no branches
+        const uint32_t ri = rr4.x & 0xffffu;
+        double R[9];
+        {
+          const double* Rs = RS + 9 * ri;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) R[e] = Rs[e];
+        }
+        const uint32_t dest = F0[k * G + ri];
+        const double2* php = PH + (size_t)t0 * NAT + k;
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          rotate_phase_store(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true,
+                             out_base + (size_t)qis[t] * wrow + 3 * dest);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) {
+        if ((uint32_t)t >= nt) break;
+        const uint32_t qi = t0 + t;
+        uint32_t dest = k;
+        double2* out = out_base + (size_t)qis[t] * wrow;
+        if (kind >= 0) {
+          const uint32_t rr = rrs[t];
+          const uint32_t ri = rr & 0xffffu;
+          double2 ph = make_double2(1.0, 0.0);
+          if (gamma) {
+            dest = F0[k * G + ri];
+            ph = PH[(size_t)qi * NAT + k];
+          }
+          out += 3 * dest;
+          rotate_phase_store(RS + 9 * ri, acc[t][0], acc[t][1], acc[t][2], ph, gamma, out);
+          if (kind == 2) {  // axial: det(R) R^-1 v
+            const double det = a.dd.rot_det[rr >> 16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out[c] = make_double2(out[c].x * det, out[c].y * det);
+          }
+        } else {
+          out += 3 * dest;
+          out[0] = acc[t][0];
+          out[1] = acc[t][1];
+          out[2] = acc[t][2];
+        }
+      }
+    }
+}
+
+}  // namespace b200

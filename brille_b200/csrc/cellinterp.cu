@@ -14,8 +14,7 @@
 //
 // Points whose pivot is not the cell's first corner (some weight ~ 0: on a face/edge/vertex of the cell) and failed
 // points go to a last bucket that is processed by the general kernel of interp.cu.
-#include "device_tables.cuh"
-#include "brille_b200.h"
+#include "cell_common.cuh"
 
 namespace b200 {
 
@@ -89,49 +88,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// out = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
-// that finishes a point produces the same bits (the result must not depend on which path a point happens to take)
-__device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
-                                                   const double2 ph, bool use_phase, double2* out) {
-  double2 u0, u1, u2;
-  u0.x = __fma_rn(R[2], a2.x, __fma_rn(R[1], a1.x, __dmul_rn(R[0], a0.x)));
-  u0.y = __fma_rn(R[2], a2.y, __fma_rn(R[1], a1.y, __dmul_rn(R[0], a0.y)));
-  u1.x = __fma_rn(R[5], a2.x, __fma_rn(R[4], a1.x, __dmul_rn(R[3], a0.x)));
-  u1.y = __fma_rn(R[5], a2.y, __fma_rn(R[4], a1.y, __dmul_rn(R[3], a0.y)));
-  u2.x = __fma_rn(R[8], a2.x, __fma_rn(R[7], a1.x, __dmul_rn(R[6], a0.x)));
-  u2.y = __fma_rn(R[8], a2.y, __fma_rn(R[7], a1.y, __dmul_rn(R[6], a0.y)));
-  if (use_phase) {
-    out[0] = make_double2(__fma_rn(-ph.y, u0.y, __dmul_rn(ph.x, u0.x)), __fma_rn(ph.y, u0.x, __dmul_rn(ph.x, u0.y)));
-    out[1] = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
-    out[2] = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
-  } else {
-    out[0] = u0;
-    out[1] = u1;
-    out[2] = u2;
-  }
-}
-
-// dynamic shared memory carve-up (all offsets 16-byte aligned)
-struct SmemPlan {
-  size_t D, V, W, PH, RS, F0, QI, RI, PHI, total;
-};
-__host__ __device__ inline SmemPlan plan_smem(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk, uint32_t n_at, uint32_t G, bool gamma) {
-  SmemPlan p;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
-  p.D = take((size_t)nvmax * mpp * S * 16);  // nvmax = 8 when the grid has cube cells, else 4
-  p.V = take((size_t)nvmax * mpp * no0v * 8);
-  p.W = take((size_t)chunk * 8 * 8);
-  p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
-  p.RS = take((size_t)G * 9 * 8);
-  p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
-  p.QI = take((size_t)chunk * 4);
-  p.RI = take((size_t)chunk * 4);
-  p.PHI = take((size_t)(nvmax - 1) * mpp * 16);
-  p.total = o;
-  return p;
 }
 
 __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
@@ -306,93 +262,12 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       }
       __syncthreads();
     }
-    // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
-    for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
-      const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
-      double acc = 0.0;
-      for (int i = 0; i < NV; ++i) acc += W[(size_t)i * CH + t] * V[(size_t)i * mpp * no0v + r];
-      a.vals_out[(size_t)QI[t] * vrow + (size_t)b0 * no0v + r] = acc;
-    }
-    // ---- eigenvectors: weighted sum of pre-phased rows, rotation, atom permutation, Gamma phase ----------------------
-    // A task is one 3-vector (mode b, atom k) for TQ consecutive points: the three complex numbers of every corner are
-    // read from shared memory once and reused for the TQ points (register tile), which makes the loop FP64-bound
-    // instead of shared-memory-bound.
-    constexpr int TQ = 4;
-    const uint32_t per_q = mb * NAT;
-    const uint32_t ntile = (item.len + TQ - 1) / TQ;
-    for (uint32_t task = tid; task < ntile * per_q; task += nthr) {
-      const uint32_t tile = task / per_q, r = task - tile * per_q, b = r / NAT, k = r - b * NAT;
-      const uint32_t t0 = tile * TQ;
-      const double2* src = D + (size_t)b * S + 3 * k;
-      double2 acc[TQ][3];
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
-      for (int i = 0; i < NV; ++i) {
-        const double2* x = src + (size_t)i * mpp * S;
-        const double2 x0 = x[0], x1 = x[1], x2 = x[2];
-        const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
-        const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
-        const double w[TQ] = {wa.x, wa.y, wb.x, wb.y};
-#pragma unroll
-        for (int t = 0; t < TQ; ++t) {
-          acc[t][0].x += w[t] * x0.x; acc[t][0].y += w[t] * x0.y;
-          acc[t][1].x += w[t] * x1.x; acc[t][1].y += w[t] * x1.y;
-          acc[t][2].x += w[t] * x2.x; acc[t][2].y += w[t] * x2.y;
-        }
-      }
-      // ---- finish: rotation, atom permutation, Gamma phase, store ------------------------------------------------------
-      const uint32_t nt = min((uint32_t)TQ, item.len - t0);
-      const uint4 rr4 = *reinterpret_cast<const uint4*>(RI + t0);
-      const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
-      const uint32_t rrs[TQ] = {rr4.x, rr4.y, rr4.z, rr4.w}, qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
-      double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + (size_t)(b0 + b) * S;
-      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu)) {
-        // the four points share the rotation (the chunk is sorted by it): one matrix, one destination atom, no branches
-        const uint32_t ri = rr4.x & 0xffffu;
-        double R[9];
-        {
-          const double* Rs = RS + 9 * ri;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) R[e] = Rs[e];
-        }
-        const uint32_t dest = F0[k * G + ri];
-        const double2* php = PH + (size_t)t0 * NAT + k;
-#pragma unroll
-        for (int t = 0; t < TQ; ++t) {
-          rotate_phase_store(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true,
-                             out_base + (size_t)qis[t] * wrow + 3 * dest);
-        }
-        continue;
-      }
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) {
-        if ((uint32_t)t >= nt) break;
-        const uint32_t qi = t0 + t;
-        uint32_t dest = k;
-        double2* out = out_base + (size_t)qis[t] * wrow;
-        if (kind >= 0) {
-          const uint32_t rr = rrs[t];
-          const uint32_t ri = rr & 0xffffu;
-          double2 ph = make_double2(1.0, 0.0);
-          if (gamma) {
-            dest = F0[k * G + ri];
-            ph = PH[(size_t)qi * NAT + k];
-          }
-          out += 3 * dest;
-          rotate_phase_store(RS + 9 * ri, acc[t][0], acc[t][1], acc[t][2], ph, gamma, out);
-          if (kind == 2) {  // axial: det(R) R^-1 v
-            const double det = a.dd.rot_det[rr >> 16];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) out[c] = make_double2(out[c].x * det, out[c].y * det);
-          }
-        } else {
-          out += 3 * dest;
-          out[0] = acc[t][0];
-          out[1] = acc[t][1];
-          out[2] = acc[t][2];
-        }
-      }
-    }
+    // ---- eigenvalues and eigenvectors of this pass (cell_common.cuh) -----------------------------------------------------
+    CellPass cp;
+    cp.D = D; cp.V = V; cp.W = W; cp.PH = PH; cp.RS = RS; cp.F0 = F0; cp.QI = QI; cp.RI = RI;
+    cp.CH = CH; cp.mpp = mpp; cp.mb = mb; cp.b0 = b0; cp.len = item.len; cp.M = M; cp.S = S; cp.NAT = NAT; cp.no0v = no0v; cp.G = G;
+    cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
+    cell_compute_pass(cp, tid, nthr);
   }
 }
 
