@@ -17,6 +17,7 @@ SOURCES = {
     "locate.cu": ["-fmad=false"],
     "interp.cu": [],
     "cellinterp.cu": [],
+    "cellinterp_tma.cu": [],
     "capi.cu": [],
 }
 

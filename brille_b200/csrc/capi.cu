@@ -95,13 +95,13 @@ struct Workspace {
     WS(lo.tet, int32_t, 1)
     WS(lo.n_vert, int32_t, 1)
     WS(lo.vertex, uint32_t, 8)
-    WS(lo.weight, double, 8)
+    WS(lo.weight, double, REC_DOUBLES)
     WS(lo.slots, uint64_t, 1)
     WS(lo.status, uint32_t, 1)
     WS(key, uint32_t, 1)
     WS(rank, uint32_t, 1)
-    WS(bk.order, uint32_t, 1)
 #undef WS
+    if ((e = get<uint32_t>(&bk.order, n)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&cell_count, nb)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.cell_offset, (size_t)nb + 1)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.n_items, 4)) != cudaSuccess) return e;
@@ -145,11 +145,22 @@ struct b200_grid {
   size_t host_chunk = 0;   // max points per chunk of the host-buffer pipeline (0 = sized from free memory)
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
+  int cell_kernel = 0;     // 0 auto (pipelined kernel when its cell table fits), 1 on-the-fly staging kernel, 2 pipelined only
+  unsigned char* cell_table = nullptr;  // pre-aligned per-cell records (cellinterp_tma.cu), built lazily per fill
+  CellTableDev ct{};
+  bool cell_table_refused = false;      // did not fit: do not try again until the data changes
   uint64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
 };
+
+static void drop_cell_table(b200_grid* g) {
+  if (g->cell_table) cudaFree(g->cell_table);
+  g->cell_table = nullptr;
+  g->ct = CellTableDev{};
+  g->cell_table_refused = false;
+}
 
 // ----------------------------------------------------------------------------------------------------
 // table derivation
@@ -519,6 +530,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
   cudaDeviceSynchronize();
   g->structure_pool.release();
   g->data_pool.release();
+  drop_cell_table(g);
   g->ws.release();
   if (g->d_fail) cudaFree(g->d_fail);
   for (int s = 0; s < 2; ++s) {
@@ -541,6 +553,7 @@ extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
   CU(cudaSetDevice(g->device));
   CU(cudaDeviceSynchronize());
   g->data_pool.release();
+  drop_cell_table(g);
   g->has_data = false;
   if (t->n_vertices != g->n_vertices)
     return fail(B200_E_INVALID, "Provided " + std::to_string(t->n_vertices) + " arrays but " + std::to_string(g->n_vertices) + " were expected!");
@@ -639,7 +652,35 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   // (decided on the size of the whole call, not of the chunk, so that chunking never changes which kernel a point sees)
   if (cell && g->interp_path == 0 && n_call < 4 * (size_t)nb) cell = false;
   uint32_t mpp = 0, chunk = g->chunk;
-  if (cell) {
+  bool tma = false;
+  if (cell && g->cell_kernel != 1) {
+    // pipelined kernel: needs the per-cell records, built once per fill (synchronously: the two host-pipeline streams share it)
+    const uint32_t ch = cell_tma_pick(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 108 * 1024, &mpp);
+    if (ch && mpp) {
+      if (g->cell_table && g->ct.mpp == mpp) {
+        tma = true;
+      } else if (!g->cell_table_refused) {
+        if (g->cell_table) drop_cell_table(g);
+        const CellTableDev ct = cell_table_layout(g->dd, g->gd.cells.n_cubes, g->gd.cells.n_tets, mpp);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        if (ct.total_bytes <= free_b / 4 && cudaMalloc(&g->cell_table, ct.total_bytes) == cudaSuccess) {
+          CU(launch_build_cell_table(g->dd, g->gd.cells.cube_vertices, g->gd.cells.tet_vertices, ct, g->cell_table, g->sm_count, stream));
+          CU(cudaStreamSynchronize(stream));
+          g->ct = ct;
+          g->launches += 1;
+          tma = true;
+        } else {
+          (void)cudaGetLastError();
+          g->cell_table = nullptr;
+          g->cell_table_refused = true;
+        }
+      }
+      if (tma) chunk = ch;
+    }
+    if (!tma && g->cell_kernel == 2) return fail(B200_E_CUDA, "the cell table of the pipelined kernel does not fit in device memory");
+  }
+  if (cell && !tma) {
     chunk = cell_pick_chunk(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 100 * 1024, &mpp);
     if (chunk == 0 || mpp == 0) {
       cell = false;
@@ -679,7 +720,8 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     a.vecs_out = dvecs;
     a.ir = ir;
     a.modes_per_pass = mpp;
-    CU(launch_interp_cell(a, n, stream));
+    if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream));
+    else CU(launch_interp_cell(a, n, stream));
     // points that are not generic members of their cell (and failed points): general kernel over the last bucket
     CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, ws.bk.order, ws.bk.n_items));
     g->launches += 2;
@@ -734,8 +776,10 @@ static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_
 #define CP(dst, src, type, per) if (dprobe->dst) CU(cudaMemcpyAsync(dprobe->dst, src, nQ * (per) * sizeof(type), cudaMemcpyDeviceToDevice, stream));
     CP(q_ir, lo.q_ir, double, 3) CP(x_ir, g->ws.x_ir, double, 3) CP(tau, g->ws.tau, int32_t, 3) CP(ridx, lo.ridx, int32_t, 1)
     CP(invridx, lo.invridx, int32_t, 1) CP(cell, lo.cell, uint32_t, 1) CP(tet, lo.tet, int32_t, 1) CP(n_vert, lo.n_vert, int32_t, 1)
-    CP(vertex, lo.vertex, uint32_t, 8) CP(weight, lo.weight, double, 8) CP(status, lo.status, uint32_t, 1)
+    CP(vertex, lo.vertex, uint32_t, 8) CP(status, lo.status, uint32_t, 1)
 #undef CP
+    if (dprobe->weight && nQ)  // the weight rows are the heads of the 96-byte point records
+      CU(cudaMemcpy2DAsync(dprobe->weight, 8 * sizeof(double), lo.weight, REC_BYTES, 8 * sizeof(double), nQ, cudaMemcpyDeviceToDevice, stream));
   }
   if (n_failed) {
     unsigned long long c[3];
@@ -807,7 +851,9 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       CP(invridx, w.invridx, int32_t, 1) CP(status, w.status, uint32_t, 1)
       if (!(mode & MODE_NO_LOCATE)) {
         CP(cell, w.cell, uint32_t, 1) CP(tet, w.tet, int32_t, 1) CP(n_vert, w.n_vert, int32_t, 1)
-        CP(vertex, w.vertex, uint32_t, 8) CP(weight, w.weight, double, 8)
+        CP(vertex, w.vertex, uint32_t, 8)
+        if (probe->weight && n)
+          CU(cudaMemcpy2DAsync(probe->weight + lo * 8, 8 * sizeof(double), w.weight, REC_BYTES, 8 * sizeof(double), n, cudaMemcpyDeviceToHost, h.stream));
       }
 #undef CP
     }
@@ -891,6 +937,9 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   if (n == "interp_path") {
     if (value < 0 || value > 2) return fail(B200_E_INVALID, "interp_path must be 0 (auto), 1 (general) or 2 (cell-batched)");
     g->interp_path = (int)value;
+  } else if (n == "cell_kernel") {
+    if (value < 0 || value > 2) return fail(B200_E_INVALID, "cell_kernel must be 0 (auto), 1 (on-the-fly staging) or 2 (pipelined, cell table)");
+    g->cell_kernel = (int)value;
   } else if (n == "chunk") {
     if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads

@@ -5,6 +5,18 @@
 
 namespace b200 {
 
+// Store 48 contiguous bytes at a 16-byte aligned address as one aligned 32-byte store (sm_100 STG.256) plus one 16-byte
+// store.  Consecutive lanes hold consecutive 48-byte pieces, so within each of the two instructions the lanes cover whole
+// 32-byte sectors: L2 receives one full-sector write per sector instead of three partial ones from three 16-byte stores.
+__device__ __forceinline__ void store48(double2* out, const double2 o0, const double2 o1, const double2 o2) {
+  const bool even = (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
+  const double2 lo = even ? o0 : o1, hi = even ? o1 : o2, single = even ? o2 : o0;
+  double2* const p32 = even ? out : out + 1;
+  double2* const p16 = even ? out + 2 : out;
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p32), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p16), "d"(single.x), "d"(single.y) : "memory");
+}
+
 // out = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
 // that finishes a point produces the same bits (the result must not depend on which path a point happens to take)
 __device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
@@ -17,14 +29,32 @@ __device__ __forceinline__ void rotate_phase_store(const double* R, const double
   u2.x = __fma_rn(R[8], a2.x, __fma_rn(R[7], a1.x, __dmul_rn(R[6], a0.x)));
   u2.y = __fma_rn(R[8], a2.y, __fma_rn(R[7], a1.y, __dmul_rn(R[6], a0.y)));
   if (use_phase) {
-    out[0] = make_double2(__fma_rn(-ph.y, u0.y, __dmul_rn(ph.x, u0.x)), __fma_rn(ph.y, u0.x, __dmul_rn(ph.x, u0.y)));
-    out[1] = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
-    out[2] = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
-  } else {
-    out[0] = u0;
-    out[1] = u1;
-    out[2] = u2;
+    u0 = make_double2(__fma_rn(-ph.y, u0.y, __dmul_rn(ph.x, u0.x)), __fma_rn(ph.y, u0.x, __dmul_rn(ph.x, u0.y)));
+    u1 = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
+    u2 = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
   }
+  store48(out, u0, u1, u2);
+}
+
+// Phase that aligns a vertex' eigenvector to the pivot's (utilities.tpp:567-579): z = <d_pivot|d_v>, factor
+// e^{-i arg z} = conj(z)/|z| (the reference evaluates polar(1, -atan2(Im z, Re z)), the same number up to rounding;
+// z == 0 gives 1 in both).  Explicit fused operations: the on-the-fly kernel and the cell-table builder must agree bitwise.
+__device__ __forceinline__ void align_accumulate(const double2 p0, const double2 x, double& re, double& im) {
+  re = __fma_rn(p0.y, x.y, __fma_rn(p0.x, x.x, re));
+  im = __fma_rn(-p0.y, x.x, __fma_rn(p0.x, x.y, im));
+}
+__device__ __forceinline__ double2 align_factor(double re, double im) {
+  const double m = fmax(fabs(re), fabs(im));
+  double2 f = make_double2(1.0, 0.0);
+  if (m > 0.0) {
+    const double r = re / m, q = im / m;
+    const double n = 1.0 / sqrt(__fma_rn(q, q, __dmul_rn(r, r)));
+    f = make_double2(__dmul_rn(r, n), -__dmul_rn(q, n));
+  }
+  return f;
+}
+__device__ __forceinline__ double2 align_apply(const double2 f, const double2 x) {
+  return make_double2(__fma_rn(-f.y, x.y, __dmul_rn(f.x, x.x)), __fma_rn(f.y, x.x, __dmul_rn(f.x, x.y)));
 }
 
 // dynamic shared memory carve-up (all offsets 16-byte aligned)
@@ -84,22 +114,43 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
   struct { uint32_t len; } item = {c.len};
   struct { const double* rot_det; } dd_ = {c.rot_det};
   struct { double* vals_out; double* vecs_out; decltype(dd_) dd; } a = {c.vals_out, c.vecs_out, dd_};
-    // ---- eigenvalues: plain weighted sum ---------------------------------------------------------------------------
-    for (uint32_t p = tid; p < item.len * mb * no0v; p += nthr) {
-      const uint32_t t = p / (mb * no0v), r = p - t * (mb * no0v);
-      double acc = 0.0;
-      for (int i = 0; i < NV; ++i) acc += W[(size_t)i * CH + t] * V[(size_t)i * mpp * no0v + r];
-      a.vals_out[(size_t)QI[t] * vrow + (size_t)b0 * no0v + r] = acc;
+    // ---- eigenvalues: plain weighted sum; a task is one value column for TQ consecutive points ------------------------
+    constexpr int TQ = 4;
+    const uint32_t ntile = (item.len + TQ - 1) / TQ;
+    {
+      const uint32_t per_v = mb * no0v;
+      for (uint32_t task = tid; task < ntile * per_v; task += nthr) {
+        const uint32_t tile = task / per_v, r = task - tile * per_v, t0 = tile * TQ;
+        double acc[TQ] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < NV; ++i) {
+          const double v = V[(size_t)i * mpp * no0v + r];
+          const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
+          const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
+          acc[0] = __fma_rn(wa.x, v, acc[0]);
+          acc[1] = __fma_rn(wa.y, v, acc[1]);
+          acc[2] = __fma_rn(wb.x, v, acc[2]);
+          acc[3] = __fma_rn(wb.y, v, acc[3]);
+        }
+        const uint32_t nt = min((uint32_t)TQ, item.len - t0);
+        const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
+        const uint32_t qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
+#pragma unroll
+        for (int t = 0; t < TQ; ++t)
+          if ((uint32_t)t < nt) a.vals_out[(size_t)qis[t] * vrow + (size_t)b0 * no0v + r] = acc[t];
+      }
     }
     // ---- eigenvectors: weighted sum of pre-phased rows, rotation, atom permutation, Gamma phase ----------------------
     // A task is one 3-vector (mode b, atom k) for TQ consecutive points: the three complex numbers of every corner are
     // read from shared memory once and reused for the TQ points (register tile), which makes the loop FP64-bound
     // instead of shared-memory-bound.
-    constexpr int TQ = 4;
     const uint32_t per_q = mb * NAT;
-    const uint32_t ntile = (item.len + TQ - 1) / TQ;
-    for (uint32_t task = tid; task < ntile * per_q; task += nthr) {
-      const uint32_t tile = task / per_q, r = task - tile * per_q, b = r / NAT, k = r - b * NAT;
+    // task -> (tile, r = b * NAT + k) is advanced incrementally: no integer division in the loop
+    const uint32_t step_tile = (uint32_t)nthr / per_q, step_r = (uint32_t)nthr - step_tile * per_q;
+    const uint32_t nat_magic = 0xffffffffu / NAT + 1u;  // floor(r / NAT) == umulhi(r, magic) for r * NAT < 2^32
+    uint32_t tile = (uint32_t)tid / per_q, r = (uint32_t)tid - tile * per_q;
+    for (uint32_t task = tid; task < ntile * per_q; task += nthr, tile += step_tile, r += step_r) {
+      if (r >= per_q) { r -= per_q; ++tile; }
+      const uint32_t b = NAT == 1u ? r : __umulhi(r, nat_magic), k = r - b * NAT;
       const uint32_t t0 = tile * TQ;
       const double2* src = D + (size_t)b * S + 3 * k;
       double2 acc[TQ][3];
@@ -161,13 +212,11 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
           if (kind == 2) {  // axial: det(R) R^-1 v
             const double det = a.dd.rot_det[rr >> 16];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) out[c] = make_double2(out[c].x * det, out[c].y * det);
+            for (int c = 0; c < 3; ++c) out[c] = make_double2(out[c].x * det, out[c].y * det);  // (rare path: read back)
           }
         } else {
           out += 3 * dest;
-          out[0] = acc[t][0];
-          out[1] = acc[t][1];
-          out[2] = acc[t][2];
+          store48(out, acc[t][0], acc[t][1], acc[t][2]);
         }
       }
     }

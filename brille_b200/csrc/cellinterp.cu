@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
     my_q = a.bk.order[item.start + tid];
     my_r = a.ridx[my_q];
     my_inv = a.invridx[my_q];
-    const double2* wp = reinterpret_cast<const double2*>(a.weight + 8 * (size_t)my_q);
+    const double2* wp = reinterpret_cast<const double2*>(a.weight + REC_DOUBLES * (size_t)my_q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) my_w[j] = wp[j];
     if (gamma) {
@@ -194,18 +194,8 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       const double2* d0 = D + (size_t)b * S;  // pivot (emission index 0) keeps its own branch
       const double2* dx = D + ((size_t)i * mpp + b) * S;
       double re = 0.0, im = 0.0;
-      for (uint32_t e = 0; e < S; ++e) {
-        const double2 p0 = d0[e], x = dx[e];
-        re += p0.x * x.x + p0.y * x.y;
-        im += p0.x * x.y - p0.y * x.x;
-      }
-      const double m = fmax(fabs(re), fabs(im));
-      double2 f = make_double2(1.0, 0.0);
-      if (m > 0.0) {
-        const double r = re / m, q = im / m;
-        const double n = 1.0 / sqrt(r * r + q * q);
-        f = make_double2(r * n, -q * n);
-      }
+      for (uint32_t e = 0; e < S; ++e) align_accumulate(d0[e], dx[e], re, im);
+      const double2 f = align_factor(re, im);
       PHI[pr] = f;
     }
     __syncthreads();
@@ -213,8 +203,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
       const uint32_t pr = idx / S, e = idx - pr * S, i = 1 + pr / mb, b = pr - (i - 1) * mb;
       const double2 f = PHI[pr];
       double2* dx = D + ((size_t)i * mpp + b) * S + e;
-      const double2 x = *dx;
-      *dx = make_double2(f.x * x.x - f.y * x.y, f.x * x.y + f.y * x.x);
+      *dx = align_apply(f, *dx);
     }
     __syncthreads();
     if (b0 == 0) {
@@ -253,7 +242,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
           // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
           for (uint32_t k = 0; k < NAT; ++k) {
             const double* gv = a.dd.gamma_vectors + 3 * (size_t)a.dd.gamma_vidx[(size_t)k * G + mi];
-            const double dot = ((0.0 + my_qir[0] * gv[0]) + my_qir[1] * gv[1]) + my_qir[2] * gv[2];
+            const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(my_qir[0], gv[0])), __dmul_rn(my_qir[1], gv[1])), __dmul_rn(my_qir[2], gv[2]));
             double sn, cs;
             sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
             PH[(size_t)t * NAT + k] = make_double2(cs, sn);

@@ -1,0 +1,437 @@
+// cellinterp_tma.cu -- the cell-batched interpolation stage, persistent and software-pipelined (the default fast path).
+//
+// Same arithmetic as cellinterp.cu (interpolator_at.tpp:91-127 + interpolator_gamma.tpp:49-139).  Two things change:
+//
+//   1. CELL TABLE.  Everything the on-the-fly kernel derives while staging a cell -- which vertex rows, the permutation
+//      of their modes relative to the pivot (interpolatordual.hpp:374-382) and the phase e^{-i arg<d_pivot|d_v>} that
+//      aligns every vertex' eigenvector to the pivot's (utilities.tpp:567-579) -- depends only on (cell, fill data).
+//      k_build_cell_table evaluates it ONCE per fill() into one contiguous record per cell and per pass of modes:
+//          [ D: NV x mpp x S complex | V: NV x mpp x no0v double ]
+//      (NV = 8 cube / 4 tetrahedron, emission order of trellis_node.hpp:143-147,285-287).  A record is exactly what
+//      the compute pass wants in shared memory, so staging a cell becomes one bulk asynchronous copy (TMA,
+//      cp.async.bulk + mbarrier) issued by one thread.
+//
+//   2. PERSISTENT CTAs.  Each CTA walks a contiguous range of the work items (cell, <= chunk points) produced by the
+//      counting sort.  While item n is computed, the record of the next cell is already in flight into the other
+//      half of a double buffer, the per-point records of item n+1 (weights, q_ir, rotation indices; gathered through
+//      the sort order) are in flight as cp.async copies and the sort order of item n+2 sits in a register.
+//      Consecutive items of the same cell reuse the staged record.  Rotation tables and the Gamma vectors are loaded
+//      once per CTA.
+#include "cell_common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, bulk copy (TMA without tensor map)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cell table
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t cell_tile_bytes(uint32_t nv, uint32_t mpp, uint32_t S, uint32_t no0v) {
+  return (size_t)nv * mpp * ((size_t)S * 16 + (size_t)no0v * 8);  // nv is 4 or 8: always a multiple of 16
+}
+__host__ __device__ inline size_t cell_record_offset(const CellTableDev& ct, uint32_t key) {
+  return key < ct.n_cubes ? (size_t)key * ct.cube_bytes : (size_t)ct.n_cubes * ct.cube_bytes + (size_t)(key - ct.n_cubes) * ct.tet_bytes;
+}
+
+// one thread per (cell, emitted vertex, padded mode)
+__global__ void __launch_bounds__(256) k_build_cell_table(DataDev dd, const uint32_t* __restrict__ cube_vertices,
+                                                          const uint32_t* __restrict__ tet_vertices, CellTableDev ct,
+                                                          unsigned char* __restrict__ table) {
+  const InterpDev& vals = dd.values;
+  const InterpDev& vecs = dd.vectors;
+  const uint32_t M = vecs.branches, S = vecs.span, no0v = vals.span, mpp = ct.mpp;
+  const uint32_t padded = ct.n_pass * mpp;
+  const size_t n_cube_rows = (size_t)ct.n_cubes * 8 * padded, n_rows = n_cube_rows + (size_t)ct.n_tets * 4 * padded;
+  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_rows; g += (size_t)gridDim.x * blockDim.x) {
+    const bool is_cube = g < n_cube_rows;
+    const uint32_t NV = is_cube ? 8u : 4u;
+    const size_t gl = is_cube ? g : g - n_cube_rows;
+    const uint32_t cellidx = (uint32_t)(gl / ((size_t)NV * padded));
+    const uint32_t rem = (uint32_t)(gl - (size_t)cellidx * NV * padded);
+    const uint32_t i = rem / padded, bb = rem - i * padded, pass = bb / mpp, bl = bb - pass * mpp;
+    const uint32_t key = is_cube ? cellidx : ct.n_cubes + cellidx;
+    unsigned char* rec = table + cell_record_offset(ct, key) + (size_t)pass * cell_tile_bytes(NV, mpp, S, no0v);
+    double2* Drow = reinterpret_cast<double2*>(rec) + ((size_t)i * mpp + bl) * S;
+    double* Vrow = reinterpret_cast<double*>(rec + (size_t)NV * mpp * S * 16) + ((size_t)i * mpp + bl) * no0v;
+    if (bb >= M) {  // padding of the last pass
+      for (uint32_t e = 0; e < S; ++e) Drow[e] = make_double2(0.0, 0.0);
+      for (uint32_t e = 0; e < no0v; ++e) Vrow[e] = 0.0;
+      continue;
+    }
+    // emission order: cube corner 7-j (trellis_node.hpp:143-147), tetrahedron corner j (:285-287); pivot = first emitted
+    const uint32_t slot = is_cube ? 7u - i : i, pslot = is_cube ? 7u : 0u;
+    const uint32_t* cv = is_cube ? cube_vertices + (size_t)cellidx * 8 : tet_vertices + (size_t)cellidx * 4;
+    const uint32_t v = cv[slot], v0 = cv[pslot];
+    uint32_t pb = bb, pb0 = bb;
+    if (dd.n_perm_rows > 1) {
+      const uint32_t* pt = is_cube ? dd.cube_perm + (size_t)cellidx * 64 + pslot * 8 : dd.tet_perm + (size_t)cellidx * 16 + pslot * 4;
+      pb = dd.perm_rows[(size_t)pt[slot] * M + bb];
+      pb0 = dd.perm_rows[(size_t)pt[pslot] * M + bb];
+    }
+    const double2* src = reinterpret_cast<const double2*>(vecs.data) + (size_t)v * wrow + (size_t)pb * S;
+    if (i == 0) {
+      for (uint32_t e = 0; e < S; ++e) Drow[e] = src[e];
+    } else {
+      const double2* piv = reinterpret_cast<const double2*>(vecs.data) + (size_t)v0 * wrow + (size_t)pb0 * S;
+      double re = 0.0, im = 0.0;
+      for (uint32_t e = 0; e < S; ++e) align_accumulate(piv[e], src[e], re, im);
+      const double2 f = align_factor(re, im);
+      for (uint32_t e = 0; e < S; ++e) Drow[e] = align_apply(f, src[e]);
+    }
+    const double* vsrc = vals.data + (size_t)v * vrow + (size_t)pb * no0v;
+    for (uint32_t e = 0; e < no0v; ++e) Vrow[e] = vsrc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared memory plan of the pipelined kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct TmaPlan {
+  size_t D0, D1, RW, RQ, RR, RV, W, PH, RS, F0, GV, QI, RI, MQ, BAR, total;
+};
+__host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk,
+                                                 uint32_t n_at, uint32_t G, bool gamma) {
+  TmaPlan p;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+  const size_t tile = cell_tile_bytes(nvmax, mpp, S, no0v);
+  p.D0 = take(tile);
+  p.D1 = take(tile);
+  p.RW = take((size_t)chunk * REC_BYTES);  // raw per-point records of the next item, in flight as one bulk copy
+  p.RQ = take(0);
+  p.RR = take(0);
+  p.RV = take(0);
+  p.W = take((size_t)nvmax * chunk * 8);
+  p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
+  p.RS = take((size_t)G * 9 * 8);
+  p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
+  p.GV = take(gamma ? (size_t)n_at * G * 24 : 0);
+  p.QI = take((size_t)chunk * 4);
+  p.RI = take((size_t)chunk * 4);
+  p.MQ = take(0);
+  p.BAR = take(32);
+  p.total = o;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t NO_ITEM = 0xffffffffu;
+constexpr uint32_t ITEM_BLOCK = 4;
+
+__global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTableDev ct, const unsigned char* __restrict__ table) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const InterpDev& vals = a.dd.values;
+  const InterpDev& vecs = a.dd.vectors;
+  const uint32_t M = vecs.branches, S = vecs.span, NAT = vecs.no1, no0v = vals.span, G = a.dd.n_ops;
+  const int kind = a.ir ? vecs.rot_kind : -1;
+  const bool gamma = kind >= 3;
+  const uint32_t mpp = ct.mpp, n_pass = ct.n_pass, CH = a.bk.chunk;
+  const TmaPlan pl = plan_smem_tma(a.n_cubes ? 8u : 4u, mpp, S, no0v, CH, NAT, G, gamma);
+  unsigned char* const D0p = smem + pl.D0;
+  unsigned char* const D1p = smem + pl.D1;
+  double* RW = reinterpret_cast<double*>(smem + pl.RW);
+  double* W = reinterpret_cast<double*>(smem + pl.W);
+  double2* PH = reinterpret_cast<double2*>(smem + pl.PH);
+  double* RS = reinterpret_cast<double*>(smem + pl.RS);
+  uint32_t* F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
+  double* GV = reinterpret_cast<double*>(smem + pl.GV);
+  uint32_t* QI = reinterpret_cast<uint32_t*>(smem + pl.QI);
+  uint32_t* RI = reinterpret_cast<uint32_t*>(smem + pl.RI);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.BAR);
+  __shared__ uint32_t s_hist[64];
+
+  // ---- this CTA's work items: blocks of ITEM_BLOCK consecutive items (same-cell reuse), dealt round-robin to the CTAs
+  // (the item list is ordered cubes first, then tetrahedra: a cyclic deal gives every CTA the same mix of both) ----------
+  const uint32_t n_items = a.bk.n_items[0];
+  if (blockIdx.x * ITEM_BLOCK >= n_items) return;
+  const uint32_t it1 = n_items;
+  // local item l -> global item ((l / ITEM_BLOCK) * gridDim.x + blockIdx.x) * ITEM_BLOCK + l % ITEM_BLOCK (monotonic in l)
+#define GLOBAL_ITEM(l_) ((((l_) / ITEM_BLOCK) * gridDim.x + blockIdx.x) * ITEM_BLOCK + ((l_) % ITEM_BLOCK))
+
+  // ---- per-CTA constants ---------------------------------------------------------------------------------------------
+  {
+    const double* src = nullptr;
+    switch (kind) {
+      case 0: src = a.dd.rot_int; break;                  // R
+      case 1: src = a.dd.rot_int + 9 * (size_t)G; break;  // R^T
+      case 2: src = a.dd.rot_int; break;                  // R^-1 = R[invridx]
+      case 3: src = a.dd.rot_int; break;
+      case 4: src = a.dd.rot_cart; break;
+      default: break;
+    }
+    if (src)
+      for (uint32_t i = tid; i < G * 9; i += nthr) RS[i] = src[i];
+    if (gamma) {
+      for (uint32_t i = tid; i < NAT * G; i += nthr) {
+        F0[i] = a.dd.gamma_F0[i];
+        const double* gv = a.dd.gamma_vectors + 3 * (size_t)a.dd.gamma_vidx[i];
+        GV[3 * i] = gv[0];
+        GV[3 * i + 1] = gv[1];
+        GV[3 * i + 2] = gv[2];
+      }
+    }
+    if (tid < 64) s_hist[tid] = 0;
+    if (tid == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      mbar_init(&bar[2], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  // an item is (key, start, len); three scalars each so that the descriptors stay in registers
+#define LOAD_ITEM(it_, key_, start_, len_)                                \
+  do {                                                                    \
+    key_ = NO_ITEM; start_ = 0; len_ = 0;                                 \
+    const uint32_t gi_ = GLOBAL_ITEM(it_);                                \
+    if (gi_ < it1) {                                                      \
+      const CellItem* ci_ = a.bk.items + gi_;                             \
+      key_ = ci_->key; start_ = ci_->start; len_ = ci_->len;              \
+    }                                                                     \
+  } while (0)
+  auto issue_tile = [&](uint32_t key, uint32_t pass, int b) {  // one thread
+    const uint32_t nv = key < a.n_cubes ? 8u : 4u;
+    const uint32_t bytes = (uint32_t)cell_tile_bytes(nv, mpp, S, no0v);
+    const unsigned char* src = table + cell_record_offset(ct, key) + (size_t)pass * bytes;
+    mbar_expect_tx(bar + b, bytes);
+    bulk_g2s(b ? D1p : D0p, src, bytes, bar + b);
+  };
+  // raw records of an item: every thread fetches the 96-byte record of its own point with one bulk copy; all of them
+  // complete on bar[2], on which thread 0 announces the total
+  auto issue_raw = [&](uint32_t q, bool has, uint32_t len) {
+    if (tid == 0) mbar_expect_tx(bar + 2, len * REC_BYTES);
+    if (has) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_BYTES, bar + 2);
+  };
+
+  // descriptors of items n, n+1, n+2 (n+3 is loaded while n is processed, so that no load waits on the one before it)
+  uint32_t cur_key, cur_start, cur_len, nxt_key, nxt_start, nxt_len, nn_key, nn_start, nn_len;
+  LOAD_ITEM(0u, cur_key, cur_start, cur_len);
+  LOAD_ITEM(1u, nxt_key, nxt_start, nxt_len);
+  LOAD_ITEM(2u, nn_key, nn_start, nn_len);
+  int buf = 0;
+  uint32_t parity = 0u;  // bit b = phase parity of bar[b]
+  bool fresh = true;
+  issue_raw((uint32_t)tid < cur_len ? a.bk.order[cur_start + tid] : 0u, (uint32_t)tid < cur_len, cur_len);
+  uint32_t q_nxt = (uint32_t)tid < nxt_len ? a.bk.order[nxt_start + tid] : 0u;  // sort order, two items ahead of its use
+  if (tid == 0) issue_tile(cur_key, 0, 0);
+
+  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
+  (void)vrow; (void)wrow;
+  for (uint32_t it = 0; cur_key != NO_ITEM; ++it) {
+    const bool is_cube = cur_key < a.n_cubes;
+    const int NV = is_cube ? 8 : 4;
+    uint32_t n3_key = NO_ITEM, n3_start = 0, n3_len = 0, q_nn = 0;
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      const uint32_t b0 = pass * mpp, mb = min(mpp, M - b0);
+      if (pass == 0) {
+        // ---- per-point records of this item: raw (bulk copies on bar[2]) -> sorted by rotation matrix -----------------------
+        mbar_wait(bar + 2, (parity >> 2) & 1u);
+        parity ^= 4u;
+        const bool has = (uint32_t)tid < cur_len;
+        const double* rec = RW + REC_DOUBLES * (size_t)tid;  // this thread's raw record: weight[8] | q_ir[3] | rot, index
+        uint32_t my_q = 0, mi = 0, my_rank = 0;
+        int my_r = 0;
+        if (has) {
+          const uint2 ri2 = *reinterpret_cast<const uint2*>(rec + 11);
+          my_q = ri2.y;
+          const uint32_t rot = ri2.x;
+          my_r = (int)(rot & 0xffffu);
+          const int my_inv = (int)(rot >> 16);
+          // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+          mi = (uint32_t)((kind == 0 || kind == 1) ? my_r : my_inv);
+          my_rank = atomicAdd(&s_hist[mi], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive scan of <= 64 bins by one warp
+          const uint32_t c0 = s_hist[tid], c1 = s_hist[tid + 32];
+          uint32_t x0 = c0, x1 = c1;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+            if (tid >= o) { x0 += y0; x1 += y1; }
+          }
+          const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
+          s_hist[tid] = x0 - c0;
+          s_hist[tid + 32] = tot0 + x1 - c1;
+        }
+        __syncthreads();
+        if (has) {
+          const uint32_t t = s_hist[mi] + my_rank;
+          QI[t] = my_q;
+          RI[t] = mi | ((uint32_t)my_r << 16);
+          const double2* rw = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (2 * j < NV) {
+              const double2 w2 = rw[j];
+              W[(size_t)(2 * j) * CH + t] = w2.x;
+              W[(size_t)(2 * j + 1) * CH + t] = w2.y;
+            }
+          }
+          if (gamma) {
+            // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
+            const double q0 = rec[8], q1 = rec[9], q2 = rec[10];
+            for (uint32_t k = 0; k < NAT; ++k) {
+              const double* gv = GV + 3 * ((size_t)k * G + mi);
+              const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q0, gv[0])), __dmul_rn(q1, gv[1])), __dmul_rn(q2, gv[2]));
+              double sn, cs;
+              sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
+              PH[(size_t)t * NAT + k] = make_double2(cs, sn);
+            }
+          }
+        } else if ((uint32_t)tid < ((cur_len + 3u) & ~3u)) {  // padding points of the last register tile carry zero weight
+          for (int i = 0; i < NV; ++i) W[(size_t)i * CH + tid] = 0.0;
+          QI[tid] = 0;
+          RI[tid] = 0;
+        }
+        __syncthreads();  // sorted records visible; raw records and the histogram are free again
+        if (tid < 64) s_hist[tid] = 0;
+        // ---- keep the pipeline full: raw records of item n+1, descriptor of item n+3 -----------------------------------
+        if (nxt_key != NO_ITEM) issue_raw(q_nxt, (uint32_t)tid < nxt_len, nxt_len);
+        q_nn = (uint32_t)tid < nn_len ? a.bk.order[nn_start + tid] : 0u;
+        LOAD_ITEM(it + 3, n3_key, n3_start, n3_len);
+      }
+      // ---- prefetch the next tile into the other buffer (its last readers finished before the previous barrier) ------
+      uint32_t nkey = NO_ITEM, npass = 0;
+      if (pass + 1 < n_pass) { nkey = cur_key; npass = pass + 1; }
+      else if (nxt_key != NO_ITEM) { nkey = nxt_key; npass = 0; }
+      const bool reuse_next = n_pass == 1 && nkey == cur_key;
+      const bool load_next = nkey != NO_ITEM && !reuse_next;
+      if (load_next && tid == 0) issue_tile(nkey, npass, buf ^ 1);
+      if (fresh) {
+        mbar_wait(bar + buf, (parity >> buf) & 1u);
+        parity ^= 1u << buf;
+      }
+      // ---- eigenvalues and eigenvectors of this pass (cell_common.cuh) ---------------------------------------------------
+      CellPass cp;
+      unsigned char* const Dcur = buf ? D1p : D0p;
+      cp.D = reinterpret_cast<const double2*>(Dcur);
+      cp.V = reinterpret_cast<const double*>(Dcur + (size_t)NV * mpp * S * 16);
+      cp.W = W; cp.PH = PH; cp.RS = RS; cp.F0 = F0; cp.QI = QI; cp.RI = RI;
+      cp.CH = CH; cp.mpp = mpp; cp.mb = mb; cp.b0 = b0; cp.len = cur_len; cp.M = M; cp.S = S; cp.NAT = NAT; cp.no0v = no0v; cp.G = G;
+      cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
+      cell_compute_pass(cp, tid, nthr);
+      __syncthreads();  // every reader of this tile and of the sorted records is done
+      if (load_next) buf ^= 1;
+      fresh = load_next;
+    }
+    cur_key = nxt_key; cur_start = nxt_start; cur_len = nxt_len;
+    nxt_key = nn_key; nxt_start = nn_start; nxt_len = nn_len;
+    nn_key = n3_key; nn_start = n3_start; nn_len = n3_len;
+    q_nxt = q_nn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+// modes per pass / points per item of the pipelined kernel for `budget` bytes of dynamic shared memory
+uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out) {
+  const bool gamma = dd.vectors.rot_kind >= 3;
+  const uint32_t M = dd.vectors.branches;
+  uint32_t best_chunk = 0, best_mpp = 0;
+  for (uint32_t chunk = preferred; chunk >= 32; chunk /= 2) {
+    uint32_t mpp = 0;
+    for (uint32_t m = M; m >= 1; --m)
+      if (plan_smem_tma(has_cubes ? 8u : 4u, m, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) {
+        mpp = m;
+        break;
+      }
+    if (mpp == 0) continue;
+    if (best_chunk == 0) { best_chunk = chunk; best_mpp = mpp; }
+    if (8 * mpp >= M) { best_chunk = chunk; best_mpp = mpp; break; }  // at most 8 passes: stop shrinking the chunk
+    if (mpp > best_mpp) { best_chunk = chunk; best_mpp = mpp; }
+  }
+  if (best_mpp) {  // equalise the passes (same count, smaller padding)
+    const uint32_t n_pass = (M + best_mpp - 1) / best_mpp;
+    best_mpp = (M + n_pass - 1) / n_pass;
+  }
+  *mpp_out = best_mpp;
+  return best_chunk;
+}
+
+CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_tets, uint32_t mpp) {
+  CellTableDev ct{};
+  ct.n_cubes = n_cubes;
+  ct.n_tets = n_tets;
+  ct.mpp = mpp;
+  ct.n_pass = (dd.vectors.branches + mpp - 1) / mpp;
+  ct.cube_bytes = (uint64_t)ct.n_pass * cell_tile_bytes(8, mpp, dd.vectors.span, dd.values.span);
+  ct.tet_bytes = (uint64_t)ct.n_pass * cell_tile_bytes(4, mpp, dd.vectors.span, dd.values.span);
+  ct.total_bytes = (uint64_t)n_cubes * ct.cube_bytes + (uint64_t)n_tets * ct.tet_bytes;
+  return ct;
+}
+
+cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vertices, const uint32_t* tet_vertices,
+                                    const CellTableDev& ct, unsigned char* table, int sm_count, cudaStream_t stream) {
+  const size_t rows = ((size_t)ct.n_cubes * 8 + (size_t)ct.n_tets * 4) * ct.n_pass * ct.mpp;
+  if (rows == 0) return cudaSuccess;
+  const size_t want = (rows + 255) / 256, cap = (size_t)sm_count * 32;
+  k_build_cell_table<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(dd, cube_vertices, tet_vertices, ct, table);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
+                                   int sm_count, cudaStream_t stream) {
+  const DataDev& dd = args.dd;
+  const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
+  const size_t smem = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const size_t max_items = (n + args.bk.chunk - 1) / args.bk.chunk + (args.bk.n_buckets - 1);
+  static int ctas_per_sm = 0;
+  static size_t occ_smem = 0;
+  if (occ_smem != smem) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+    occ_smem = smem;
+  }
+  size_t grid = (size_t)sm_count * (size_t)ctas_per_sm;
+  const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
+  if (grid > max_blocks) grid = max_blocks;
+  if (grid == 0) return cudaSuccess;
+  k_interp_cell_tma<<<(unsigned)grid, 256, smem, stream>>>(args, ct, table);
+  return cudaGetLastError();
+}
+
+#undef LOAD_ITEM
+#undef GLOBAL_ITEM
+}  // namespace b200

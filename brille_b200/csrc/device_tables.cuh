@@ -101,6 +101,11 @@ struct GridDev {
   CellsDev cells;
 };
 
+// The weight row of a point is the head of a 96-byte record (3 whole sectors) that holds everything the cell-batched
+// interpolation needs about the point:  weight[8] | q_ir[3] | (ridx | invridx << 16 , point index).  The pipelined cell
+// kernel fetches it with one bulk copy per point.
+constexpr uint32_t REC_DOUBLES = 12, REC_BYTES = 96;
+
 // per-Q result of the locate stage, consumed by the interpolation stage (SoA, all device pointers)
 struct LocateOut {
   double* q_ir;      // (n,3)
@@ -112,7 +117,7 @@ struct LocateOut {
   int32_t* tet;      // (n) global tetrahedron index or -1
   int32_t* n_vert;   // (n)
   uint32_t* vertex;  // (n,8)
-  double* weight;    // (n,8)
+  double* weight;    // (n,REC_DOUBLES): 8 weights + the rest of the point's record
   uint64_t* slots;   // (n) 8 packed corner slots (emission order), byte j = slot of emitted vertex j
   uint32_t* status;  // (n)
   // bucketing for the cell-batched interpolation kernel (all optional: NULL => not bucketed)
@@ -194,6 +199,14 @@ struct CellArgs {
   uint32_t modes_per_pass;  // modes staged per pass (<= branches)
 };
 
+// pre-aligned per-cell records of the pipelined cell kernel (cellinterp_tma.cu)
+struct CellTableDev {
+  uint32_t n_cubes, n_tets;
+  uint32_t mpp, n_pass;          // modes per pass, number of passes (record = n_pass tiles)
+  uint64_t cube_bytes, tet_bytes;  // record sizes
+  uint64_t total_bytes;
+};
+
 // mode bits of the locate kernel
 constexpr uint32_t MODE_NO_MOVE = 1u;    // skip moveinto/ir_moveinto (do_not_move_points)
 constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather than moveinto
@@ -211,5 +224,11 @@ uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, 
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
                                cudaStream_t stream);
 cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
+uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
+CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_tets, uint32_t mpp);
+cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vertices, const uint32_t* tet_vertices,
+                                    const CellTableDev& ct, unsigned char* table, int sm_count, cudaStream_t stream);
+cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
+                                   int sm_count, cudaStream_t stream);
 
 }  // namespace b200

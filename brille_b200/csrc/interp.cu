@@ -286,7 +286,7 @@ k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_ou
       const uint4* vp = reinterpret_cast<const uint4*>(in.vertex + 8 * q);
       uint4 a = vp[0], c = vp[1];
       vtx[0] = a.x; vtx[1] = a.y; vtx[2] = a.z; vtx[3] = a.w; vtx[4] = c.x; vtx[5] = c.y; vtx[6] = c.z; vtx[7] = c.w;
-      const double2* wp = reinterpret_cast<const double2*>(in.weight + 8 * q);
+      const double2* wp = reinterpret_cast<const double2*>(in.weight + REC_DOUBLES * q);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { double2 w2 = wp[j]; wgt[2 * j] = w2.x; wgt[2 * j + 1] = w2.y; }
     }

@@ -732,7 +732,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     if (!(mode & MODE_NO_LOCATE)) {
       EmitOut e;
       e.v = out.vertex + 8 * i;
-      e.w = out.weight + 8 * i;
+      e.w = out.weight + REC_DOUBLES * i;
       if (KIND == B200_GRID_TRELLIS) st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
       else if (KIND == B200_GRID_NEST) st |= nest_locate(gd.ne, x, e, cell, tet);
       else st |= mesh_locate(bz, gd.me, x, e, cell, tet);
@@ -749,6 +749,11 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       out.slots[i] = e.slots;
     }
     out.status[i] = st;
+    {  // the rest of the point's record (device_tables.cuh): q_ir, rotation indices, point index
+      double2* rec = reinterpret_cast<double2*>(out.weight + REC_DOUBLES * i);
+      rec[4] = make_double2(q[0], q[1]);
+      rec[5] = make_double2(q[2], __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
+    }
     if (out.key) {
       // bucket for the cell-batched interpolation: only "generic" points (every corner of the cell carries weight, i.e.
       // the pivot is the cell's first emitted corner) share a bucket with their cell

@@ -242,8 +242,10 @@ int b200_grid_enable_timing(b200_grid_t* grid, int on);
 double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
 /* tuning knobs: "interp_path" 0 auto | 1 general per-(Q,mode) kernel | 2 cell-batched kernel whenever the data layout
  * allows it; "chunk" points per CTA work item of the cell-batched kernel (default 256, reduced automatically
- * when many atoms/modes would not fit shared memory); "host_chunk" upper bound on the points per chunk of the
- * host-buffer pipeline (0 = sized from free device memory)                                                     */
+ * when many atoms/modes would not fit shared memory); "cell_kernel" 0 auto | 1 cell kernel that stages and phase-aligns
+ * the vertex rows on the fly | 2 persistent pipelined cell kernel fed from the per-cell record table (built once per
+ * fill; auto uses it whenever the table fits in a quarter of the free device memory); "host_chunk" upper bound on
+ * the points per chunk of the host-buffer pipeline (0 = sized from free device memory)                          */
 int b200_grid_set_option(b200_grid_t* grid, const char* name, double value);
 /* output row sizes in bytes for one Q (values, vectors) and algorithmic HBM bytes per Q of the path          */
 int b200_grid_row_bytes(const b200_grid_t* grid, size_t* vals_bytes, size_t* vecs_bytes);

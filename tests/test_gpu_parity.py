@@ -14,6 +14,17 @@ FIXTURES = ["nacl_prim_trellis.npz", "nacl_prim_trellis_sorted.npz", "fd3m_scala
             "p63mmc_nest.npz", "p63mmc_nest_sorted.npz", "p63mmc_mesh.npz"]
 
 
+# kernel selections every parity case runs under: the general per-(Q,mode) kernel, the cell-batched kernel that stages the
+# vertex rows on the fly, and the persistent pipelined cell kernel fed from the per-cell record table (the default)
+PATHS = [(1, 0), (2, 1), (2, 2)]
+PATH_IDS = ["general", "cell-onthefly", "cell-pipelined"]
+
+
+def apply_path(g, path):
+    g.set_option("interp_path", path[0])
+    g.set_option("cell_kernel", path[1])
+
+
 def rel_close(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
 
@@ -22,12 +33,12 @@ def probe_dict(pr):
     return {"tau": pr.tau, "q_ir": pr.q_ir, "ridx": pr.ridx, "invridx": pr.invridx, "n_vert": pr.n_vert, "vertex": pr.vertex, "weight": pr.weight}
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
 @pytest.mark.parametrize("name", FIXTURES)
 def test_golden_fixtures(name, path):
     s, d, _, rest = load_golden(name)
     g = brille_b200.B200Grid(None, structure=s, data=d)
-    g.set_option("interp_path", path)
+    apply_path(g, path)
     vals, vecs, pr = g.ir_interpolate_at(rest["Q"], probe=True)
     assert_decisions_equal(pr, ref_decisions(rest), "cuda", adaptive_ulps=4 if str(s["kind"]) in ("nest", "mesh") else 0)
     assert_values_close(vals, rest["ref_values"])
@@ -93,12 +104,12 @@ def test_errors_and_edge_cases():
     assert one[0].shape[0] == 1
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
 @pytest.mark.parametrize("builder,n", [("C1", 200000), ("C2", 100000), ("C3", 100000)])
 def test_against_oracle_and_reference(host, bridge, builder, n, path):
     wl = W.BUILDERS[builder](host)
     g = brille_b200.accelerate(wl.grid)
-    g.set_option("interp_path", path)
+    apply_path(g, path)
     Q = wl.make_q(n, 11)
     vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
     orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
@@ -115,7 +126,7 @@ def test_against_oracle_and_reference(host, bridge, builder, n, path):
     assert_values_close(vecs[:m], rw)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
 @pytest.mark.parametrize("cls,args", [("BZNestQdc", (5,)), ("BZMeshQdc", (3,))])
 def test_nest_and_mesh_against_oracle_and_reference(host, bridge, cls, args, path):
     """BZNestQdc (nest.hpp) and BZMeshQdc (mesh.hpp, triangulation_layers.hpp) on the C3 lattice."""
@@ -124,7 +135,7 @@ def test_nest_and_mesh_against_oracle_and_reference(host, bridge, cls, args, pat
     hg = getattr(host, cls)(bz, bz.ir_polyhedron.volume / 1000, *args)
     W._gamma_fill(hg, 12, 4, 17)
     g = brille_b200.accelerate(hg)
-    g.set_option("interp_path", path)
+    apply_path(g, path)
     Q = np.random.default_rng(5).uniform(-3, 3, (100000, 3))
     vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
     orc = Oracle(bridge.flatten(hg), bridge.flatten_data(hg))
@@ -193,12 +204,48 @@ def test_c4_p21c_nest_72_modes(host, bridge):
     assert_values_close(vecs[:4000], rw)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["general", "cell"])
+@pytest.mark.parametrize("which", ["C2", "C3", "C3-sorted", "C4"])
+def test_cell_kernels_agree_bitwise(host, which):
+    """The pipelined cell kernel reads per-cell records built once per fill; the on-the-fly kernel derives the same
+    numbers per work item with the same operations: identical bits, also across mode passes (C4) and permutations."""
+    if which == "C4":
+        wl = W.c4_p21c_nest(host, density=300)
+        n = 30000
+    elif which == "C2":
+        wl = W.c2_nacl(host, density=300)
+        n = 200000
+    else:
+        wl = W.c3_p63mmc(host, density=300, seed=5)
+        n = 200000
+        if which == "C3-sorted":
+            wl.grid.sort()
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(n, 31)
+    out = {}
+    for ck in (1, 2):
+        g.set_option("interp_path", 2)
+        g.set_option("cell_kernel", ck)
+        out[ck] = g.ir_interpolate_at(Q)
+    assert np.array_equal(out[1][0], out[2][0])
+    assert np.array_equal(out[1][1], out[2][1])
+    # a second fill replaces the cell records
+    if which == "C2":
+        vals, vecs = out[2]
+        g2 = brille_b200.accelerate(wl.grid)
+        g2.set_option("cell_kernel", 2)
+        a = g2.ir_interpolate_at(Q[:50000])
+        g2._sync_data()
+        b = g2.ir_interpolate_at(Q[:50000])
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[1], vecs[:50000])
+    g.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
 def test_sorted_permutations_against_reference(host, bridge, path):
     wl = W.c3_p63mmc(host, density=150, seed=9)
     wl.grid.sort()
     g = brille_b200.accelerate(wl.grid)
-    g.set_option("interp_path", path)
+    apply_path(g, path)
     Q = wl.make_q(20000, 12)
     vals, vecs = g.ir_interpolate_at(Q)
     rv, rw = wl.grid.ir_interpolate_at(Q, True, 8)
