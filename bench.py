@@ -292,7 +292,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * ne, "d2h_bytes_per_step": (bpq - 24) * ne,
                     "note": "b200_ir_interpolate_at with pinned host buffers; chunked H2D/kernels/D2H overlapped on two streams", "checksum": checksum},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_interp_cell (cell-batched interpolate+rotate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_interp_cell_tma (persistent cell-batched interpolate+rotate, TMA-staged cell records)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_q": bpq,
                          "kernel_ms": int_ms, "locate_kernel_ms": loc_ms, "bucket_sort_ms": sort_ms,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},

@@ -53,7 +53,7 @@ struct Workspace {
   double* x_ir = nullptr;
   int32_t* tau = nullptr;
   // counting sort by cell (cellinterp.cu)
-  uint32_t n_buckets = 0, chunk = 0;
+  uint32_t n_buckets = 0, chunk = 0, sub = 0;
   uint32_t* key = nullptr;
   uint32_t* rank = nullptr;
   uint32_t* cell_count = nullptr;
@@ -68,7 +68,7 @@ struct Workspace {
     tau = nullptr;
     key = rank = cell_count = nullptr;
     bk = BucketDev{};
-    n_buckets = chunk = 0;
+    n_buckets = chunk = sub = 0;
   }
   template <class T>
   cudaError_t get(T** p, size_t count) {
@@ -79,8 +79,8 @@ struct Workspace {
     return e;
   }
   uint32_t n_atoms_cap = 0;
-  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch, uint32_t n_atoms) {
-    if (n <= capacity && nb == n_buckets && ch == chunk && n_atoms == n_atoms_cap) return cudaSuccess;
+  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch, uint32_t n_atoms, uint32_t nsub) {
+    if (n <= capacity && nb == n_buckets && ch == chunk && n_atoms == n_atoms_cap && nsub == sub) return cudaSuccess;
     n_atoms_cap = n_atoms;
     if (n < capacity) n = capacity;
     release();
@@ -102,11 +102,15 @@ struct Workspace {
     WS(rank, uint32_t, 1)
 #undef WS
     if ((e = get<uint32_t>(&bk.order, n)) != cudaSuccess) return e;
-    if ((e = get<uint32_t>(&cell_count, nb)) != cudaSuccess) return e;
-    if ((e = get<uint32_t>(&bk.cell_offset, (size_t)nb + 1)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&cell_count, (size_t)nb * nsub)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.cell_offset, (size_t)nb * nsub + 1)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.cell_total, nb)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.cell_start, nb)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.n_items, 4)) != cudaSuccess) return e;
     if ((e = get<CellItem>(&bk.items, (n + ch - 1) / ch + nb)) != cudaSuccess) return e;
     bk.n_buckets = nb;
+    bk.sub = nsub;
+    sub = nsub;
     bk.chunk = ch;
     bk.cell_count = cell_count;
     n_buckets = nb;
@@ -687,7 +691,8 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
       chunk = g->chunk;
     }
   }
-  CU(ws.ensure(n, nb, chunk, 0u));
+  const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
+  CU(ws.ensure(n, nb, chunk, 0u, nsub));
   CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
@@ -696,7 +701,8 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     lo.key = ws.key;
     lo.rank = ws.rank;
     lo.cell_count = ws.cell_count;
-    CU(cudaMemsetAsync(ws.cell_count, 0, nb * sizeof(uint32_t), stream));
+    lo.sub = nsub;
+    CU(cudaMemsetAsync(ws.cell_count, 0, (size_t)nb * nsub * sizeof(uint32_t), stream));
   }
   if (g->timing) cudaEventRecord(g->ev[0], stream);
   CU(launch_locate(g->d_bz, g->gd, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
@@ -704,7 +710,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   if (g->timing) cudaEventRecord(g->ev[1], stream);
   if (interp && cell) {
     CU(launch_bucket_sort(ws.bk, ws.key, ws.rank, n, g->sm_count, stream));
-    g->launches += 2;
+    g->launches += 4;
     if (g->timing) cudaEventRecord(g->ev[2], stream);
     CellArgs a{};
     a.dd = g->dd;

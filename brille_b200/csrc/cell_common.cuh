@@ -8,20 +8,22 @@ namespace b200 {
 // Store 48 contiguous bytes at a 16-byte aligned address as one aligned 32-byte store (sm_100 STG.256) plus one 16-byte
 // store.  Consecutive lanes hold consecutive 48-byte pieces, so within each of the two instructions the lanes cover whole
 // 32-byte sectors: L2 receives one full-sector write per sector instead of three partial ones from three 16-byte stores.
+__device__ __forceinline__ void store32(double2* p, const double2 lo, const double2 hi) {  // p 32-byte aligned
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
+}
+__device__ __forceinline__ void store16(double2* p, const double2 v) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
 __device__ __forceinline__ void store48(double2* out, const double2 o0, const double2 o1, const double2 o2) {
   const bool even = (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
-  const double2 lo = even ? o0 : o1, hi = even ? o1 : o2, single = even ? o2 : o0;
-  double2* const p32 = even ? out : out + 1;
-  double2* const p16 = even ? out + 2 : out;
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p32), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
-  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p16), "d"(single.x), "d"(single.y) : "memory");
+  store32(even ? out : out + 1, even ? o0 : o1, even ? o1 : o2);
+  store16(even ? out + 2 : out, even ? o2 : o0);
 }
 
-// out = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
+// u = ph * (R * a) for one complex 3-vector, written with explicit fused/unfused operations so that every code path
 // that finishes a point produces the same bits (the result must not depend on which path a point happens to take)
-__device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
-                                                   const double2 ph, bool use_phase, double2* out) {
-  double2 u0, u1, u2;
+__device__ __forceinline__ void rotate_phase(const double* R, const double2 a0, const double2 a1, const double2 a2, const double2 ph,
+                                             bool use_phase, double2& u0, double2& u1, double2& u2) {
   u0.x = __fma_rn(R[2], a2.x, __fma_rn(R[1], a1.x, __dmul_rn(R[0], a0.x)));
   u0.y = __fma_rn(R[2], a2.y, __fma_rn(R[1], a1.y, __dmul_rn(R[0], a0.y)));
   u1.x = __fma_rn(R[5], a2.x, __fma_rn(R[4], a1.x, __dmul_rn(R[3], a0.x)));
@@ -33,6 +35,11 @@ __device__ __forceinline__ void rotate_phase_store(const double* R, const double
     u1 = make_double2(__fma_rn(-ph.y, u1.y, __dmul_rn(ph.x, u1.x)), __fma_rn(ph.y, u1.x, __dmul_rn(ph.x, u1.y)));
     u2 = make_double2(__fma_rn(-ph.y, u2.y, __dmul_rn(ph.x, u2.x)), __fma_rn(ph.y, u2.x, __dmul_rn(ph.x, u2.y)));
   }
+}
+__device__ __forceinline__ void rotate_phase_store(const double* R, const double2 a0, const double2 a1, const double2 a2,
+                                                   const double2 ph, bool use_phase, double2* out) {
+  double2 u0, u1, u2;
+  rotate_phase(R, a0, a1, a2, ph, use_phase, u0, u1, u2);
   store48(out, u0, u1, u2);
 }
 
@@ -175,21 +182,30 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
       const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
       const uint32_t rrs[TQ] = {rr4.x, rr4.y, rr4.z, rr4.w}, qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
       double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + (size_t)(b0 + b) * S;
-      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu)) {
-        // the four points share the rotation (the chunk is sorted by it): one matrix, one destination atom, no branches
+      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu) && ((wrow & 1) == 0)) {
+        // The four points share the rotation (the sort is by cell and operation): one matrix, one destination atom, no
+        // branches.  The 48 output bytes of a point go out as one 32-byte-aligned 32-byte store plus one 16-byte store
+        // (see store48); which of the three components forms the aligned pair depends only on the parity of the
+        // destination (rows are a multiple of 32 bytes here), so the ROWS of the matrix are loaded in store order
+        // (pair, pair, single) and no data has to be shuffled afterwards.
         const uint32_t ri = rr4.x & 0xffffu;
-        double R[9];
-        {
-          const double* Rs = RS + 9 * ri;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) R[e] = Rs[e];
-        }
         const uint32_t dest = F0[k * G + ri];
+        double2* const out0 = out_base + 3 * dest;
+        const bool even = (reinterpret_cast<uintptr_t>(out0) & 31u) == 0;  // row starts are 32-byte aligned
+        const double* Rs = RS + 9 * ri;
+        const double* r0 = Rs + (even ? 0 : 3);  // rows of the aligned pair ...
+        const double* r1 = Rs + (even ? 3 : 6);
+        const double* r2 = Rs + (even ? 6 : 0);  // ... and of the single component
+        const double R[9] = {r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]};
+        const uint32_t off32 = even ? 0u : 1u, off16 = even ? 2u : 0u;
         const double2* php = PH + (size_t)t0 * NAT + k;
 #pragma unroll
         for (int t = 0; t < TQ; ++t) {
-          rotate_phase_store(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true,
-                             out_base + (size_t)qis[t] * wrow + 3 * dest);
+          double2 u0, u1, u2;
+          rotate_phase(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true, u0, u1, u2);
+          double2* const o = out0 + (size_t)qis[t] * wrow;
+          store32(o + off32, u0, u1);
+          store16(o + off16, u2);
         }
         continue;
       }

@@ -21,6 +21,18 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------------------------
 // counting sort, part 2: single-CTA exclusive scan of the bucket populations + work-item table
 // ---------------------------------------------------------------------------------------------------------------
+// part 2a: population of every bucket (cell) = sum over its sub-buckets (one per point group operation); one thread per
+// bucket, spread over many CTAs so that the strided loads overlap
+__global__ void __launch_bounds__(256) k_bucket_totals(BucketDev b) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n_buckets) return;
+  const uint32_t* c = b.cell_count + (size_t)i * b.sub;
+  uint32_t t = 0;
+  for (uint32_t r = 0; r < b.sub; ++r) t += c[r];
+  b.cell_total[i] = t;
+}
+
+// part 2b: single-CTA exclusive scan of the bucket populations + work-item table
 __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
   __shared__ uint32_t s_pts[1024], s_its[1024];
   __shared__ uint32_t carry_pts, carry_its;
@@ -30,7 +42,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
   const uint32_t nb = b.n_buckets, last = nb - 1;
   for (uint32_t base = 0; base < nb; base += 1024) {
     const uint32_t i = base + tid;
-    const uint32_t c = i < nb ? b.cell_count[i] : 0u;
+    const uint32_t c = i < nb ? b.cell_total[i] : 0u;
     const uint32_t it = (i < last) ? (c + b.chunk - 1) / b.chunk : 0u;  // the last bucket produces no cell items
     s_pts[tid] = c;
     s_its[tid] = it;
@@ -44,7 +56,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
     }
     const uint32_t p0 = carry_pts + s_pts[tid] - c, i0 = carry_its + s_its[tid] - it;
     if (i < nb) {
-      b.cell_offset[i] = p0;
+      b.cell_start[i] = p0;
       for (uint32_t k = 0; k < it; ++k) {
         CellItem ci;
         ci.key = i;
@@ -64,9 +76,19 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    b.cell_offset[nb] = carry_pts;
-    b.n_items[0] = carry_its;
+  if (tid == 0) b.n_items[0] = carry_its;
+}
+
+// part 2c: first position of every sub-bucket
+__global__ void __launch_bounds__(256) k_bucket_suboffsets(BucketDev b) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n_buckets) return;
+  const uint32_t* c = b.cell_count + (size_t)i * b.sub;
+  uint32_t* o = b.cell_offset + (size_t)i * b.sub;
+  uint32_t run = b.cell_start[i];
+  for (uint32_t r = 0; r < b.sub; ++r) {
+    o[r] = run;
+    run += __ldg(c + r);
   }
 }
 
@@ -295,7 +317,10 @@ uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, 
 
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
                                cudaStream_t stream) {
+  const unsigned cell_blocks = (bk.n_buckets + 255) / 256;
+  k_bucket_totals<<<cell_blocks, 256, 0, stream>>>(bk);
   k_bucket_scan<<<1, 1024, 0, stream>>>(bk);
+  k_bucket_suboffsets<<<cell_blocks, 256, 0, stream>>>(bk);
   size_t want = (n + 255) / 256, cap = (size_t)sm_count * 16;
   k_bucket_scatter<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(key, rank, bk.cell_offset, bk.order, n);
   return cudaGetLastError();

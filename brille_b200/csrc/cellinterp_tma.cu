@@ -11,12 +11,15 @@
 //      the compute pass wants in shared memory, so staging a cell becomes one bulk asynchronous copy (TMA,
 //      cp.async.bulk + mbarrier) issued by one thread.
 //
-//   2. PERSISTENT CTAs.  Each CTA walks a contiguous range of the work items (cell, <= chunk points) produced by the
-//      counting sort.  While item n is computed, the record of the next cell is already in flight into the other
-//      half of a double buffer, the per-point records of item n+1 (weights, q_ir, rotation indices; gathered through
-//      the sort order) are in flight as cp.async copies and the sort order of item n+2 sits in a register.
-//      Consecutive items of the same cell reuse the staged record.  Rotation tables and the Gamma vectors are loaded
-//      once per CTA.
+//   2. PERSISTENT CTAs, ONE BARRIER PER ITEM.  Each CTA walks its share of the work items (cell, <= chunk points)
+//      produced by the counting sort, which orders the points by (cell, point group operation).  While item n is
+//      computed, the record of the next cell is already in flight into the other half of a double buffer (TMA); every
+//      thread then turns the raw 96-byte record of "its" point of item n+1 (fetched with a per-point bulk copy issued
+//      one item earlier, through the sort order loaded another item earlier) into the transposed weights, Gamma phases
+//      and indices of item n+1 in the other half of a second double buffer.  Nothing in that step needs another
+//      thread, so warps drift freely between the two steps and the trigonometry of one warp overlaps the stores of
+//      another; the single __syncthreads per item publishes the buffers.  Consecutive items of the same cell reuse
+//      the staged record.  Rotation tables and the Gamma vectors are loaded once per CTA.
 #include "cell_common.cuh"
 
 namespace b200 {
@@ -116,28 +119,28 @@ __global__ void __launch_bounds__(256) k_build_cell_table(DataDev dd, const uint
 // shared memory plan of the pipelined kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct TmaPlan {
-  size_t D0, D1, RW, RQ, RR, RV, W, PH, RS, F0, GV, QI, RI, MQ, BAR, total;
+  uint32_t D0, D1, RW, W, PH, RS, F0, GV, QI, RI, BAR, per_set, total;
 };
 __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk,
                                                  uint32_t n_at, uint32_t G, bool gamma) {
   TmaPlan p;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+  uint32_t o = 0;
+  auto take = [&](size_t bytes) { uint32_t at = o; o += (uint32_t)((bytes + 15) / 16 * 16); return at; };
   const size_t tile = cell_tile_bytes(nvmax, mpp, S, no0v);
   p.D0 = take(tile);
   p.D1 = take(tile);
-  p.RW = take((size_t)chunk * REC_BYTES);  // raw per-point records of the next item, in flight as one bulk copy
-  p.RQ = take(0);
-  p.RR = take(0);
-  p.RV = take(0);
+  p.RW = take((size_t)chunk * REC_BYTES);  // raw per-point records of the next item (per-point bulk copies)
+  // two sets of per-item tables (W, PH, QI, RI): the set of item n is read while the set of item n+1 is written
+  const uint32_t set0 = o;
   p.W = take((size_t)nvmax * chunk * 8);
   p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
+  p.QI = take((size_t)chunk * 4);
+  p.RI = take((size_t)chunk * 4);
+  p.per_set = o - set0;
+  o += p.per_set;
   p.RS = take((size_t)G * 9 * 8);
   p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
   p.GV = take(gamma ? (size_t)n_at * G * 24 : 0);
-  p.QI = take((size_t)chunk * 4);
-  p.RI = take((size_t)chunk * 4);
-  p.MQ = take(0);
   p.BAR = take(32);
   p.total = o;
   return p;
@@ -149,7 +152,8 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
 constexpr uint32_t NO_ITEM = 0xffffffffu;
 constexpr uint32_t ITEM_BLOCK = 4;
 
-__global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTableDev ct, const unsigned char* __restrict__ table) {
+__global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
+                                                            const unsigned char* __restrict__ table, const __grid_constant__ TmaPlan pl) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const InterpDev& vals = a.dd.values;
@@ -158,25 +162,18 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTabl
   const int kind = a.ir ? vecs.rot_kind : -1;
   const bool gamma = kind >= 3;
   const uint32_t mpp = ct.mpp, n_pass = ct.n_pass, CH = a.bk.chunk;
-  const TmaPlan pl = plan_smem_tma(a.n_cubes ? 8u : 4u, mpp, S, no0v, CH, NAT, G, gamma);
   unsigned char* const D0p = smem + pl.D0;
   unsigned char* const D1p = smem + pl.D1;
-  double* RW = reinterpret_cast<double*>(smem + pl.RW);
-  double* W = reinterpret_cast<double*>(smem + pl.W);
-  double2* PH = reinterpret_cast<double2*>(smem + pl.PH);
-  double* RS = reinterpret_cast<double*>(smem + pl.RS);
-  uint32_t* F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
-  double* GV = reinterpret_cast<double*>(smem + pl.GV);
-  uint32_t* QI = reinterpret_cast<uint32_t*>(smem + pl.QI);
-  uint32_t* RI = reinterpret_cast<uint32_t*>(smem + pl.RI);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.BAR);
-  __shared__ uint32_t s_hist[64];
+  double* const RW = reinterpret_cast<double*>(smem + pl.RW);
+  double* const RS = reinterpret_cast<double*>(smem + pl.RS);
+  uint32_t* const F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
+  double* const GV = reinterpret_cast<double*>(smem + pl.GV);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + pl.BAR);
 
   // ---- this CTA's work items: blocks of ITEM_BLOCK consecutive items (same-cell reuse), dealt round-robin to the CTAs
   // (the item list is ordered cubes first, then tetrahedra: a cyclic deal gives every CTA the same mix of both) ----------
   const uint32_t n_items = a.bk.n_items[0];
   if (blockIdx.x * ITEM_BLOCK >= n_items) return;
-  const uint32_t it1 = n_items;
   // local item l -> global item ((l / ITEM_BLOCK) * gridDim.x + blockIdx.x) * ITEM_BLOCK + l % ITEM_BLOCK (monotonic in l)
 #define GLOBAL_ITEM(l_) ((((l_) / ITEM_BLOCK) * gridDim.x + blockIdx.x) * ITEM_BLOCK + ((l_) % ITEM_BLOCK))
 
@@ -202,22 +199,23 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTabl
         GV[3 * i + 2] = gv[2];
       }
     }
-    if (tid < 64) s_hist[tid] = 0;
     if (tid == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
       mbar_init(&bar[2], 1);
+      mbar_init(&bar[3], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
   __syncthreads();
 
-  // an item is (key, start, len); three scalars each so that the descriptors stay in registers
+  uint32_t parity = 0u;  // bit b = phase parity of bar[b]
+  // an item is (key, start, len); scalars, so that the descriptors stay in registers
 #define LOAD_ITEM(it_, key_, start_, len_)                                \
   do {                                                                    \
     key_ = NO_ITEM; start_ = 0; len_ = 0;                                 \
     const uint32_t gi_ = GLOBAL_ITEM(it_);                                \
-    if (gi_ < it1) {                                                      \
+    if (gi_ < n_items) {                                                  \
       const CellItem* ci_ = a.bk.items + gi_;                             \
       key_ = ci_->key; start_ = ci_->start; len_ = ci_->len;              \
     }                                                                     \
@@ -230,100 +228,95 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTabl
     bulk_g2s(b ? D1p : D0p, src, bytes, bar + b);
   };
   // raw records of an item: every thread fetches the 96-byte record of its own point with one bulk copy; all of them
-  // complete on bar[2], on which thread 0 announces the total
-  auto issue_raw = [&](uint32_t q, bool has, uint32_t len) {
-    if (tid == 0) mbar_expect_tx(bar + 2, len * REC_BYTES);
-    if (has) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_BYTES, bar + 2);
+  // complete on bar[2 + (item & 1)], on which thread 0 announces the total.  Two barriers, because threads issue the copies
+  // of item n+2 right after they have seen item n+1 complete, without a CTA barrier in between: with a single mbarrier a
+  // copy of item n+2 could be counted in the phase of item n+1, and a late thread could miss a whole phase.
+  auto issue_raw = [&](uint32_t q, uint32_t len, uint32_t item) {
+    uint64_t* const rb = bar + 2 + (item & 1u);
+    if (tid == 0 && len) mbar_expect_tx(rb, len * REC_BYTES);
+    if ((uint32_t)tid < len) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_BYTES, rb);
+  };
+  auto wait_raw = [&](uint32_t item) {  // every thread, exactly once per item
+    const uint32_t b = 2u + (item & 1u);
+    mbar_wait(bar + b, (parity >> b) & 1u);
+    parity ^= 1u << b;
+  };
+  // this thread's point of an item: raw record -> transposed weights, Gamma phases, indices in table set `set`.
+  // The sort already ordered the points of a cell by operation: position in the item == position in the tables.
+  auto make_tables = [&](uint32_t len, int nv, int set) {
+    unsigned char* const base = smem + (set ? pl.per_set : 0);
+    double* const W = reinterpret_cast<double*>(base + pl.W);
+    double2* const PH = reinterpret_cast<double2*>(base + pl.PH);
+    uint32_t* const QI = reinterpret_cast<uint32_t*>(base + pl.QI);
+    uint32_t* const RI = reinterpret_cast<uint32_t*>(base + pl.RI);
+    if ((uint32_t)tid < len) {
+      const double* rec = RW + REC_DOUBLES * (size_t)tid;  // weight[8] | q_ir[3] | rot, index
+      const uint2 ri2 = *reinterpret_cast<const uint2*>(rec + 11);
+      const uint32_t my_r = ri2.x & 0xffffu, my_inv = ri2.x >> 16;
+      // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
+      const uint32_t mi = (kind == 0 || kind == 1) ? my_r : my_inv;
+      QI[tid] = ri2.y;
+      RI[tid] = mi | (my_r << 16);
+      const double2* rw = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (2 * j < nv) {
+          const double2 w2 = rw[j];
+          W[(size_t)(2 * j) * CH + tid] = w2.x;
+          W[(size_t)(2 * j + 1) * CH + tid] = w2.y;
+        }
+      }
+    } else if ((uint32_t)tid < ((len + 3u) & ~3u)) {  // padding points of the last register tile carry zero weight
+      for (int i = 0; i < nv; ++i) W[(size_t)i * CH + tid] = 0.0;
+      QI[tid] = 0;
+      RI[tid] = 0;
+    }
+    if (gamma) {
+      // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58.  The (point, atom)
+      // pairs are dealt to ALL threads (every record of the item is visible once its mbarrier phase completed), so that
+      // short items do not leave most warps idle here.
+      const uint32_t nat_magic = 0xffffffffu / NAT + 1u;  // floor(u / NAT) == umulhi(u, magic) for u * NAT < 2^32
+      for (uint32_t u = tid; u < len * NAT; u += nthr) {
+        const uint32_t t = NAT == 1u ? u : __umulhi(u, nat_magic), k = u - t * NAT;
+        const double* rec = RW + REC_DOUBLES * (size_t)t;
+        const uint32_t rot = *reinterpret_cast<const uint32_t*>(rec + 11);
+        const uint32_t mi = (kind == 0 || kind == 1) ? (rot & 0xffffu) : (rot >> 16);
+        const double* gv = GV + 3 * ((size_t)k * G + mi);
+        const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(rec[8], gv[0])), __dmul_rn(rec[9], gv[1])), __dmul_rn(rec[10], gv[2]));
+        double sn, cs;
+        sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
+        PH[u] = make_double2(cs, sn);
+      }
+    }
   };
 
-  // descriptors of items n, n+1, n+2 (n+3 is loaded while n is processed, so that no load waits on the one before it)
+  // Pipeline (item n is being computed):
+  //   raw records of item n+1: issued at the top of iteration n (the raw buffer is free: its readers finished before the
+  //                            barrier that ended iteration n-1), consumed at the bottom of iteration n
+  //   point indices (sort order) of item n+2: loaded into a register at the bottom of iteration n
+  //   descriptor of item n+3: loaded at the end of iteration n
+  // so that no global load waits on the one before it.
   uint32_t cur_key, cur_start, cur_len, nxt_key, nxt_start, nxt_len, nn_key, nn_start, nn_len;
   LOAD_ITEM(0u, cur_key, cur_start, cur_len);
   LOAD_ITEM(1u, nxt_key, nxt_start, nxt_len);
   LOAD_ITEM(2u, nn_key, nn_start, nn_len);
-  int buf = 0;
-  uint32_t parity = 0u;  // bit b = phase parity of bar[b]
+  int buf = 0, set = 0;
   bool fresh = true;
-  issue_raw((uint32_t)tid < cur_len ? a.bk.order[cur_start + tid] : 0u, (uint32_t)tid < cur_len, cur_len);
-  uint32_t q_nxt = (uint32_t)tid < nxt_len ? a.bk.order[nxt_start + tid] : 0u;  // sort order, two items ahead of its use
   if (tid == 0) issue_tile(cur_key, 0, 0);
+  // prologue: tables of the first item
+  issue_raw((uint32_t)tid < cur_len ? a.bk.order[cur_start + tid] : 0u, cur_len, 0u);
+  uint32_t q_nx = (uint32_t)tid < nxt_len ? a.bk.order[nxt_start + tid] : 0u;
+  wait_raw(0u);
+  make_tables(cur_len, cur_key < a.n_cubes ? 8 : 4, 0);
+  __syncthreads();
+  (void)nxt_start;
 
-  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
-  (void)vrow; (void)wrow;
   for (uint32_t it = 0; cur_key != NO_ITEM; ++it) {
-    const bool is_cube = cur_key < a.n_cubes;
-    const int NV = is_cube ? 8 : 4;
-    uint32_t n3_key = NO_ITEM, n3_start = 0, n3_len = 0, q_nn = 0;
+    const int NV = cur_key < a.n_cubes ? 8 : 4;
+    unsigned char* const tbase = smem + (set ? pl.per_set : 0);
+    if (nxt_key != NO_ITEM) issue_raw(q_nx, nxt_len, it + 1);
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const uint32_t b0 = pass * mpp, mb = min(mpp, M - b0);
-      if (pass == 0) {
-        // ---- per-point records of this item: raw (bulk copies on bar[2]) -> sorted by rotation matrix -----------------------
-        mbar_wait(bar + 2, (parity >> 2) & 1u);
-        parity ^= 4u;
-        const bool has = (uint32_t)tid < cur_len;
-        const double* rec = RW + REC_DOUBLES * (size_t)tid;  // this thread's raw record: weight[8] | q_ir[3] | rot, index
-        uint32_t my_q = 0, mi = 0, my_rank = 0;
-        int my_r = 0;
-        if (has) {
-          const uint2 ri2 = *reinterpret_cast<const uint2*>(rec + 11);
-          my_q = ri2.y;
-          const uint32_t rot = ri2.x;
-          my_r = (int)(rot & 0xffffu);
-          const int my_inv = (int)(rot >> 16);
-          // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
-          mi = (uint32_t)((kind == 0 || kind == 1) ? my_r : my_inv);
-          my_rank = atomicAdd(&s_hist[mi], 1u);
-        }
-        __syncthreads();
-        if (tid < 32) {  // exclusive scan of <= 64 bins by one warp
-          const uint32_t c0 = s_hist[tid], c1 = s_hist[tid + 32];
-          uint32_t x0 = c0, x1 = c1;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
-            if (tid >= o) { x0 += y0; x1 += y1; }
-          }
-          const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
-          s_hist[tid] = x0 - c0;
-          s_hist[tid + 32] = tot0 + x1 - c1;
-        }
-        __syncthreads();
-        if (has) {
-          const uint32_t t = s_hist[mi] + my_rank;
-          QI[t] = my_q;
-          RI[t] = mi | ((uint32_t)my_r << 16);
-          const double2* rw = reinterpret_cast<const double2*>(rec);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (2 * j < NV) {
-              const double2 w2 = rw[j];
-              W[(size_t)(2 * j) * CH + t] = w2.x;
-              W[(size_t)(2 * j + 1) * CH + t] = w2.y;
-            }
-          }
-          if (gamma) {
-            // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58
-            const double q0 = rec[8], q1 = rec[9], q2 = rec[10];
-            for (uint32_t k = 0; k < NAT; ++k) {
-              const double* gv = GV + 3 * ((size_t)k * G + mi);
-              const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(q0, gv[0])), __dmul_rn(q1, gv[1])), __dmul_rn(q2, gv[2]));
-              double sn, cs;
-              sincos(6.283185307179586476925286766559 * dot, &sn, &cs);
-              PH[(size_t)t * NAT + k] = make_double2(cs, sn);
-            }
-          }
-        } else if ((uint32_t)tid < ((cur_len + 3u) & ~3u)) {  // padding points of the last register tile carry zero weight
-          for (int i = 0; i < NV; ++i) W[(size_t)i * CH + tid] = 0.0;
-          QI[tid] = 0;
-          RI[tid] = 0;
-        }
-        __syncthreads();  // sorted records visible; raw records and the histogram are free again
-        if (tid < 64) s_hist[tid] = 0;
-        // ---- keep the pipeline full: raw records of item n+1, descriptor of item n+3 -----------------------------------
-        if (nxt_key != NO_ITEM) issue_raw(q_nxt, (uint32_t)tid < nxt_len, nxt_len);
-        q_nn = (uint32_t)tid < nn_len ? a.bk.order[nn_start + tid] : 0u;
-        LOAD_ITEM(it + 3, n3_key, n3_start, n3_len);
-      }
       // ---- prefetch the next tile into the other buffer (its last readers finished before the previous barrier) ------
       uint32_t nkey = NO_ITEM, npass = 0;
       if (pass + 1 < n_pass) { nkey = cur_key; npass = pass + 1; }
@@ -340,18 +333,29 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTabl
       unsigned char* const Dcur = buf ? D1p : D0p;
       cp.D = reinterpret_cast<const double2*>(Dcur);
       cp.V = reinterpret_cast<const double*>(Dcur + (size_t)NV * mpp * S * 16);
-      cp.W = W; cp.PH = PH; cp.RS = RS; cp.F0 = F0; cp.QI = QI; cp.RI = RI;
+      cp.W = reinterpret_cast<const double*>(tbase + pl.W);
+      cp.PH = reinterpret_cast<const double2*>(tbase + pl.PH);
+      cp.QI = reinterpret_cast<const uint32_t*>(tbase + pl.QI);
+      cp.RI = reinterpret_cast<const uint32_t*>(tbase + pl.RI);
+      cp.RS = RS; cp.F0 = F0;
       cp.CH = CH; cp.mpp = mpp; cp.mb = mb; cp.b0 = b0; cp.len = cur_len; cp.M = M; cp.S = S; cp.NAT = NAT; cp.no0v = no0v; cp.G = G;
       cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
       cell_compute_pass(cp, tid, nthr);
-      __syncthreads();  // every reader of this tile and of the sorted records is done
+      if (pass + 1 == n_pass) {
+        if (nxt_key != NO_ITEM) {  // tables of item n+1 into the other set
+          wait_raw(it + 1);
+          make_tables(nxt_len, nxt_key < a.n_cubes ? 8 : 4, set ^ 1);
+        }
+        q_nx = (uint32_t)tid < nn_len ? a.bk.order[nn_start + tid] : 0u;
+      }
+      __syncthreads();  // every reader of this tile, this table set and the raw records is done; the other set is complete
       if (load_next) buf ^= 1;
       fresh = load_next;
     }
-    cur_key = nxt_key; cur_start = nxt_start; cur_len = nxt_len;
-    nxt_key = nn_key; nxt_start = nn_start; nxt_len = nn_len;
-    nn_key = n3_key; nn_start = n3_start; nn_len = n3_len;
-    q_nxt = q_nn;
+    cur_key = nxt_key; cur_len = nxt_len;
+    nxt_key = nn_key; nxt_len = nn_len;
+    LOAD_ITEM(it + 3, nn_key, nn_start, nn_len);
+    set ^= 1;
   }
 }
 
@@ -362,17 +366,18 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(CellArgs a, CellTabl
 uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out) {
   const bool gamma = dd.vectors.rot_kind >= 3;
   const uint32_t M = dd.vectors.branches;
-  uint32_t best_chunk = 0, best_mpp = 0;
-  for (uint32_t chunk = preferred; chunk >= 32; chunk /= 2) {
-    uint32_t mpp = 0;
+  auto modes_that_fit = [&](uint32_t chunk) {
     for (uint32_t m = M; m >= 1; --m)
-      if (plan_smem_tma(has_cubes ? 8u : 4u, m, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) {
-        mpp = m;
-        break;
-      }
-    if (mpp == 0) continue;
-    if (best_chunk == 0) { best_chunk = chunk; best_mpp = mpp; }
-    if (8 * mpp >= M) { best_chunk = chunk; best_mpp = mpp; break; }  // at most 8 passes: stop shrinking the chunk
+      if (plan_smem_tma(has_cubes ? 8u : 4u, m, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) return m;
+    return 0u;
+  };
+  uint32_t best_chunk = 0, best_mpp = 0;
+  // all modes in one pass with a decent number of points per item, if that fits ...
+  for (uint32_t chunk = preferred; chunk >= 64 && !best_chunk; chunk /= 2)
+    if (modes_that_fit(chunk) == M) { best_chunk = chunk; best_mpp = M; }
+  // ... otherwise shrink the chunk until at most 8 passes are needed (else: fewest passes)
+  for (uint32_t chunk = preferred; chunk >= 32 && !(best_mpp && 8 * best_mpp >= M); chunk /= 2) {
+    const uint32_t mpp = modes_that_fit(chunk);
     if (mpp > best_mpp) { best_chunk = chunk; best_mpp = mpp; }
   }
   if (best_mpp) {  // equalise the passes (same count, smaller padding)
@@ -408,7 +413,8 @@ cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct,
                                    int sm_count, cudaStream_t stream) {
   const DataDev& dd = args.dd;
   const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
-  const size_t smem = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
+  const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma);
+  const size_t smem = plan.total;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -428,7 +434,7 @@ cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct,
   const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
   if (grid > max_blocks) grid = max_blocks;
   if (grid == 0) return cudaSuccess;
-  k_interp_cell_tma<<<(unsigned)grid, 256, smem, stream>>>(args, ct, table);
+  k_interp_cell_tma<<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
   return cudaGetLastError();
 }
 

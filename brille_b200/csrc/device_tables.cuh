@@ -121,10 +121,13 @@ struct LocateOut {
   uint64_t* slots;   // (n) 8 packed corner slots (emission order), byte j = slot of emitted vertex j
   uint32_t* status;  // (n)
   // bucketing for the cell-batched interpolation kernel (all optional: NULL => not bucketed)
-  uint32_t* key;         // (n) bucket of the point: cube c -> c, tetrahedron t -> n_cubes + t, everything that is not a
-                         //     full generic cell (some weight ~ 0, failed points) -> n_cubes + n_tets
-  uint32_t* rank;        // (n) arrival order of the point inside its bucket
-  uint32_t* cell_count;  // (n_cubes + n_tets + 1) bucket populations, zeroed before the launch
+  uint32_t* key;         // (n) sub-bucket of the point: bucket * sub + invridx, where the bucket is c for cube c,
+                         //     n_cubes + t for tetrahedron t and n_cubes + n_tets for everything that is not a full
+                         //     generic cell (some weight ~ 0, failed points)
+  uint32_t* rank;        // (n) arrival order of the point inside its sub-bucket
+  uint32_t* cell_count;  // ((n_cubes + n_tets + 1) * sub) sub-bucket populations, zeroed before the launch
+  uint32_t sub;          // sub-buckets per bucket = number of point group operations: the sort is by (cell, operation), so
+                         //     that consecutive points of a cell share the rotation matrix
 };
 
 struct InterpDev {
@@ -175,9 +178,12 @@ struct CellItem {
 
 struct BucketDev {
   uint32_t n_buckets;          // n_cubes + n_tets + 1
+  uint32_t sub;                // sub-buckets per bucket (point group operations)
   uint32_t chunk;              // points per CTA item
-  const uint32_t* cell_count;  // (n_buckets)
-  uint32_t* cell_offset;       // (n_buckets + 1) exclusive scan of cell_count
+  const uint32_t* cell_count;  // (n_buckets * sub)
+  uint32_t* cell_offset;       // (n_buckets * sub) exclusive scan of cell_count: first position of every sub-bucket
+  uint32_t* cell_total;        // (n_buckets) bucket populations
+  uint32_t* cell_start;        // (n_buckets) first position of every bucket
   CellItem* items;             // (max_items)
   uint32_t* n_items;           // [0] number of items, [1] start of the last (general) bucket, [2] its population
   uint32_t* order;             // (n) point indices in bucket order

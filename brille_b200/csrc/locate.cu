@@ -762,6 +762,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
         if (tet >= 0 && n_emit == 4) key = gd.cells.n_cubes + (uint32_t)tet;
         else if (tet < 0 && n_emit == 8) key = gd.cells.node_index[cell];
       }
+      key = key * out.sub + (uint32_t)invridx;
       out.key[i] = key;
       out.rank[i] = atomicAdd(out.cell_count + key, 1u);
     }

@@ -19,7 +19,9 @@ __global__ void k_store(char* out, const uint32_t* rows, size_t n) {
   const int lane = threadIdx.x & 31;
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * blockDim.x) >> 5;
   for (size_t r = warp; r < n; r += nwarp) {
-    char* row = out + (size_t)rows[r] * ROW;
+    // rows == nullptr: pseudo-random row from arithmetic (no load in front of the stores)
+    const size_t ri = rows ? (size_t)rows[r] : (size_t)((r * 7919003ull) % n);
+    char* row = out + ri * ROW;
     const double a = (double)r, b = (double)lane;
     if (MODE == 0) {
       for (int o = lane * 16; o < ROW; o += 512) st16(row + o, a, b);
@@ -70,17 +72,21 @@ static void run_tma(const char* name, char* out, const uint32_t* rows, size_t n,
   printf("%-44s %7.3f ms  %7.1f GB/s (%d CTAs/SM)\n", name, ms, (double)n * ROW / ms * 1e-6, ctas_per_sm);
 }
 
+// ctas_per_sm < 8: occupancy is limited with dynamic shared memory, like the interpolation kernel (2 CTAs of 256 threads)
 template <int MODE>
-static void run(const char* name, char* out, const uint32_t* rows, size_t n) {
+static void run(const char* name, char* out, const uint32_t* rows, size_t n, int ctas_per_sm = 8) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int it = 0; it < 2; ++it) k_store<MODE><<<148 * 16, 256>>>(out, rows, n);
+  const size_t smem = ctas_per_sm >= 8 ? 0 : (size_t)(220 * 1024 / ctas_per_sm - 2048);
+  cudaFuncSetAttribute(k_store<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = 148 * ctas_per_sm;
+  for (int it = 0; it < 2; ++it) k_store<MODE><<<grid, 256, smem>>>(out, rows, n);
   cudaEventRecord(e0);
-  for (int it = 0; it < 5; ++it) k_store<MODE><<<148 * 16, 256>>>(out, rows, n);
+  for (int it = 0; it < 5; ++it) k_store<MODE><<<grid, 256, smem>>>(out, rows, n);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-  printf("%-44s %7.3f ms  %7.1f GB/s\n", name, ms, (double)n * ROW / ms * 1e-6);
+  printf("%-44s %7.3f ms  %7.1f GB/s (%d CTAs/SM)\n", name, ms, (double)n * ROW / ms * 1e-6, ctas_per_sm);
 }
 
 int main() {
@@ -97,6 +103,15 @@ int main() {
     run<1>("contiguous 1 KB per instruction (STG.256)", out, rows, n);
     run<2>("48-byte pieces, 3 x 16 B", out, rows, n);
     run<3>("48-byte pieces, 32 B + 16 B", out, rows, n);
+    run<3>("48-byte pieces, 32 B + 16 B", out, rows, n, 4);
+    run<3>("48-byte pieces, 32 B + 16 B", out, rows, n, 2);
+    run<3>("48-byte pieces, 32 B + 16 B", out, rows, n, 1);
+    run<0>("contiguous 512 B per instruction", out, rows, n, 2);
+    if (pass) {
+      printf("-- arithmetic random rows (no index load)\n");
+      for (int c : {8, 4, 2, 1}) run<3>("48-byte pieces, 32 B + 16 B", out, nullptr, n, c);
+      for (int c : {8, 4, 2, 1}) run<0>("contiguous 512 B per instruction", out, nullptr, n, c);
+    }
     run_tma("TMA bulk store 2304 B per row", out, rows, n, 1);
     run_tma("TMA bulk store 2304 B per row", out, rows, n, 2);
     run_tma("TMA bulk store 2304 B per row", out, rows, n, 4);
