@@ -103,6 +103,7 @@ struct CellPass {
   const double* rot_det;
   double* vals_out;
   double* vecs_out;
+  uint32_t* task_ctr;  // shared counter (zero at the start of the pass) for the dynamic deal of tasks, or nullptr
 };
 
 __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, int nthr) {
@@ -154,9 +155,26 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
     // task -> (tile, r = b * NAT + k) is advanced incrementally: no integer division in the loop
     const uint32_t step_tile = (uint32_t)nthr / per_q, step_r = (uint32_t)nthr - step_tile * per_q;
     const uint32_t nat_magic = 0xffffffffu / NAT + 1u;  // floor(r / NAT) == umulhi(r, magic) for r * NAT < 2^32
+    const uint32_t pq_magic = 0xffffffffu / per_q + 1u;
+    const uint32_t n_task = ntile * per_q;
     uint32_t tile = (uint32_t)tid / per_q, r = (uint32_t)tid - tile * per_q;
-    for (uint32_t task = tid; task < ntile * per_q; task += nthr, tile += step_tile, r += step_r) {
-      if (r >= per_q) { r -= per_q; ++tile; }
+    // Static deal (task = tid, tid + nthr, ...) or, when the caller provides a shared counter, warps draw rounds of 32
+    // consecutive tasks from it: a warp that was held up draws fewer rounds, so all warps reach the barrier that ends the
+    // pass within one round of each other.
+    for (uint32_t task = tid;; task += nthr, tile += step_tile, r += step_r) {
+      if (c.task_ctr) {
+        uint32_t base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(c.task_ctr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_task) break;
+        task = base + (uint32_t)(tid & 31);
+        if (task >= n_task) continue;  // (only the last round of a pass is partial)
+        tile = per_q == 1u ? task : __umulhi(task, pq_magic);
+        r = task - tile * per_q;
+      } else {
+        if (task >= n_task) break;
+        if (r >= per_q) { r -= per_q; ++tile; }
+      }
       const uint32_t b = NAT == 1u ? r : __umulhi(r, nat_magic), k = r - b * NAT;
       const uint32_t t0 = tile * TQ;
       const double2* src = D + (size_t)b * S + 3 * k;

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
   uint32_t* const F0 = reinterpret_cast<uint32_t*>(smem + pl.F0);
   double* const GV = reinterpret_cast<double*>(smem + pl.GV);
   uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + pl.BAR);
+  __shared__ uint32_t s_task_ctr[2];
 
   // ---- this CTA's work items: blocks of ITEM_BLOCK consecutive items (same-cell reuse), dealt round-robin to the CTAs
   // (the item list is ordered cubes first, then tetrahedra: a cyclic deal gives every CTA the same mix of both) ----------
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
       }
     }
     if (tid == 0) {
+      s_task_ctr[0] = s_task_ctr[1] = 0u;
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
       mbar_init(&bar[2], 1);
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
   LOAD_ITEM(2u, nn_key, nn_start, nn_len);
   int buf = 0, set = 0;
   bool fresh = true;
+  uint32_t n_done = 0;  // passes done by this CTA (selects the task counter)
   if (tid == 0) issue_tile(cur_key, 0, 0);
   // prologue: tables of the first item
   issue_raw((uint32_t)tid < cur_len ? a.bk.order[cur_start + tid] : 0u, cur_len, 0u);
@@ -340,6 +343,8 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
       cp.RS = RS; cp.F0 = F0;
       cp.CH = CH; cp.mpp = mpp; cp.mb = mb; cp.b0 = b0; cp.len = cur_len; cp.M = M; cp.S = S; cp.NAT = NAT; cp.no0v = no0v; cp.G = G;
       cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
+      cp.task_ctr = s_task_ctr + (n_done & 1u);
+      if (tid == 0) s_task_ctr[(n_done + 1u) & 1u] = 0u;  // the counter of the next pass: idle since the previous barrier
       cell_compute_pass(cp, tid, nthr);
       if (pass + 1 == n_pass) {
         if (nxt_key != NO_ITEM) {  // tables of item n+1 into the other set
@@ -351,6 +356,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
       __syncthreads();  // every reader of this tile, this table set and the raw records is done; the other set is complete
       if (load_next) buf ^= 1;
       fresh = load_next;
+      ++n_done;
     }
     cur_key = nxt_key; cur_len = nxt_len;
     nxt_key = nn_key; nxt_len = nn_len;
