@@ -56,6 +56,8 @@ struct TrellisSpy : BrillouinZoneTrellis3<T, R, S> {
 template <class T>
 struct InterpSpy : Interpolator<T> {
   static LengthUnit lenunit(const Interpolator<T>& i) { return i.*(&InterpSpy::lenunit_); }
+  static const std::array<double, 3>& costmult(const Interpolator<T>& i) { return i.*(&InterpSpy::_costmult); }
+  static const std::array<ind_t, 3>& funtype(const Interpolator<T>& i) { return i.*(&InterpSpy::_funtype); }
 };
 template <class T, class R>
 struct DualSpy : DualInterpolator<T, R> {
@@ -519,6 +521,57 @@ static py::dict flatten_mesh_data(const BrillouinZoneMesh3<T, R, double>& g) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// sort()   (interpolatordual.hpp:398-434): the connected vertex pairs and the cost configuration
+// ---------------------------------------------------------------------------------------------
+// The pairs (i < j) of the permutation table in key order -- exactly the list DualInterpolator::sort() walks -- and what
+// Interpolator::add_cost needs to know (interpolator_cost.tpp:18-58, interpolator.hpp:246-305).
+template <class T, class R>
+static py::dict sort_plan(const DualInterpolator<T, R>& data) {
+  py::dict d;
+  const PermutationTable& table = DualSpy<T, R>::table(data);
+  const size_t no = PermSpy::nidx(table);
+  std::vector<unsigned> pairs;
+  for (const auto& kv : PermSpy::map(table)) {  // std::map: ascending keys, like std::set<size_t> keys()
+    const size_t key = kv.first;
+    const size_t i = key / no;
+    if (i * (no + 1) < key) {
+      pairs.push_back(static_cast<unsigned>(i));
+      pairs.push_back(static_cast<unsigned>(key - i * no));
+    }
+  }
+  d["pairs"] = np2(pairs, 2);
+  d["n_vertices"] = static_cast<unsigned>(no);
+  const auto& vc = InterpSpy<T>::costmult(data.values());
+  const auto& wc = InterpSpy<R>::costmult(data.vectors());
+  d["values_costmult"] = np1(std::vector<double>{vc[0], vc[1], vc[2]});
+  d["vectors_costmult"] = np1(std::vector<double>{wc[0], wc[1], wc[2]});
+  d["values_vector_cost"] = static_cast<int>(InterpSpy<T>::funtype(data.values())[0]);
+  d["vectors_vector_cost"] = static_cast<int>(InterpSpy<R>::funtype(data.vectors())[0]);
+  return d;
+}
+// the permutations the host table holds for the ordered pairs (i,j) and (j,i) (identity when unset): (n_pairs, 2, modes)
+template <class T, class R>
+static py::array_t<unsigned> pair_permutations(const DualInterpolator<T, R>& data, py::array_t<unsigned, py::array::c_style | py::array::forcecast> pairs) {
+  const PermutationTable& table = DualSpy<T, R>::table(data);
+  PermLookup look(table);
+  const auto& rows = PermSpy::perms(table);
+  const size_t m = rows.empty() ? 0 : rows[0].size();
+  const py::ssize_t n = pairs.shape(0);
+  py::array_t<unsigned> out({n, static_cast<py::ssize_t>(2), static_cast<py::ssize_t>(m)});
+  auto p = pairs.unchecked<2>();
+  unsigned* o = out.mutable_data();
+  for (py::ssize_t k = 0; k < n; ++k) {
+    const auto& a = rows[look.row(p(k, 0), p(k, 1))];
+    const auto& b = rows[look.row(p(k, 1), p(k, 0))];
+    for (size_t e = 0; e < m; ++e) {
+      o[(2 * k) * m + e] = a[e];
+      o[(2 * k + 1) * m + e] = b[e];
+    }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // module
 // ---------------------------------------------------------------------------------------------
 template <class T, class R>
@@ -528,6 +581,10 @@ static void def_trellis(py::module& m) {
         "Structure tables (Brillouin zone + trellis) of a BZTrellisQ* object");
   m.def("flatten_data", [](const G& g) { return flatten_trellis_data(g); }, py::arg("grid"),
         "Data tables (values, vectors, permutations, gamma table) of a BZTrellisQ* object");
+  m.def("sort_plan", [](const G& g) { return sort_plan(g.data()); }, py::arg("grid"),
+        "Vertex pairs and cost configuration of DualInterpolator::sort()");
+  m.def("pair_permutations", [](const G& g, py::array_t<unsigned, py::array::c_style | py::array::forcecast> p) { return pair_permutations(g.data(), p); },
+        py::arg("grid"), py::arg("pairs"));
 }
 
 template <class T, class R>
@@ -538,6 +595,12 @@ static void def_nest_mesh(py::module& m) {
   m.def("flatten_data", [](const N& g) { return flatten_nest_data(g); }, py::arg("grid"));
   m.def("flatten", [](const M& g) { return flatten_mesh(g); }, py::arg("grid"));
   m.def("flatten_data", [](const M& g) { return flatten_mesh_data(g); }, py::arg("grid"));
+  m.def("sort_plan", [](const N& g) { return sort_plan(g.data()); }, py::arg("grid"));
+  m.def("sort_plan", [](const M& g) { return sort_plan(g.data()); }, py::arg("grid"));
+  m.def("pair_permutations", [](const N& g, py::array_t<unsigned, py::array::c_style | py::array::forcecast> p) { return pair_permutations(g.data(), p); },
+        py::arg("grid"), py::arg("pairs"));
+  m.def("pair_permutations", [](const M& g, py::array_t<unsigned, py::array::c_style | py::array::forcecast> p) { return pair_permutations(g.data(), p); },
+        py::arg("grid"), py::arg("pairs"));
 }
 
 PYBIND11_MODULE(_bridge, m) {
