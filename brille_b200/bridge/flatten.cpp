@@ -348,6 +348,22 @@ static py::dict flatten_trellis_data(const BrillouinZoneTrellis3<T, R, S>& g) {
   bool any = false;
   flatten_perm_rows(g.data(), d, any);
   d["perm_nonidentity"] = any ? 1 : 0;
+  {  // the vertex lists the per-cell pair tables are indexed by (also the input of the device-side sort())
+    using Spy = TrellisSpy<T, R, S>;
+    const auto& nodes = Spy::nodes(g);
+    std::vector<unsigned> cv, tv;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      auto t = nodes.type(static_cast<ind_t>(i));
+      if (NodeType::cube == t) {
+        for (auto v : CubeNodeSpy::vi(nodes.cube_at(static_cast<ind_t>(i)))) cv.push_back(v);
+      } else if (NodeType::poly == t) {
+        for (const auto& vi : PolyNodeSpy::vi(nodes.poly_at(static_cast<ind_t>(i))))
+          for (int a = 0; a < 4; ++a) tv.push_back(vi[a]);
+      }
+    }
+    d["perm_cube_vertices"] = np2(cv, 8);
+    d["perm_tet_vertices"] = np2(tv, 4);
+  }
   if (any) {
     // per-cell pair -> permutation-row index, so the device needs no map lookups
     using Spy = TrellisSpy<T, R, S>;
@@ -431,6 +447,8 @@ static void flatten_tet_perms(const DualInterpolator<T, R>& data, const std::vec
   bool any = false;
   flatten_perm_rows(data, d, any);
   d["perm_nonidentity"] = any ? 1 : 0;
+  d["perm_cube_vertices"] = np2(std::vector<unsigned>(), 8);
+  d["perm_tet_vertices"] = np2(tets, 4);
   if (!any) return;
   PermLookup look(DualSpy<T, R>::table(data));
   std::vector<unsigned> tp;

@@ -32,7 +32,19 @@ EXPORTS = (
     "b200_grid_kernel_ms",
     "b200_grid_row_bytes",
     "b200_grid_set_option",
+    "b200_grid_sort_pairs",
 )
+
+
+class SortConfig(C.Structure):
+    """``b200_sort_config_t``"""
+
+    _fields_ = [
+        ("values_costmult", C.c_double * 3),
+        ("vectors_costmult", C.c_double * 3),
+        ("values_vector_cost", C.c_int32),
+        ("vectors_vector_cost", C.c_int32),
+    ]
 
 
 class B200Error(RuntimeError):
@@ -86,6 +98,8 @@ def lib():
     L.b200_grid_kernel_ms.argtypes = [vp, C.c_char_p]
     L.b200_grid_set_option.restype = C.c_int
     L.b200_grid_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.b200_grid_sort_pairs.restype = C.c_int
+    L.b200_grid_sort_pairs.argtypes = [vp, vp, C.c_size_t, C.POINTER(SortConfig), vp, vp, vp]
     L.b200_grid_row_bytes.restype = C.c_int
     L.b200_grid_row_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L

@@ -925,6 +925,24 @@ extern "C" int b200_device_count(void) {
   return n;
 }
 extern "C" uint64_t b200_grid_launch_count(const b200_grid_t* g) { return g ? g->launches : 0; }
+extern "C" int b200_grid_sort_pairs(b200_grid_t* g, const uint32_t* pairs, size_t n_pairs, const b200_sort_config_t* cfg, int32_t* row_out,
+                                    int32_t* col_out, double* cost_out) {
+  if (!g || !cfg || (n_pairs && (!pairs || !row_out || !col_out))) return fail(B200_E_INVALID, "NULL argument");
+  if (!g->has_data) return fail(B200_E_NODATA, "The interpolation data must be filled before sorting.");
+  if (!g->dd.vectors.is_complex && g->dd.vectors.span)
+    return fail(B200_E_UNSUPPORTED, "sort() of real-valued eigenvectors is not offloaded (the reference's anti-phase of real data is undefined)");
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (pairs[2 * k] >= g->n_vertices || pairs[2 * k + 1] >= g->n_vertices) return fail(B200_E_INVALID, "vertex index out of range in pairs");
+  CU(cudaSetDevice(g->device));
+  CU(cudaDeviceSynchronize());
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t ws = std::min<size_t>(free_b / 4, (size_t)1 << 30);
+  CU(run_sort_pairs(g->dd, cfg->values_costmult, cfg->values_vector_cost, cfg->vectors_costmult, cfg->vectors_vector_cost, pairs, n_pairs,
+                    row_out, col_out, cost_out, g->sm_count, ws, &g->launches));
+  return B200_OK;
+}
+
 extern "C" int b200_grid_enable_timing(b200_grid_t* g, int on) {
   if (!g) return fail(B200_E_INVALID, "NULL grid");
   g->timing = on != 0;

@@ -126,10 +126,40 @@ class B200Grid:
         self._sync_data()
         return out
 
-    def sort(self, *args, **kwargs):
-        out = self._host.sort(*args, **kwargs)
-        self._sync_data()
-        return out
+    def sort(self, *args, device=True, **kwargs):
+        """brille ``sort`` (wrap/_common_grid.hpp:486, interpolatordual.hpp:398-434): the equivalent-mode permutation of every
+        connected vertex pair.
+
+        ``device=True`` (default) solves the pairs on the GPU (``b200_grid_sort_pairs``) and installs the permutations in
+        the device tables; brille's host object is left untouched (its own ``ir_interpolate_at`` keeps interpolating
+        unsorted data).  ``device=False`` runs brille's host ``sort`` and re-uploads the tables, as do grids whose
+        eigenvectors are real (not offloaded, see the header)."""
+        data = _bridge().flatten_data(self._host) if self._host is not None else None
+        if not device or data is None or not np.iscomplexobj(np.asarray(data["vectors_data"])):
+            out = self._host.sort(*args, **kwargs)
+            self._sync_data()
+            return out
+        self._set_data(data)  # the costs are evaluated on the data as filled
+        plan = _bridge().sort_plan(self._host)
+        row, col = self.sort_pairs(plan["pairs"], plan)
+        self._set_data(install_permutations(data, plan["pairs"], row, col, int(plan["n_vertices"])))
+        return None
+
+    def sort_pairs(self, pairs, plan, want_cost=False):
+        """Permutations (row for (i, j), col for (j, i)) of the given vertex pairs, computed on the device."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        cfg = capi.SortConfig()
+        cfg.values_costmult[:] = [float(x) for x in plan["values_costmult"]]
+        cfg.vectors_costmult[:] = [float(x) for x in plan["vectors_costmult"]]
+        cfg.values_vector_cost = int(plan["values_vector_cost"])
+        cfg.vectors_vector_cost = int(plan["vectors_vector_cost"])
+        B = int(self._data_tables.values.branches)
+        row = np.zeros((pairs.shape[0], B), dtype=np.int32)
+        col = np.zeros((pairs.shape[0], B), dtype=np.int32)
+        cost = np.zeros((pairs.shape[0], B, B), dtype=np.float64) if want_cost else None
+        capi.check(capi.lib().b200_grid_sort_pairs(self._handle, pairs.ctypes.data, pairs.shape[0], C.byref(cfg), row.ctypes.data, col.ctypes.data,
+                                                   cost.ctypes.data if want_cost else None))
+        return (row, col, cost) if want_cost else (row, col)
 
     # ------------------------------------------------------------------ the path
     def _check_q(self, Q):
@@ -258,6 +288,45 @@ class _Owned(np.ndarray):
 
     def __array_finalize__(self, obj):
         self._owner = getattr(obj, "_owner", None)
+
+
+def install_permutations(data, pairs, row, col, n_vertices):
+    """A copy of the bridge data dictionary whose permutation tables hold ``row``/``col`` of the vertex ``pairs``.
+
+    Table row 0 is the identity (pairs that are not connected, i == j), row 1 + 2k the permutation of (i, j) = pairs[k] and
+    row 2 + 2k the one of (j, i) -- the lookup of PermutationTable::safe_get (permutation_table.hpp:193-198,214) without
+    its de-duplication of equal permutations."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint64).reshape(-1, 2)
+    B = row.shape[1]
+    rows = np.empty((1 + 2 * pairs.shape[0], B), dtype=np.uint32)
+    rows[0] = np.arange(B, dtype=np.uint32)
+    rows[1::2] = row
+    rows[2::2] = col
+    keys = pairs[:, 0] * np.uint64(n_vertices) + pairs[:, 1]
+    order = np.argsort(keys, kind="stable")
+    skeys = keys[order]
+
+    def table(cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        if cells.size == 0:
+            return np.zeros((0, cells.shape[1] ** 2 if cells.ndim == 2 else 0), dtype=np.uint32)
+        a = cells[:, :, None]
+        b = cells[:, None, :]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        key = lo * np.uint64(n_vertices) + hi
+        pos = np.searchsorted(skeys, key)
+        pos = np.minimum(pos, max(len(skeys) - 1, 0))
+        found = (len(skeys) > 0) & (skeys[pos] == key) & (a != b) if len(skeys) else np.zeros(key.shape, dtype=bool)
+        k = order[pos] if len(skeys) else np.zeros(key.shape, dtype=np.int64)
+        idx = np.where(found, 1 + 2 * k + (a > b), 0)
+        return idx.reshape(cells.shape[0], -1).astype(np.uint32)
+
+    d = dict(data)
+    d["perm_rows"] = rows
+    d["perm_nonidentity"] = 1
+    d["cube_perm"] = table(np.asarray(data["perm_cube_vertices"]).reshape(-1, 8)) if np.asarray(data["perm_cube_vertices"]).size else np.zeros((0, 64), dtype=np.uint32)
+    d["tet_perm"] = table(np.asarray(data["perm_tet_vertices"]).reshape(-1, 4))
+    return d
 
 
 def accelerate(host_grid, device=0):

@@ -224,6 +224,26 @@ int b200_interpolate_at(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t 
  * fills probe->q_ir, tau, ridx, invridx, status (x_ir if requested).  ir=0 selects moveinto.                */
 int b200_moveinto(b200_grid_t* grid, const double* Q, size_t nQ, int ir, b200_probe_t* probe);
 
+/* ---- sort() on the device --------------------------------------------------------------
+ * Replaces the parallel loop of DualInterpolator::sort() (interpolatordual.hpp:398-434): for every connected vertex
+ * pair (i, j) of `pairs` (n_pairs x 2, i < j; the keys of brille's PermutationTable) the modes x modes cost matrix of
+ * Interpolator::add_cost (interpolator_cost.tpp:18-58) is built from the data given to b200_grid_set_data and the
+ * Jonker-Volgenant assignment (lapjv.hpp:281-538) is solved.  row_out (n_pairs x modes) receives the permutation the
+ * reference stores for (i, j), col_out the one it stores for (j, i).  The cost configuration is what
+ * set_flags_weights leaves in the Interpolators (interpolator.hpp:246-305): relative weights of the scalar / vector /
+ * matrix parts and the vector cost function (0 sin^2 of the Hermitian angle, 1 distance, 2 1 - |<a|b>|^2, 3 vector
+ * angle, 4 Hermitian angle).  Real-valued eigenvectors are refused (B200_E_UNSUPPORTED): the reference reads an
+ * uninitialised buffer for them (utilities.tpp:530).  cost_out (optional, n_pairs x modes x modes) receives the cost
+ * matrices.  Host buffers; synchronous.                                                                           */
+typedef struct b200_sort_config {
+  double values_costmult[3];
+  double vectors_costmult[3];
+  int32_t values_vector_cost;
+  int32_t vectors_vector_cost;
+} b200_sort_config_t;
+int b200_grid_sort_pairs(b200_grid_t* grid, const uint32_t* pairs, size_t n_pairs, const b200_sort_config_t* config,
+                         int32_t* row_out, int32_t* col_out, double* cost_out);
+
 /* Page-locked host memory for Q / output buffers: with pinned buffers the chunked copies of the host-buffer
  * entry points overlap the kernels (pageable memory works too but serialises the copies).                  */
 void* b200_alloc_pinned(size_t bytes);

@@ -41,6 +41,8 @@ def lib():
         _lib.oracle_sort_pairs.restype = C.c_int
         _lib.oracle_sort_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_lapjv_batch.restype = C.c_int
+        _lib.oracle_lapjv_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.oracle_moveinto.restype = C.c_int
         _lib.oracle_moveinto.argtypes = [C.POINTER(T.BZTables), C.c_void_p, C.c_size_t, C.c_int, C.POINTER(T.Probe)]
     return _lib
@@ -110,3 +112,13 @@ def sort_pairs(data, plan, pairs=None, want_cost=False):
                                  wcm.ctypes.data, wfun, B, pairs.ctypes.data, n, row.ctypes.data, col.ctypes.data,
                                  cost.ctypes.data if want_cost else None)
     return (rc, row, col, cost) if want_cost else (rc, row, col)
+
+
+def lapjv_batch(cost):
+    """Jonker-Volgenant assignment (lapjv.hpp:281-538 restated) of every (branches, branches) cost matrix in ``cost``."""
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    n, B, _ = cost.shape
+    row = np.zeros((n, B), dtype=np.int32)
+    col = np.zeros((n, B), dtype=np.int32)
+    lib().oracle_lapjv_batch(cost.ctypes.data, n, B, row.ctypes.data, col.ctypes.data)
+    return row, col

@@ -408,3 +408,18 @@ int oracle_sort_pairs(const double* values, int v_cplx, const uint32_t* v_el, co
   }
   return rc;
 }
+
+/* The assignment step alone on given cost matrices (n_pairs, branches, branches): lets the tests check the integer part of
+ * the device path bit for bit on the device's own cost matrices. */
+int oracle_lapjv_batch(const double* cost, size_t n_pairs, uint32_t branches, int32_t* row, int32_t* col) {
+  const uint32_t B = branches;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (long long k = 0; k < (long long)n_pairs; ++k) {
+    double* u = (double*)calloc(B, sizeof(double));
+    double* v = (double*)calloc(B, sizeof(double));
+    lapjv((int)B, cost + (size_t)k * B * B, row + (size_t)k * B, col + (size_t)k * B, u, v);
+    free(u);
+    free(v);
+  }
+  return 0;
+}

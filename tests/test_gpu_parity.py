@@ -284,3 +284,97 @@ def test_full_size_properties(host):
     for j in (1, 5, 11, 17):
         vr, _ = g.ir_interpolate_at(sub @ ops[j].astype(float))  # rows are R^T q
         assert rel_close(vr, vals[:50000]) <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sort() on the device: interpolatordual.hpp:398-434, interpolator_cost.tpp, lapjv.hpp
+# ---------------------------------------------------------------------------------------------------------------------
+def _sort_workload(host, which):
+    if which == "C2":
+        return W.c2_nacl(host, density=300)
+    if which == "C3":
+        return W.c3_p63mmc(host, density=300, seed=5)
+    if which == "C4":
+        return W.c4_p21c_nest(host, density=40)
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    if which == "C3nest":
+        g = host.BZNestQdc(bz, bz.ir_polyhedron.volume / 200, 5)
+    else:
+        g = host.BZMeshQdc(bz, bz.ir_polyhedron.volume / 200, 3)
+    return W.Workload(which, g, bz, 12, 4, W._uniform_q(-3, 3), W._gamma_fill(g, 12, 4, 3))
+
+
+@pytest.mark.parametrize("which", ["C2", "C3", "C3nest", "C3mesh", "C4"])
+def test_device_sort_matches_reference_and_oracle(host, bridge, which):
+    """sort() on the device against the oracle and the reference's own sort().
+
+    The path has a floating-point part (cost matrices: atan2, cos, sin, acos of CUDA's libm instead of glibc's) and an
+    integer part (the Jonker-Volgenant solver).  Bars: (1) cost matrices within 4 ulp of the oracle's; (2) the solver is
+    bit-identical to the restated reference solver on the same (device) cost matrices; (3) the permutations equal the
+    reference's own.  The reference's solver breaks ties with a cost-proportional epsilon (lapjv.hpp:312-314), which makes
+    a pair in ~1000 depend on the last bit of a cost: for those the two assignments must be equally good (total cost within
+    1e-3) -- the analogue of a Q within tolerance of a face taking either side."""
+    from oracle import oracle as orc
+
+    wl = _sort_workload(host, which)
+    plan = bridge.sort_plan(wl.grid)
+    data = bridge.flatten_data(wl.grid)
+    g = brille_b200.accelerate(wl.grid)
+    row, col, cost = g.sort_pairs(plan["pairs"], plan, want_cost=True)
+    rc, orow, ocol, ocost = orc.sort_pairs(data, plan, want_cost=True)
+    assert rc == 0
+    assert np.abs(cost - ocost).max() <= 4 * 2.3e-16 * np.abs(ocost).max(), "(1) cost matrices"
+    lrow, lcol = orc.lapjv_batch(cost)
+    assert np.array_equal(row, lrow) and np.array_equal(col, lcol), "(2) solver on the device's cost matrices"
+    B = row.shape[1]
+    assert np.array_equal(np.take_along_axis(col, row, axis=1), np.broadcast_to(np.arange(B), row.shape))
+    # (3) the reference's own sort()
+    g.sort()  # device: installs the permutations in the device tables only
+    Q = wl.make_q(20000, 77)
+    vals, vecs = g.ir_interpolate_at(Q)
+    wl.grid.sort()
+    ref = bridge.pair_permutations(wl.grid, plan["pairs"])
+    assert np.array_equal(orow.astype(np.uint32), ref[:, 0, :]) and np.array_equal(ocol.astype(np.uint32), ref[:, 1, :]), "oracle vs reference"
+    differ = np.where((row.astype(np.uint32) != ref[:, 0, :]).any(axis=1))[0]
+    assert len(differ) <= max(1, len(row) // 200), f"{len(differ)} of {len(row)} pairs differ"
+    ar = np.arange(B)
+    for k in differ:
+        mine, theirs = ocost[k][ar, row[k]].sum(), ocost[k][ar, orow[k]].sum()
+        assert abs(mine - theirs) <= 1e-3 * abs(theirs), (k, mine, theirs)
+    # interpolation through the device-sorted tables: against the oracle with the same tables, and against the reference
+    # (after its own sort) wherever no differing pair is involved
+    from brille_b200.grid import install_permutations
+
+    o = Oracle(bridge.flatten(wl.grid), install_permutations(data, plan["pairs"], row, col, int(plan["n_vertices"])))
+    rc, ov, ow, _ = o.interpolate_at(Q)
+    assert rc == 0
+    assert_values_close(vals, ov)
+    assert_values_close(vecs, ow)
+    if len(differ) == 0:
+        rv, rw = wl.grid.ir_interpolate_at(Q, True, 8)
+        assert_values_close(vals, rv)
+        assert_values_close(vecs, rw)
+        g2 = brille_b200.accelerate(wl.grid)  # tables flattened from the host-sorted object: same bits
+        v2, w2 = g2.ir_interpolate_at(Q)
+        assert np.array_equal(v2, vals) and np.array_equal(w2, vecs)
+
+
+def test_device_sort_cost_functions_and_errors(host, bridge):
+    wl = W.c2_nacl(host, density=100)
+    wl.grid.set_flags_weights(np.array([0, 0, 0, 1], dtype=np.int32), np.array([1.0, 1.0, 1.0]),
+                              np.array([2, 3, 0, 4], dtype=np.int32), np.array([0.5, 2.0, 1.0]))
+    plan = bridge.sort_plan(wl.grid)
+    g = brille_b200.accelerate(wl.grid)
+    row, col = g.sort_pairs(plan["pairs"], plan)
+    wl.grid.sort()
+    ref = bridge.pair_permutations(wl.grid, plan["pairs"])
+    same = (row.astype(np.uint32) == ref[:, 0, :]).all(axis=1) & (col.astype(np.uint32) == ref[:, 1, :]).all(axis=1)
+    assert same.mean() >= 0.995
+    with pytest.raises(RuntimeError, match="out of range"):
+        g.sort_pairs(np.array([[0, 10**6]], dtype=np.uint32), plan)
+    # real eigenvectors: not offloaded
+    s, d, _, rest = load_golden("p1_trellis_dd.npz")
+    gd = brille_b200.B200Grid(None, structure=s, data=d)
+    with pytest.raises(RuntimeError, match="real-valued"):
+        gd.sort_pairs(np.array([[0, 1]], dtype=np.uint32), plan)
