@@ -153,6 +153,7 @@ struct b200_grid {
   unsigned char* cell_table = nullptr;  // pre-aligned per-cell records (cellinterp_tma.cu), built lazily per fill
   CellTableDev ct{};
   bool cell_table_refused = false;      // did not fit: do not try again until the data changes
+  SortWorkspace sort_ws;                // device work space of b200_grid_sort_pairs
   uint64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -535,6 +536,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
   g->structure_pool.release();
   g->data_pool.release();
   drop_cell_table(g);
+  g->sort_ws.release();
   g->ws.release();
   if (g->d_fail) cudaFree(g->d_fail);
   for (int s = 0; s < 2; ++s) {
@@ -937,9 +939,9 @@ extern "C" int b200_grid_sort_pairs(b200_grid_t* g, const uint32_t* pairs, size_
   CU(cudaDeviceSynchronize());
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  const size_t ws = std::min<size_t>(free_b / 4, (size_t)1 << 30);
+  const size_t ws = std::min<size_t>((free_b + g->sort_ws.batch * 8 * g->sort_ws.branches * g->sort_ws.branches) / 4, (size_t)1 << 30);
   CU(run_sort_pairs(g->dd, cfg->values_costmult, cfg->values_vector_cost, cfg->vectors_costmult, cfg->vectors_vector_cost, pairs, n_pairs,
-                    row_out, col_out, cost_out, g->sm_count, ws, &g->launches));
+                    row_out, col_out, cost_out, g->sm_count, ws, g->sort_ws, &g->launches));
   return B200_OK;
 }
 

@@ -237,7 +237,21 @@ cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vert
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
                                    int sm_count, cudaStream_t stream);
 
+// device work space of sort() (sortpairs.cu), kept by the grid between calls
+struct SortWorkspace {
+  size_t batch = 0;
+  uint32_t branches = 0;
+  uint32_t* pairs = nullptr;
+  double* cost = nullptr;
+  double* fwork = nullptr;
+  int* row = nullptr;
+  int* col = nullptr;
+  int* iwork = nullptr;
+  cudaError_t ensure(size_t n_pairs, uint32_t branches);
+  void release();
+};
 cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun, const double w_mult[3], int w_vfun, const uint32_t* h_pairs,
-                           size_t n_pairs, int32_t* h_row, int32_t* h_col, double* h_cost, int sm_count, size_t max_ws_bytes, uint64_t* launches);
+                           size_t n_pairs, int32_t* h_row, int32_t* h_col, double* h_cost, int sm_count, size_t max_ws_bytes,
+                           SortWorkspace& ws, uint64_t* launches);
 
 }  // namespace b200

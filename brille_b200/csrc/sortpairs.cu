@@ -395,9 +395,31 @@ __global__ void __launch_bounds__(128) k_pair_assign(uint32_t B, size_t n_pairs,
   }
 }
 
-// host side: pairs are processed in batches so that the cost matrices stay within `max_ws_bytes`
+// host side: pairs are processed in batches so that the cost matrices stay within `max_ws_bytes`; the work space is kept
+// by the caller between calls (cudaMalloc / cudaFree cost more than the kernels)
+void SortWorkspace::release() {
+  cudaFree(pairs); cudaFree(cost); cudaFree(fwork); cudaFree(row); cudaFree(col); cudaFree(iwork);
+  pairs = nullptr; cost = fwork = nullptr; row = col = iwork = nullptr;
+  batch = 0; branches = 0;
+}
+cudaError_t SortWorkspace::ensure(size_t n, uint32_t B) {
+  if (n <= batch && B == branches) return cudaSuccess;
+  release();
+  cudaError_t e;
+  if ((e = cudaMalloc(&pairs, n * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&cost, n * B * B * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fwork, n * 2 * B * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&iwork, n * 4 * B * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&row, n * B * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&col, n * B * sizeof(int))) != cudaSuccess) return e;
+  batch = n;
+  branches = B;
+  return cudaSuccess;
+}
+
 cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun, const double w_mult[3], int w_vfun, const uint32_t* h_pairs,
-                           size_t n_pairs, int32_t* h_row, int32_t* h_col, double* h_cost, int sm_count, size_t max_ws_bytes, uint64_t* launches) {
+                           size_t n_pairs, int32_t* h_row, int32_t* h_col, double* h_cost, int sm_count, size_t max_ws_bytes,
+                           SortWorkspace& ws, uint64_t* launches) {
   const uint32_t B = dd.vectors.branches;
   if (n_pairs == 0 || B == 0) return cudaSuccess;
   CostCfg cfg;
@@ -408,34 +430,23 @@ cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun
   size_t batch = max_ws_bytes / per_pair;
   if (batch < 1) batch = 1;
   if (batch > n_pairs) batch = n_pairs;
-  uint32_t* d_pairs = nullptr;
-  double *d_cost = nullptr, *d_f = nullptr;
-  int *d_row = nullptr, *d_col = nullptr, *d_i = nullptr;
-  cudaError_t e = cudaSuccess;
-  auto done = [&](cudaError_t r) {
-    cudaFree(d_pairs); cudaFree(d_cost); cudaFree(d_f); cudaFree(d_row); cudaFree(d_col); cudaFree(d_i);
-    return r;
-  };
-  if ((e = cudaMalloc(&d_pairs, batch * 2 * sizeof(uint32_t))) != cudaSuccess) return done(e);
-  if ((e = cudaMalloc(&d_cost, batch * B * B * sizeof(double))) != cudaSuccess) return done(e);
-  if ((e = cudaMalloc(&d_f, batch * 2 * B * sizeof(double))) != cudaSuccess) return done(e);
-  if ((e = cudaMalloc(&d_i, batch * 4 * B * sizeof(int))) != cudaSuccess) return done(e);
-  if ((e = cudaMalloc(&d_row, batch * B * sizeof(int))) != cudaSuccess) return done(e);
-  if ((e = cudaMalloc(&d_col, batch * B * sizeof(int))) != cudaSuccess) return done(e);
+  cudaError_t e = ws.ensure(batch, B);
+  if (e != cudaSuccess) { ws.release(); return e; }
+  batch = ws.batch;
   for (size_t lo = 0; lo < n_pairs; lo += batch) {
     const size_t n = n_pairs - lo < batch ? n_pairs - lo : batch;
-    if ((e = cudaMemcpy(d_pairs, h_pairs + 2 * lo, n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return done(e);
+    if ((e = cudaMemcpy(ws.pairs, h_pairs + 2 * lo, n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     const size_t entries = n * B * B, want = (entries + 255) / 256, cap = (size_t)sm_count * 32;
-    k_pair_costs<<<(unsigned)(want < cap ? want : cap), 256>>>(dd.values, dd.vectors, cfg, d_pairs, n, d_cost);
+    k_pair_costs<<<(unsigned)(want < cap ? want : cap), 256>>>(dd.values, dd.vectors, cfg, ws.pairs, n, ws.cost);
     const size_t want2 = (n + 127) / 128;
-    k_pair_assign<<<(unsigned)(want2 < cap ? want2 : cap), 128>>>(B, n, d_cost, d_row, d_col, d_f, d_i);
+    k_pair_assign<<<(unsigned)(want2 < cap ? want2 : cap), 128>>>(B, n, ws.cost, ws.row, ws.col, ws.fwork, ws.iwork);
     if (launches) *launches += 2;
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
-    if ((e = cudaMemcpy(h_row + lo * B, d_row, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(e);
-    if ((e = cudaMemcpy(h_col + lo * B, d_col, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(e);
-    if (h_cost && (e = cudaMemcpy(h_cost + lo * B * B, d_cost, n * B * B * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(e);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(h_row + lo * B, ws.row, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(h_col + lo * B, ws.col, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if (h_cost && (e = cudaMemcpy(h_cost + lo * B * B, ws.cost, n * B * B * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
   }
-  return done(cudaSuccess);
+  return cudaSuccess;
 }
 
 }  // namespace b200
