@@ -149,6 +149,7 @@ struct b200_grid {
   size_t host_chunk = 0;   // max points per chunk of the host-buffer pipeline (0 = sized from free memory)
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
+  int tile = 4;            // points per register tile of the pipelined cell kernel (4: 2 CTAs/SM, 2: 3 CTAs/SM)
   int cell_kernel = 0;     // 0 auto (pipelined kernel when its cell table fits), 1 on-the-fly staging kernel, 2 pipelined only
   unsigned char* cell_table = nullptr;  // pre-aligned per-cell records (cellinterp_tma.cu), built lazily per fill
   CellTableDev ct{};
@@ -661,7 +662,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   bool tma = false;
   if (cell && g->cell_kernel != 1) {
     // pipelined kernel: needs the per-cell records, built once per fill (synchronously: the two host-pipeline streams share it)
-    const uint32_t ch = cell_tma_pick(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 108 * 1024, &mpp);
+    const uint32_t ch = cell_tma_pick(g->dd, g->gd.cells.n_cubes > 0, g->chunk, (g->tile == 2 ? 72 : 108) * 1024, &mpp);
     if (ch && mpp) {
       if (g->cell_table && g->ct.mpp == mpp) {
         tma = true;
@@ -728,7 +729,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     a.vecs_out = dvecs;
     a.ir = ir;
     a.modes_per_pass = mpp;
-    if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream));
+    if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile));
     else CU(launch_interp_cell(a, n, stream));
     // points that are not generic members of their cell (and failed points): general kernel over the last bucket
     CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, ws.bk.order, ws.bk.n_items));
@@ -963,6 +964,9 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   if (n == "interp_path") {
     if (value < 0 || value > 2) return fail(B200_E_INVALID, "interp_path must be 0 (auto), 1 (general) or 2 (cell-batched)");
     g->interp_path = (int)value;
+  } else if (n == "tile") {
+    if (value != 2 && value != 4) return fail(B200_E_INVALID, "tile must be 2 or 4");
+    g->tile = (int)value;
   } else if (n == "cell_kernel") {
     if (value < 0 || value > 2) return fail(B200_E_INVALID, "cell_kernel must be 0 (auto), 1 (on-the-fly staging) or 2 (pipelined, cell table)");
     g->cell_kernel = (int)value;

@@ -106,6 +106,31 @@ struct CellPass {
   uint32_t* task_ctr;  // shared counter (zero at the start of the pass) for the dynamic deal of tasks, or nullptr
 };
 
+// TQ consecutive doubles / 32-bit words of a shared-memory array (TQ = 2 or 4, 8- resp. 16-byte aligned)
+template <int TQ>
+__device__ __forceinline__ void load_tile(const double* p, double* w) {
+  if (TQ == 4) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+  } else {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    w[0] = a.x; w[1] = a.y;
+  }
+}
+template <int TQ>
+__device__ __forceinline__ void load_tile(const uint32_t* p, uint32_t* w) {
+  if (TQ == 4) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+  } else {
+    const uint2 a = *reinterpret_cast<const uint2*>(p);
+    w[0] = a.x; w[1] = a.y;
+  }
+}
+
+// TQ = points per register tile: 4 (48 accumulator registers, 2 CTAs/SM) or 2 (24, 3 CTAs/SM).  The arithmetic per point
+// does not depend on TQ: both give the same bits.
+template <int TQ>
 __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, int nthr) {
   const double2* D = c.D;
   const double* V = c.V;
@@ -123,25 +148,24 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
   struct { const double* rot_det; } dd_ = {c.rot_det};
   struct { double* vals_out; double* vecs_out; decltype(dd_) dd; } a = {c.vals_out, c.vecs_out, dd_};
     // ---- eigenvalues: plain weighted sum; a task is one value column for TQ consecutive points ------------------------
-    constexpr int TQ = 4;
     const uint32_t ntile = (item.len + TQ - 1) / TQ;
     {
       const uint32_t per_v = mb * no0v;
       for (uint32_t task = tid; task < ntile * per_v; task += nthr) {
         const uint32_t tile = task / per_v, r = task - tile * per_v, t0 = tile * TQ;
-        double acc[TQ] = {0.0, 0.0, 0.0, 0.0};
+        double acc[TQ];
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) acc[t] = 0.0;
         for (int i = 0; i < NV; ++i) {
           const double v = V[(size_t)i * mpp * no0v + r];
-          const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
-          const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
-          acc[0] = __fma_rn(wa.x, v, acc[0]);
-          acc[1] = __fma_rn(wa.y, v, acc[1]);
-          acc[2] = __fma_rn(wb.x, v, acc[2]);
-          acc[3] = __fma_rn(wb.y, v, acc[3]);
+          double w[TQ];
+          load_tile<TQ>(W + (size_t)i * CH + t0, w);
+#pragma unroll
+          for (int t = 0; t < TQ; ++t) acc[t] = __fma_rn(w[t], v, acc[t]);
         }
         const uint32_t nt = min((uint32_t)TQ, item.len - t0);
-        const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
-        const uint32_t qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
+        uint32_t qis[TQ];
+        load_tile<TQ>(QI + t0, qis);
 #pragma unroll
         for (int t = 0; t < TQ; ++t)
           if ((uint32_t)t < nt) a.vals_out[(size_t)qis[t] * vrow + (size_t)b0 * no0v + r] = acc[t];
@@ -184,9 +208,8 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
       for (int i = 0; i < NV; ++i) {
         const double2* x = src + (size_t)i * mpp * S;
         const double2 x0 = x[0], x1 = x[1], x2 = x[2];
-        const double2 wa = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0);
-        const double2 wb = *reinterpret_cast<const double2*>(W + (size_t)i * CH + t0 + 2);
-        const double w[TQ] = {wa.x, wa.y, wb.x, wb.y};
+        double w[TQ];
+        load_tile<TQ>(W + (size_t)i * CH + t0, w);
 #pragma unroll
         for (int t = 0; t < TQ; ++t) {
           acc[t][0].x += w[t] * x0.x; acc[t][0].y += w[t] * x0.y;
@@ -196,17 +219,17 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
       }
       // ---- finish: rotation, atom permutation, Gamma phase, store ------------------------------------------------------
       const uint32_t nt = min((uint32_t)TQ, item.len - t0);
-      const uint4 rr4 = *reinterpret_cast<const uint4*>(RI + t0);
-      const uint4 qi4 = *reinterpret_cast<const uint4*>(QI + t0);
-      const uint32_t rrs[TQ] = {rr4.x, rr4.y, rr4.z, rr4.w}, qis[TQ] = {qi4.x, qi4.y, qi4.z, qi4.w};
+      uint32_t rrs[TQ], qis[TQ];
+      load_tile<TQ>(RI + t0, rrs);
+      load_tile<TQ>(QI + t0, qis);
       double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + (size_t)(b0 + b) * S;
-      if (gamma && nt == TQ && (rr4.x & 0xffffu) == (rr4.w & 0xffffu) && ((wrow & 1) == 0)) {
+      if (gamma && nt == TQ && (rrs[0] & 0xffffu) == (rrs[TQ - 1] & 0xffffu) && ((wrow & 1) == 0)) {
         // The four points share the rotation (the sort is by cell and operation): one matrix, one destination atom, no
         // branches.  The 48 output bytes of a point go out as one 32-byte-aligned 32-byte store plus one 16-byte store
         // (see store48); which of the three components forms the aligned pair depends only on the parity of the
         // destination (rows are a multiple of 32 bytes here), so the ROWS of the matrix are loaded in store order
         // (pair, pair, single) and no data has to be shuffled afterwards.
-        const uint32_t ri = rr4.x & 0xffffu;
+        const uint32_t ri = rrs[0] & 0xffffu;
         const uint32_t dest = F0[k * G + ri];
         double2* const out0 = out_base + 3 * dest;
         const bool even = (reinterpret_cast<uintptr_t>(out0) & 31u) == 0;  // row starts are 32-byte aligned

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
     cp.D = D; cp.V = V; cp.W = W; cp.PH = PH; cp.RS = RS; cp.F0 = F0; cp.QI = QI; cp.RI = RI;
     cp.CH = CH; cp.mpp = mpp; cp.mb = mb; cp.b0 = b0; cp.len = item.len; cp.M = M; cp.S = S; cp.NAT = NAT; cp.no0v = no0v; cp.G = G;
     cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out; cp.task_ctr = nullptr;
-    cell_compute_pass(cp, tid, nthr);
+    cell_compute_pass<4>(cp, tid, nthr);
   }
 }
 

@@ -152,7 +152,8 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
 constexpr uint32_t NO_ITEM = 0xffffffffu;
 constexpr uint32_t ITEM_BLOCK = 4;
 
-__global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
+template <int TQ>
+__global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
                                                             const unsigned char* __restrict__ table, const __grid_constant__ TmaPlan pl) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell_tma(const __grid_constan
       cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
       cp.task_ctr = s_task_ctr + (n_done & 1u);
       if (tid == 0) s_task_ctr[(n_done + 1u) & 1u] = 0u;  // the counter of the next pass: idle since the previous barrier
-      cell_compute_pass(cp, tid, nthr);
+      cell_compute_pass<TQ>(cp, tid, nthr);
       if (pass + 1 == n_pass) {
         if (nxt_key != NO_ITEM) {  // tables of item n+1 into the other set
           wait_raw(it + 1);
@@ -415,15 +416,13 @@ cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vert
   return cudaGetLastError();
 }
 
-cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
-                                   int sm_count, cudaStream_t stream) {
-  const DataDev& dd = args.dd;
-  const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
-  const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma);
+template <int TQ>
+static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n, int sm_count,
+                                   const TmaPlan& plan, cudaStream_t stream) {
   const size_t smem = plan.total;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -431,7 +430,7 @@ cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct,
   static int ctas_per_sm = 0;
   static size_t occ_smem = 0;
   if (occ_smem != smem) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma, 256, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ>, 256, smem);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
     occ_smem = smem;
@@ -440,8 +439,17 @@ cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct,
   const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
   if (grid > max_blocks) grid = max_blocks;
   if (grid == 0) return cudaSuccess;
-  k_interp_cell_tma<<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
+  k_interp_cell_tma<TQ><<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
   return cudaGetLastError();
+}
+
+cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
+                                   int sm_count, cudaStream_t stream, int tile) {
+  const DataDev& dd = args.dd;
+  const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
+  const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma);
+  if (tile == 2) return launch_tma_tile<2>(args, ct, table, n, sm_count, plan, stream);
+  return launch_tma_tile<4>(args, ct, table, n, sm_count, plan, stream);
 }
 
 #undef LOAD_ITEM

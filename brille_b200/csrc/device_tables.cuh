@@ -235,7 +235,7 @@ CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_t
 cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vertices, const uint32_t* tet_vertices,
                                     const CellTableDev& ct, unsigned char* table, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
-                                   int sm_count, cudaStream_t stream);
+                                   int sm_count, cudaStream_t stream, int tile);
 
 // device work space of sort() (sortpairs.cu), kept by the grid between calls
 struct SortWorkspace {

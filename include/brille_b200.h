@@ -264,7 +264,8 @@ double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
  * allows it; "chunk" points per CTA work item of the cell-batched kernel (default 256, reduced automatically
  * when many atoms/modes would not fit shared memory); "cell_kernel" 0 auto | 1 cell kernel that stages and phase-aligns
  * the vertex rows on the fly | 2 persistent pipelined cell kernel fed from the per-cell record table (built once per
- * fill; auto uses it whenever the table fits in a quarter of the free device memory); "host_chunk" upper bound on
+ * fill; auto uses it whenever the table fits in a quarter of the free device memory); "tile" points per register tile
+ * of the pipelined kernel (4: 124 registers, 2 CTAs/SM, default; 2: 80 registers, 3 CTAs/SM - measured slower); "host_chunk" upper bound on
  * the points per chunk of the host-buffer pipeline (0 = sized from free device memory)                          */
 int b200_grid_set_option(b200_grid_t* grid, const char* name, double value);
 /* output row sizes in bytes for one Q (values, vectors) and algorithmic HBM bytes per Q of the path          */
