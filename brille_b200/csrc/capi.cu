@@ -58,6 +58,11 @@ struct Workspace {
   uint32_t* rank = nullptr;
   uint32_t* cell_count = nullptr;
   BucketDev bk{};
+  // split trellis location: parked points, node buckets
+  ParkedPoint* parked = nullptr;
+  uint32_t* node_count = nullptr;
+  uint32_t n_nodes = 0;
+  BucketDev nbk{};
   std::vector<void*> ptrs;
   void release() {
     for (void* p : ptrs) cudaFree(p);
@@ -68,6 +73,10 @@ struct Workspace {
     tau = nullptr;
     key = rank = cell_count = nullptr;
     bk = BucketDev{};
+    parked = nullptr;
+    node_count = nullptr;
+    nbk = BucketDev{};
+    n_nodes = 0;
     n_buckets = chunk = sub = 0;
   }
   template <class T>
@@ -79,8 +88,8 @@ struct Workspace {
     return e;
   }
   uint32_t n_atoms_cap = 0;
-  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch, uint32_t n_atoms, uint32_t nsub) {
-    if (n <= capacity && nb == n_buckets && ch == chunk && n_atoms == n_atoms_cap && nsub == sub) return cudaSuccess;
+  cudaError_t ensure(size_t n, uint32_t nb, uint32_t ch, uint32_t n_atoms, uint32_t nsub, uint32_t nnodes) {
+    if (n <= capacity && nb == n_buckets && ch == chunk && n_atoms == n_atoms_cap && nsub == sub && nnodes == n_nodes) return cudaSuccess;
     n_atoms_cap = n_atoms;
     if (n < capacity) n = capacity;
     release();
@@ -108,6 +117,22 @@ struct Workspace {
     if ((e = get<uint32_t>(&bk.cell_start, nb)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.n_items, 4)) != cudaSuccess) return e;
     if ((e = get<CellItem>(&bk.items, (n + ch - 1) / ch + nb)) != cudaSuccess) return e;
+    if (nnodes) {  // node buckets of the split trellis location: bucket nnodes = "no node"
+      const uint32_t nnb = nnodes + 1;
+      if ((e = get<ParkedPoint>(&parked, n)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&node_count, nnb)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.cell_offset, (size_t)nnb + 1)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.cell_total, nnb)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.cell_start, nnb)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.n_items, 4)) != cudaSuccess) return e;
+      if ((e = get<CellItem>(&nbk.items, (size_t)nnb + 8)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.order, n)) != cudaSuccess) return e;
+      nbk.n_buckets = nnb;
+      nbk.sub = 1;
+      nbk.chunk = 1u << 30;  // at most one (unused) work item per node
+      nbk.cell_count = node_count;
+    }
+    n_nodes = nnodes;
     bk.n_buckets = nb;
     bk.sub = nsub;
     sub = nsub;
@@ -149,6 +174,7 @@ struct b200_grid {
   size_t host_chunk = 0;   // max points per chunk of the host-buffer pipeline (0 = sized from free memory)
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
+  int split_locate = 1;    // trellis: two-kernel location with the points regrouped by node in between
   int tile = 4;            // points per register tile of the pipelined cell kernel (4: 2 CTAs/SM, 2: 3 CTAs/SM)
   int cell_kernel = 0;     // 0 auto (pipelined kernel when its cell table fits), 1 on-the-fly staging kernel, 2 pipelined only
   unsigned char* cell_table = nullptr;  // pre-aligned per-cell records (cellinterp_tma.cu), built lazily per fill
@@ -652,7 +678,7 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
-                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call) {
+                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call, bool want_probe) {
   const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
@@ -695,7 +721,10 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     }
   }
   const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
-  CU(ws.ensure(n, nb, chunk, 0u, nsub));
+  // two-kernel trellis location (points regrouped by node between the halves): pays off once the nodes hold a few points each
+  const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : 0u;
+  const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
+  CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes : ws.n_nodes));
   CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
@@ -708,11 +737,22 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     CU(cudaMemsetAsync(ws.cell_count, 0, (size_t)nb * nsub * sizeof(uint32_t), stream));
   }
   if (g->timing) cudaEventRecord(g->ev[0], stream);
-  CU(launch_locate(g->d_bz, g->gd, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
-  g->launches += 1;
+  if (split) {
+    lo.parked = ws.parked;
+    lo.lean = want_probe ? 0 : 1;
+    lo.node_count = ws.node_count;
+    CU(cudaMemsetAsync(ws.node_count, 0, ((size_t)n_nodes + 1) * sizeof(uint32_t), stream));
+    CU(launch_locate(g->d_bz, g->gd, dQ, n, mode | MODE_SPLIT_A, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
+    CU(launch_bucket_sort(ws.nbk, ws.key, ws.rank, n, g->sm_count, stream));
+    CU(launch_locate_in_node(g->d_bz, g->gd, n, mode, lo, ws.nbk.order, d_fail, g->sm_count, stream));
+    g->launches += 6;
+  } else {
+    CU(launch_locate(g->d_bz, g->gd, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
+    g->launches += 1;
+  }
   if (g->timing) cudaEventRecord(g->ev[1], stream);
   if (interp && cell) {
-    CU(launch_bucket_sort(ws.bk, ws.key, ws.rank, n, g->sm_count, stream));
+    CU(launch_bucket_sort(ws.bk, ws.key, ws.rank, n, g->sm_count, stream, split ? ws.nbk.order : nullptr));
     g->launches += 4;
     if (g->timing) cudaEventRecord(g->ev[2], stream);
     CellArgs a{};
@@ -778,7 +818,7 @@ static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_
   if (g->timing) g->kernel_ms.clear();
   uint32_t mode = (flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u;
   if (ir) mode |= MODE_IR;
-  rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, ir, static_cast<double*>(dvals), static_cast<double*>(dvecs), stream, nQ);
+  rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, ir, static_cast<double*>(dvals), static_cast<double*>(dvecs), stream, nQ, dprobe != nullptr);
   if (rc) return rc;
   if (dprobe) {
     const LocateOut& lo = g->ws.lo;
@@ -847,7 +887,7 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
     }
     CU(cudaMemcpyAsync(h.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h.stream));
-    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ);
+    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ, probe != nullptr);
     if (rc) return rc;
     if (interp) {
       CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
@@ -964,6 +1004,8 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   if (n == "interp_path") {
     if (value < 0 || value > 2) return fail(B200_E_INVALID, "interp_path must be 0 (auto), 1 (general) or 2 (cell-batched)");
     g->interp_path = (int)value;
+  } else if (n == "split_locate") {
+    g->split_locate = value != 0;
   } else if (n == "tile") {
     if (value != 2 && value != 4) return fail(B200_E_INVALID, "tile must be 2 or 4");
     g->tile = (int)value;

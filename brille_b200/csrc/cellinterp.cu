@@ -44,14 +44,30 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
     const uint32_t i = base + tid;
     const uint32_t c = i < nb ? b.cell_total[i] : 0u;
     const uint32_t it = (i < last) ? (c + b.chunk - 1) / b.chunk : 0u;  // the last bucket produces no cell items
-    s_pts[tid] = c;
-    s_its[tid] = it;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-      uint32_t a = tid >= off ? s_pts[tid - off] : 0u, d = tid >= off ? s_its[tid - off] : 0u;
+    {  // inclusive scan of (c, it) over the 1024 threads: within warps by shuffles, then over the 32 warp totals
+      uint32_t xc = c, xi = it;
+      const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yc = __shfl_up_sync(0xffffffffu, xc, o), yi = __shfl_up_sync(0xffffffffu, xi, o);
+        if (lane >= o) { xc += yc; xi += yi; }
+      }
+      __shared__ uint32_t w_pts[32], w_its[32];
+      if (lane == 31) { w_pts[w] = xc; w_its[w] = xi; }
       __syncthreads();
-      s_pts[tid] += a;
-      s_its[tid] += d;
+      if (w == 0) {
+        uint32_t tc = w_pts[lane], ti = w_its[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t yc = __shfl_up_sync(0xffffffffu, tc, o), yi = __shfl_up_sync(0xffffffffu, ti, o);
+          if (lane >= o) { tc += yc; ti += yi; }
+        }
+        w_pts[lane] = tc;
+        w_its[lane] = ti;
+      }
+      __syncthreads();
+      s_pts[tid] = xc + (w ? w_pts[w - 1] : 0u);
+      s_its[tid] = xi + (w ? w_its[w - 1] : 0u);
       __syncthreads();
     }
     const uint32_t p0 = carry_pts + s_pts[tid] - c, i0 = carry_its + s_its[tid] - it;
@@ -96,9 +112,10 @@ __global__ void __launch_bounds__(256) k_bucket_suboffsets(BucketDev b) {
 // per-point records themselves are gathered by the cell kernel, early enough to be hidden behind the cell staging.
 __global__ void __launch_bounds__(256)
 k_bucket_scatter(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_offset,
-                 uint32_t* __restrict__ order, size_t n) {
+                 uint32_t* __restrict__ order, size_t n, const uint32_t* __restrict__ index) {
+  // entry i of key/rank describes point index[i] (or i itself)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    order[cell_offset[key[i]] + rank[i]] = (uint32_t)i;
+    order[cell_offset[key[i]] + rank[i]] = index ? index[i] : (uint32_t)i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -316,13 +333,13 @@ uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, 
 }
 
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, const uint32_t* index) {
   const unsigned cell_blocks = (bk.n_buckets + 255) / 256;
   k_bucket_totals<<<cell_blocks, 256, 0, stream>>>(bk);
   k_bucket_scan<<<1, 1024, 0, stream>>>(bk);
   k_bucket_suboffsets<<<cell_blocks, 256, 0, stream>>>(bk);
   size_t want = (n + 255) / 256, cap = (size_t)sm_count * 16;
-  k_bucket_scatter<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(key, rank, bk.cell_offset, bk.order, n);
+  k_bucket_scatter<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(key, rank, bk.cell_offset, bk.order, n, index);
   return cudaGetLastError();
 }
 

@@ -106,6 +106,14 @@ struct GridDev {
 // kernel fetches it with one bulk copy per point.
 constexpr uint32_t REC_DOUBLES = 12, REC_BYTES = 96;
 
+// A point parked between the two kernels of the split trellis location: what the second kernel needs, one 32-byte sector
+// (the first kernel already wrote the q_ir / rotation / index part of the point's record).
+struct ParkedPoint {
+  double x[3];
+  uint32_t rot_st;  // ridx | invridx << 8 | status << 16
+  uint32_t cell;
+};
+
 // per-Q result of the locate stage, consumed by the interpolation stage (SoA, all device pointers)
 struct LocateOut {
   double* q_ir;      // (n,3)
@@ -126,6 +134,10 @@ struct LocateOut {
                          //     generic cell (some weight ~ 0, failed points)
   uint32_t* rank;        // (n) arrival order of the point inside its sub-bucket
   uint32_t* cell_count;  // ((n_cubes + n_tets + 1) * sub) sub-bucket populations, zeroed before the launch
+  // split trellis location (MODE_SPLIT_A): parked points and their node buckets (key/rank double as node bucket/rank)
+  ParkedPoint* parked;   // (n)
+  int lean;              // second kernel: points of a cell bucket write only their record (no probe was asked for)
+  uint32_t* node_count;  // (n_nodes + 1), zeroed before the launch; bucket n_nodes = no node found
   uint32_t sub;          // sub-buckets per bucket = number of point group operations: the sort is by (cell, operation), so
                          //     that consecutive points of a cell share the rotation matrix
 };
@@ -217,18 +229,22 @@ struct CellTableDev {
 constexpr uint32_t MODE_NO_MOVE = 1u;    // skip moveinto/ir_moveinto (do_not_move_points)
 constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather than moveinto
 constexpr uint32_t MODE_NO_LOCATE = 4u;  // moveinto only (b200_moveinto)
+constexpr uint32_t MODE_SPLIT_A = 8u;    // trellis: stop after the node is found and park the point (two-kernel location)
+
 
 // launchers (one per .cu file)
 cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
                           double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
                           cudaStream_t stream);
+cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n, uint32_t mode, const LocateOut& out, const uint32_t* order,
+                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
                           cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
 bool cell_path_eligible(const DataDev& dd);
 uint32_t cell_modes_per_pass(const DataDev& dd, bool has_cubes, uint32_t chunk, size_t budget);
 uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
-                               cudaStream_t stream);
+                               cudaStream_t stream, const uint32_t* index = nullptr);
 cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
 uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
 CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_tets, uint32_t mpp);

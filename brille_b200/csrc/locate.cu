@@ -253,12 +253,10 @@ __device__ __noinline__ void emit_compact(EmitOut& e, const uint32_t* vi, const 
   }
 }
 
-__device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const TrellisDev& t, const double* knots, const double* x,
-                                                   EmitOut& e, uint32_t& cell, int& tet) {
+// part 1 of the trellis location: the node of x (bins + neighbour search, trellis_poly.hpp:67-81,382-424)
+__device__ __forceinline__ uint32_t trellis_find_node(const BZDev& bz, const TrellisDev& t, const double* knots, const double* x,
+                                                      uint32_t& cell) {
   uint32_t st = 0;
-  e.n = 0;
-  e.slots = 0;
-  tet = -1;
   cell = 0xffffffffu;
   int sub[3];
   for (int d = 0; d < 3; ++d) sub[d] = find_bin(knots + t.knot_offset[d], t.n_knots[d], x[d]);
@@ -296,6 +294,16 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   }
   const int n0 = t.n_knots[0] - 1, n1 = t.n_knots[1] - 1;
   cell = (uint32_t)(sub[0] + n0 * (sub[1] + n1 * sub[2]));
+  return st;
+}
+
+// part 2: vertices and weights of x inside node `cell` (trellis_node.hpp:130-149,273-364)
+__device__ __forceinline__ uint32_t trellis_in_node(const BZDev& bz, const TrellisDev& t, const double* x, uint32_t cell, EmitOut& e,
+                                                    int& tet) {
+  uint32_t st = 0;
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
   const uint32_t payload = t.node_index[cell];
   uint4* vo = reinterpret_cast<uint4*>(e.v);
   double2* wo = reinterpret_cast<double2*>(e.w);
@@ -408,6 +416,16 @@ __device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const Trelli
   }
   if (e.n < 1) st |= B200_ST_NOT_FOUND;
   return st;
+}
+
+__device__ __forceinline__ uint32_t trellis_locate(const BZDev& bz, const TrellisDev& t, const double* knots, const double* x,
+                                                   EmitOut& e, uint32_t& cell, int& tet) {
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  const uint32_t st = trellis_find_node(bz, t, knots, x, cell);
+  if (st & B200_ST_NOT_FOUND) return st;
+  return st | trellis_in_node(bz, t, x, cell, e, tet);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -658,7 +676,8 @@ __device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, i
   return false;
 }
 
-template <int KIND>
+// SPLIT (trellis only): the kernel stops after the node is found and parks the point for k_locate_in_node
+template <int KIND, bool SPLIT = false>
 __global__ void __launch_bounds__(128)
 k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q, size_t n, uint32_t mode,
          double eps_w, double eps_o, LocateOut out, unsigned long long* __restrict__ fail_count) {
@@ -729,7 +748,27 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     out.invridx[i] = invridx;
     uint32_t cell = 0xffffffffu;
     int tet = -1, n_emit = 0;
-    if (!(mode & MODE_NO_LOCATE)) {
+    if (KIND == B200_GRID_TRELLIS && SPLIT) {
+      // two-kernel location: find the node, park the point, count it in its node's bucket; k_locate_in_node finishes it
+      st |= trellis_find_node(bz, tr, knots, x, cell);
+      ParkedPoint pp;
+      pp.x[0] = x[0]; pp.x[1] = x[1]; pp.x[2] = x[2];
+      pp.rot_st = (uint32_t)ridx | ((uint32_t)invridx << 8) | (st << 16);
+      pp.cell = cell;
+      const double2* src = reinterpret_cast<const double2*>(&pp);
+      double2* dst = reinterpret_cast<double2*>(out.parked + i);
+      dst[0] = src[0]; dst[1] = src[1];
+      {  // third sector of the point's record (device_tables.cuh): q_ir, rotation indices, point index
+        double2* rec = reinterpret_cast<double2*>(out.weight + REC_DOUBLES * i);
+        rec[4] = make_double2(q[0], q[1]);
+        rec[5] = make_double2(q[2], __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
+      }
+      const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? tr.n_nodes : cell;
+      out.key[i] = bucket;
+      out.rank[i] = atomicAdd(out.node_count + bucket, 1u);
+      continue;
+    }
+    if (!SPLIT && !(mode & MODE_NO_LOCATE)) {
       EmitOut e;
       e.v = out.vertex + 8 * i;
       e.w = out.weight + REC_DOUBLES * i;
@@ -776,13 +815,119 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
   if (f_find) atomicAdd(fail_count + 2, f_find);
 }
 
+// Second kernel of the split trellis location: the points arrive sorted by node, so the lanes of a warp work in the same
+// node -- same branch (cube / triangulated), same tetrahedra, same trip counts, loads that broadcast.  Same arithmetic and
+// the same outputs as the tail of k_locate.
+__global__ void __launch_bounds__(128, 5)
+k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t mode, LocateOut out, const uint32_t* __restrict__ order,
+                 unsigned long long* __restrict__ fail_count) {
+  const TrellisDev& tr = gd.tr;
+  const BZDev& bz = *bzg;  // only the default tolerance pair is read
+  unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
+  // software pipeline over the grid-stride loop: the sort order is loaded two trips ahead and the parked point one trip
+  // ahead, so that neither of the two dependent gathers is waited for
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i_cur = p < n ? order[p] : 0u, i_nxt = p + stride < n ? order[p + stride] : 0u;
+  double2 pa = make_double2(0.0, 0.0), pb = pa;
+  if (p < n) {
+    const double2* src = reinterpret_cast<const double2*>(out.parked + i_cur);
+    pa = src[0];
+    pb = src[1];
+  }
+  for (; p < n; p += stride) {
+    const uint32_t i_nn = p + 2 * stride < n ? order[p + 2 * stride] : 0u;
+    double2 na = make_double2(0.0, 0.0), nb = na;
+    if (p + stride < n) {
+      const double2* src = reinterpret_cast<const double2*>(out.parked + i_nxt);
+      na = src[0];
+      nb = src[1];
+    }
+    const size_t i = i_cur;
+    ParkedPoint pp;
+    pp.x[0] = pa.x; pp.x[1] = pa.y; pp.x[2] = pb.x;
+    pp.rot_st = (uint32_t)__double2loint(pb.y);
+    pp.cell = (uint32_t)__double2hiint(pb.y);
+    i_cur = i_nxt;
+    i_nxt = i_nn;
+    pa = na;
+    pb = nb;
+    uint32_t st = pp.rot_st >> 16;
+    const uint32_t cell = pp.cell;
+    const int invridx = (int)((pp.rot_st >> 8) & 0xffu);
+    int tet = -1;
+    __align__(16) uint32_t vtmp[8];  // the vertex list goes to memory only if somebody reads it (probe, general kernel)
+    EmitOut e;
+    e.v = out.lean ? vtmp : out.vertex + 8 * i;
+    e.w = out.weight + REC_DOUBLES * i;
+    e.n = 0;
+    e.slots = 0;
+    if (!(st & B200_ST_NOT_FOUND)) st |= trellis_in_node(bz, tr, pp.x, cell, e, tet);
+    if (e.n == 0) {  // not found: defined contents for the row
+      for (int j = 0; j < 8; ++j) {
+        e.v[j] = 0xffffffffu;
+        e.w[j] = 0.0;
+      }
+    }
+    const int n_emit = e.n;
+    const uint32_t general = gd.cells.n_cubes + gd.cells.n_tets;
+    uint32_t key = general;
+    if (!(st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND))) {
+      if (tet >= 0 && n_emit == 4) key = gd.cells.n_cubes + (uint32_t)tet;
+      else if (tet < 0 && n_emit == 8) key = gd.cells.node_index[cell];
+    }
+    const bool in_cell_bucket = key != general;
+    key = key * out.sub + (uint32_t)invridx;
+    {
+      // The points of a warp sit in the same node: many share the sub-bucket.  One atomicAdd per distinct key of the warp
+      // (the leader adds the group's population, the members take consecutive ranks) instead of 32 on the same address.
+      const unsigned active = __activemask();
+      const unsigned same = __match_any_sync(active, key);
+      const int leader = __ffs(same) - 1;
+      const unsigned lane = threadIdx.x & 31u;
+      uint32_t first = 0;
+      if ((int)lane == leader) first = atomicAdd(out.cell_count + key, (uint32_t)__popc(same));
+      first = __shfl_sync(same, first, leader);
+      out.key[p] = key;  // (sorted position, coalesced; the scatter goes through `order`)
+      out.rank[p] = first + (uint32_t)__popc(same & ((1u << lane) - 1u));
+    }
+    if (!(out.lean && in_cell_bucket)) {  // per-point arrays only the probe and the general kernel read
+      if (out.lean) {
+        uint4* vo = reinterpret_cast<uint4*>(out.vertex + 8 * i);
+        vo[0] = make_uint4(vtmp[0], vtmp[1], vtmp[2], vtmp[3]);
+        vo[1] = make_uint4(vtmp[4], vtmp[5], vtmp[6], vtmp[7]);
+      }
+      out.cell[i] = cell;
+      out.tet[i] = tet;
+      out.n_vert[i] = n_emit;
+      out.slots[i] = e.slots;
+      out.status[i] = st;
+    }
+    (void)mode;
+    f_bz += (st & B200_ST_OUTSIDE_BZ) != 0;
+    f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
+    f_find += (st & B200_ST_NOT_FOUND) != 0;
+  }
+  if (f_bz) atomicAdd(fail_count + 0, f_bz);
+  if (f_wedge) atomicAdd(fail_count + 1, f_wedge);
+  if (f_find) atomicAdd(fail_count + 2, f_find);
+}
+
+cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n, uint32_t mode, const LocateOut& out, const uint32_t* order,
+                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const size_t want = (n + 127) / 128, cap = (size_t)sm_count * 32;
+  k_locate_in_node<<<(unsigned)(want < cap ? want : cap), 128, 0, stream>>>(bzg, gd, n, mode, out, order, fail_count);
+  return cudaGetLastError();
+}
+
 static size_t locate_smem_bytes(const GridDev& gd, uint32_t mode) {
   const TrellisDev& tr = gd.tr;
   size_t nk = (gd.kind != B200_GRID_TRELLIS || (mode & MODE_NO_LOCATE)) ? 0 : (size_t)(tr.n_knots[0] + tr.n_knots[1] + tr.n_knots[2]);
   return ((sizeof(BZDev) + 15) / 16) * 16 + nk * sizeof(double);
 }
 
-template <int KIND>
+template <int KIND, bool SPLIT>
 static cudaError_t launch_kind(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
                                double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
                                cudaStream_t stream) {
@@ -790,13 +935,13 @@ static cudaError_t launch_kind(const BZDev* bzg, const GridDev& gd, const double
   const size_t smem = locate_smem_bytes(gd, mode);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_locate<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_locate<KIND, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
   size_t want = (n + threads - 1) / threads;
   size_t cap = (size_t)sm_count * 16;  // grid-stride: a multiple of the SM count
   int blocks = (int)(want < cap ? want : cap);
-  k_locate<KIND><<<blocks, threads, smem, stream>>>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count);
+  k_locate<KIND, SPLIT><<<blocks, threads, smem, stream>>>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count);
   return cudaGetLastError();
 }
 
@@ -805,9 +950,11 @@ cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, 
                           cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   switch (gd.kind) {
-    case B200_GRID_TRELLIS: return launch_kind<B200_GRID_TRELLIS>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
-    case B200_GRID_NEST: return launch_kind<B200_GRID_NEST>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
-    default: return launch_kind<B200_GRID_MESH>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    case B200_GRID_TRELLIS:
+      if (mode & MODE_SPLIT_A) return launch_kind<B200_GRID_TRELLIS, true>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+      return launch_kind<B200_GRID_TRELLIS, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    case B200_GRID_NEST: return launch_kind<B200_GRID_NEST, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    default: return launch_kind<B200_GRID_MESH, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
   }
 }
 
