@@ -115,8 +115,10 @@ struct Workspace {
     if ((e = get<uint32_t>(&bk.cell_offset, (size_t)nb * nsub + 1)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.cell_total, nb)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.cell_start, nb)) != cudaSuccess) return e;
+    if ((e = get<uint32_t>(&bk.item_start, nb)) != cudaSuccess) return e;
     if ((e = get<uint32_t>(&bk.n_items, 4)) != cudaSuccess) return e;
     if ((e = get<CellItem>(&bk.items, (n + ch - 1) / ch + nb)) != cudaSuccess) return e;
+    bk.max_items = (uint32_t)((n + ch - 1) / ch + nb);
     if (nnodes) {  // node buckets of the split trellis location: bucket nnodes = "no node"
       const uint32_t nnb = nnodes + 1;
       if ((e = get<ParkedPoint>(&parked, n)) != cudaSuccess) return e;
@@ -124,8 +126,9 @@ struct Workspace {
       if ((e = get<uint32_t>(&nbk.cell_offset, (size_t)nnb + 1)) != cudaSuccess) return e;
       if ((e = get<uint32_t>(&nbk.cell_total, nnb)) != cudaSuccess) return e;
       if ((e = get<uint32_t>(&nbk.cell_start, nnb)) != cudaSuccess) return e;
+      if ((e = get<uint32_t>(&nbk.item_start, nnb)) != cudaSuccess) return e;
+      nbk.max_items = 0;
       if ((e = get<uint32_t>(&nbk.n_items, 4)) != cudaSuccess) return e;
-      if ((e = get<CellItem>(&nbk.items, (size_t)nnb + 8)) != cudaSuccess) return e;
       if ((e = get<uint32_t>(&nbk.order, n)) != cudaSuccess) return e;
       nbk.n_buckets = nnb;
       nbk.sub = 1;
@@ -753,7 +756,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   if (g->timing) cudaEventRecord(g->ev[1], stream);
   if (interp && cell) {
     CU(launch_bucket_sort(ws.bk, ws.key, ws.rank, n, g->sm_count, stream, split ? ws.nbk.order : nullptr));
-    g->launches += 4;
+    g->launches += 5;
     if (g->timing) cudaEventRecord(g->ev[2], stream);
     CellArgs a{};
     a.dd = g->dd;

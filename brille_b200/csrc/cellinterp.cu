@@ -73,13 +73,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
     const uint32_t p0 = carry_pts + s_pts[tid] - c, i0 = carry_its + s_its[tid] - it;
     if (i < nb) {
       b.cell_start[i] = p0;
-      for (uint32_t k = 0; k < it; ++k) {
-        CellItem ci;
-        ci.key = i;
-        ci.start = p0 + k * b.chunk;
-        ci.len = min(b.chunk, c - k * b.chunk);
-        b.items[i0 + k] = ci;
-      }
+      b.item_start[i] = i0;  // the work items themselves are written by k_bucket_items, one thread each
       if (i == last) {
         b.n_items[1] = p0;
         b.n_items[2] = c;
@@ -95,7 +89,25 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(BucketDev b) {
   if (tid == 0) b.n_items[0] = carry_its;
 }
 
-// part 2c: first position of every sub-bucket
+// part 2c: the work items (cell, <= chunk points), one thread per item: its cell is the last one whose first item index is
+// not beyond the item (binary search in the exclusive scan of the item counts; empty cells share the index of their successor)
+__global__ void __launch_bounds__(256) k_bucket_items(BucketDev b) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= b.n_items[0]) return;
+  uint32_t lo = 0, hi = b.n_buckets - 1;  // the last bucket has no items: search [0, n_buckets - 1)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (b.item_start[mid] <= k) lo = mid; else hi = mid;
+  }
+  const uint32_t j = k - b.item_start[lo], c = b.cell_total[lo];
+  CellItem ci;
+  ci.key = lo;
+  ci.start = b.cell_start[lo] + j * b.chunk;
+  ci.len = min(b.chunk, c - j * b.chunk);
+  b.items[k] = ci;
+}
+
+// part 2d: first position of every sub-bucket
 __global__ void __launch_bounds__(256) k_bucket_suboffsets(BucketDev b) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b.n_buckets) return;
@@ -337,6 +349,7 @@ cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const u
   const unsigned cell_blocks = (bk.n_buckets + 255) / 256;
   k_bucket_totals<<<cell_blocks, 256, 0, stream>>>(bk);
   k_bucket_scan<<<1, 1024, 0, stream>>>(bk);
+  if (bk.max_items) k_bucket_items<<<(bk.max_items + 255) / 256, 256, 0, stream>>>(bk);
   k_bucket_suboffsets<<<cell_blocks, 256, 0, stream>>>(bk);
   size_t want = (n + 255) / 256, cap = (size_t)sm_count * 16;
   k_bucket_scatter<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(key, rank, bk.cell_offset, bk.order, n, index);

@@ -196,6 +196,8 @@ struct BucketDev {
   uint32_t* cell_offset;       // (n_buckets * sub) exclusive scan of cell_count: first position of every sub-bucket
   uint32_t* cell_total;        // (n_buckets) bucket populations
   uint32_t* cell_start;        // (n_buckets) first position of every bucket
+  uint32_t* item_start;        // (n_buckets) index of the first work item of every bucket
+  uint32_t max_items;          // capacity of `items` (0: no work items wanted, e.g. the node buckets of the split location)
   CellItem* items;             // (max_items)
   uint32_t* n_items;           // [0] number of items, [1] start of the last (general) bucket, [2] its population
   uint32_t* order;             // (n) point indices in bucket order
