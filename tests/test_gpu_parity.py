@@ -378,3 +378,23 @@ def test_device_sort_cost_functions_and_errors(host, bridge):
     gd = brille_b200.B200Grid(None, structure=s, data=d)
     with pytest.raises(RuntimeError, match="real-valued"):
         gd.sort_pairs(np.array([[0, 1]], dtype=np.uint32), plan)
+
+
+@pytest.mark.parametrize("which", ["C2", "C3"])
+def test_two_kernel_location_is_bit_invisible(host, which):
+    """The trellis location in two kernels (points regrouped by node in between) and in one kernel: same decisions, same
+    weights, same results, bit for bit -- with and without the probe (the probe switches the lean outputs off)."""
+    wl = W.c2_nacl(host, density=300) if which == "C2" else W.c3_p63mmc(host, density=300, seed=5)
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(300000, 41)
+    Q[:10] = 0.0  # the zone centre sits on node corners: neighbour search, compact emission, general kernel
+    out = {}
+    for split in (0, 1):
+        g.set_option("split_locate", split)
+        out[split] = g.ir_interpolate_at(Q, probe=True) + g.ir_interpolate_at(Q)
+    a, b = out[0], out[1]
+    for k in (0, 1, 3, 4):
+        assert np.array_equal(a[k], b[k])
+    for name in ("tau", "q_ir", "ridx", "invridx", "cell", "tet", "n_vert", "vertex", "weight", "status"):
+        assert np.array_equal(getattr(a[2], name), getattr(b[2], name)), name
+    g.close()
