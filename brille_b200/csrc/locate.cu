@@ -236,6 +236,12 @@ struct EmitOut {
   int n;
 };
 
+// 32 bytes to a 32-byte aligned GLOBAL address with one store: the sector is written whole, so L2 never has to fetch it to
+// merge a partial write (four 16-byte stores per weight row cost a 64-byte read per point)
+__device__ __forceinline__ void st32(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __noinline__ void emit_compact(EmitOut& e, const uint32_t* vi, const double* w, const bool* keep, int count, bool cube) {
   e.n = 0;
   e.slots = 0;
@@ -306,7 +312,6 @@ __device__ __forceinline__ uint32_t trellis_in_node(const BZDev& bz, const Trell
   tet = -1;
   const uint32_t payload = t.node_index[cell];
   uint4* vo = reinterpret_cast<uint4*>(e.v);
-  double2* wo = reinterpret_cast<double2*>(e.w);
   if (t.node_type[cell] == B200_NODE_CUBE) {
     // CubeNode::indices_weights (trellis_node.hpp:130-149)
     const double2* cp = reinterpret_cast<const double2*>(t.cube_pack + 24 * (size_t)payload);
@@ -333,7 +338,8 @@ __device__ __forceinline__ uint32_t trellis_in_node(const BZDev& bz, const Trell
       vo[0] = make_uint4(vb.w, vb.z, vb.y, vb.x);  // vertex_indices[7], [6], [5], [4]
       vo[1] = make_uint4(va.w, va.z, va.y, va.x);  // vertex_indices[3], [2], [1], [0]
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wo[j] = make_double2(w[2 * j], w[2 * j + 1]);
+      st32(e.w, w[0], w[1], w[2], w[3]);
+      st32(e.w + 4, w[4], w[5], w[6], w[7]);
       e.n = 8;
       e.slots = 0x0001020304050607ull;  // byte j = 7 - j
     } else {
@@ -403,10 +409,8 @@ __device__ __forceinline__ uint32_t trellis_in_node(const BZDev& bz, const Trell
     if (all) {
       vo[0] = vi4;
       vo[1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      wo[0] = make_double2(w[0], w[1]);
-      wo[1] = make_double2(w[2], w[3]);
-      wo[2] = make_double2(0.0, 0.0);
-      wo[3] = make_double2(0.0, 0.0);
+      st32(e.w, w[0], w[1], w[2], w[3]);
+      st32(e.w + 4, 0.0, 0.0, 0.0, 0.0);
       e.n = 4;
       e.slots = 0x03020100ull;
     } else {
@@ -499,11 +503,8 @@ __device__ __forceinline__ void emit_tet(EmitOut& e, const uint32_t* vip, const 
   if (all) {
     reinterpret_cast<uint4*>(e.v)[0] = vi4;
     reinterpret_cast<uint4*>(e.v)[1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    double2* wo = reinterpret_cast<double2*>(e.w);
-    wo[0] = make_double2(w[0], w[1]);
-    wo[1] = make_double2(w[2], w[3]);
-    wo[2] = make_double2(0.0, 0.0);
-    wo[3] = make_double2(0.0, 0.0);
+    st32(e.w, w[0], w[1], w[2], w[3]);
+    st32(e.w + 4, 0.0, 0.0, 0.0, 0.0);
     e.n = 4;
     e.slots = 0x03020100ull;
   } else {
@@ -755,14 +756,10 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       pp.x[0] = x[0]; pp.x[1] = x[1]; pp.x[2] = x[2];
       pp.rot_st = (uint32_t)ridx | ((uint32_t)invridx << 8) | (st << 16);
       pp.cell = cell;
-      const double2* src = reinterpret_cast<const double2*>(&pp);
-      double2* dst = reinterpret_cast<double2*>(out.parked + i);
-      dst[0] = src[0]; dst[1] = src[1];
-      {  // third sector of the point's record (device_tables.cuh): q_ir, rotation indices, point index
-        double2* rec = reinterpret_cast<double2*>(out.weight + REC_DOUBLES * i);
-        rec[4] = make_double2(q[0], q[1]);
-        rec[5] = make_double2(q[2], __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
-      }
+      st32(reinterpret_cast<double*>(out.parked + i), pp.x[0], pp.x[1], pp.x[2], __hiloint2double((int)pp.cell, (int)pp.rot_st));
+      // third sector of the point's record (device_tables.cuh): q_ir, rotation indices, point index
+      st32(out.weight + REC_DOUBLES * i + 8, q[0], q[1], q[2],
+           __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
       const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? tr.n_nodes : cell;
       out.key[i] = bucket;
       out.rank[i] = atomicAdd(out.node_count + bucket, 1u);
@@ -788,11 +785,9 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       out.slots[i] = e.slots;
     }
     out.status[i] = st;
-    {  // the rest of the point's record (device_tables.cuh): q_ir, rotation indices, point index
-      double2* rec = reinterpret_cast<double2*>(out.weight + REC_DOUBLES * i);
-      rec[4] = make_double2(q[0], q[1]);
-      rec[5] = make_double2(q[2], __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
-    }
+    // the rest of the point's record (device_tables.cuh): q_ir, rotation indices, point index
+    st32(out.weight + REC_DOUBLES * i + 8, q[0], q[1], q[2],
+         __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
     if (out.key) {
       // bucket for the cell-batched interpolation: only "generic" points (every corner of the cell carries weight, i.e.
       // the pivot is the cell's first emitted corner) share a bucket with their cell
