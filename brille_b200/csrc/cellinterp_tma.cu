@@ -150,7 +150,7 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t NO_ITEM = 0xffffffffu;
-constexpr uint32_t ITEM_BLOCK = 4;
+constexpr uint32_t ITEM_BLOCK = 8;
 
 template <int TQ>
 __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
