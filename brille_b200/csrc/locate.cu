@@ -695,6 +695,9 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
   }
   __syncthreads();
   unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
+  // (SPLIT) the rank returned by the bucket atomicAdd is stored one trip later, so that its latency overlaps the next point
+  uint32_t pending_rank = 0;
+  uint32_t* pending_at = nullptr;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double Qi[3] = {Q[3 * i], Q[3 * i + 1], Q[3 * i + 2]};
     double q[3];
@@ -762,7 +765,9 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
            __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
       const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? tr.n_nodes : cell;
       out.key[i] = bucket;
-      out.rank[i] = atomicAdd(out.node_count + bucket, 1u);
+      if (pending_at) *pending_at = pending_rank;
+      pending_rank = atomicAdd(out.node_count + bucket, 1u);
+      pending_at = out.rank + i;
       continue;
     }
     if (!SPLIT && !(mode & MODE_NO_LOCATE)) {
@@ -804,6 +809,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
     f_find += (st & B200_ST_NOT_FOUND) != 0;
   }
+  if (pending_at) *pending_at = pending_rank;
   // fail_count[0..2]: outside first zone / outside wedge / not found (all zero on the normal path)
   if (f_bz) atomicAdd(fail_count + 0, f_bz);
   if (f_wedge) atomicAdd(fail_count + 1, f_wedge);
