@@ -73,6 +73,23 @@ static void run_tma(const char* name, char* out, const uint32_t* rows, size_t n,
 }
 
 // ctas_per_sm < 8: occupancy is limited with dynamic shared memory, like the interpolation kernel (2 CTAs of 256 threads)
+// mode 5: like the interpolation kernel before the row-ownership fix: a row is written in two parts at different times by
+// different warps (pieces 0..31 by one warp, pieces 32..47 -- together with the first 16 of the next row -- by another)
+__global__ void k_store_split(char* out, size_t n, int delay) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * blockDim.x) >> 5;
+  // task t covers 32 consecutive 48-byte pieces of the concatenation of the (pseudo-randomly placed) rows
+  const size_t n_task = n * 48 / 32;
+  for (size_t t = warp; t < n_task; t += nwarp) {
+    const size_t tt = (t + (size_t)delay * nwarp * ((t & 1) ? 1 : 0)) % n_task;  // odd tasks run `delay` sweeps later
+    const size_t piece = tt * 32 + lane, r = piece / 48, k = piece - r * 48;
+    char* p = out + ((r * 7919003ull) % n) * ROW + k * 48;
+    const bool even = (k & 1) == 0;
+    st32(even ? p : p + 16, (double)r, 1.0);
+    st16(even ? p + 32 : p, (double)r, 1.0);
+  }
+}
+
 template <int MODE>
 static void run(const char* name, char* out, const uint32_t* rows, size_t n, int ctas_per_sm = 8) {
   cudaEvent_t e0, e1;
@@ -111,6 +128,17 @@ int main() {
       printf("-- arithmetic random rows (no index load)\n");
       for (int c : {8, 4, 2, 1}) run<3>("48-byte pieces, 32 B + 16 B", out, nullptr, n, c);
       for (int c : {8, 4, 2, 1}) run<0>("contiguous 512 B per instruction", out, nullptr, n, c);
+      for (int delay : {0, 1, 4}) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const size_t smem = 220 * 1024 / 2 - 2048;
+        cudaFuncSetAttribute(k_store_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_store_split<<<148 * 2, 256, smem>>>(out, n, delay);
+        cudaEventRecord(e0);
+        for (int it = 0; it < 5; ++it) k_store_split<<<148 * 2, 256, smem>>>(out, n, delay);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+        printf("rows split over two warps, second part %d sweeps later   %7.3f ms  %7.1f GB/s (2 CTAs/SM)\n", delay, ms, (double)n * ROW / ms * 1e-6);
+      }
     }
     run_tma("TMA bulk store 2304 B per row", out, rows, n, 1);
     run_tma("TMA bulk store 2304 B per row", out, rows, n, 2);
