@@ -398,3 +398,37 @@ def test_two_kernel_location_is_bit_invisible(host, which):
     for name in ("tau", "q_ir", "ridx", "invridx", "cell", "tet", "n_vert", "vertex", "weight", "status"):
         assert np.array_equal(getattr(a[2], name), getattr(b[2], name)), name
     g.close()
+
+
+def test_degenerate_point_sets(host, bridge):
+    """Point sets that stress the bucketing: all points identical (one node, one (cell, operation) bucket holds everything),
+    points on a line through the zone centre (node faces / edges: neighbour search, compact emission, general kernel), and a
+    call whose size sits just below / above the thresholds that switch the two-kernel location and the cell kernels on."""
+    wl = W.c3_p63mmc(host, density=300, seed=5)
+    g = brille_b200.accelerate(wl.grid)
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rng = np.random.default_rng(5)
+    one = np.tile(np.array([[0.137, 0.211, 0.303]]), (200_000, 1))
+    line = np.outer(np.linspace(-2.0, 2.0, 200_001), np.array([1.0, 0.0, 0.0]))
+    grid_pts = rng.integers(-8, 9, (100_000, 3)) / 8.0  # rational points: many sit exactly on cell faces
+    for name, Q in (("identical", one), ("line", line), ("rational", grid_pts)):
+        vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+        v2, w2 = g.ir_interpolate_at(Q)  # without the probe: lean outputs of the location
+        assert np.array_equal(vals, v2) and np.array_equal(vecs, w2), name
+        sel = np.unique(np.concatenate([np.arange(0, len(Q), max(1, len(Q) // 3000)), [len(Q) - 1]]))
+        rc, ov, ow, opr = orc.interpolate_at(Q[sel])
+        assert rc == 0, name
+        assert np.array_equal(pr.tau[sel], opr.tau) and np.array_equal(pr.ridx[sel], opr.ridx), name
+        assert np.array_equal(pr.vertex[sel], opr.vertex) and np.array_equal(pr.weight[sel], opr.weight), name
+        assert_values_close(vals[sel], ov)
+        assert_values_close(vecs[sel], ow)
+        if name == "identical":
+            assert (vals == vals[0]).all() and (vecs == vecs[0]).all()
+    # sizes around the switches (number of nodes / cells times a small factor)
+    base = wl.make_q(60_000, 9)
+    ref_v, ref_w = g.ir_interpolate_at(base)
+    for n in (1, 31, 257, 5_000, 20_001, 59_999):
+        v, w = g.ir_interpolate_at(base[:n])
+        # (the general and the cell-batched kernel agree to rounding, not bitwise)
+        assert rel_close(v, ref_v[:n]) <= 1e-12 and rel_close(w, ref_w[:n]) <= 1e-12, n
+    g.close()
