@@ -272,6 +272,50 @@ def run_ours(args):
     e2e_value = world * ne * args.steps / float(t.item())
     checksum = float(hv.array[:1000].sum())
 
+    # device-resident consumer: the same path followed by the structure-factor reduction on the device; the
+    # eigenvectors never leave HBM, 8*modes bytes per Q of |F|^2 go back instead of 16*modes*3*atoms.  Reported beside the
+    # headline numbers, not instead of them (different output).
+    consumer = None
+    if not args.no_consumer:
+        rng = np.random.default_rng(5)
+        grid.set_structure_factor(rng.normal(size=wl.n_atoms) + 1j * rng.normal(size=wl.n_atoms), positions=rng.uniform(0, 1, (wl.n_atoms, 3)),
+                                  q_transform=rng.normal(size=(3, 3)))
+        dsf = torch.empty((NQ, wl.modes), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            grid.ir_structure_factor_device(dQ, vals, dsf, scratch=vecs, check=False, stream=stream)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            grid.ir_structure_factor_device(dQ, vals, dsf, scratch=vecs, check=False, stream=stream)
+        e1.record(stream)
+        barrier()
+        c_ms = e0.elapsed_time(e1) / args.steps
+        grid.enable_timing(True)
+        grid.ir_structure_factor_device(dQ, vals, dsf, scratch=vecs, check=False, stream=stream)
+        c_kernel_ms = grid.kernel_ms("consumer")
+        grid.enable_timing(False)
+        hq2 = brille_b200.PinnedArray((NQ, 3), np.float64)
+        hv2 = brille_b200.PinnedArray((NQ, wl.modes, 1), np.float64)
+        hs2 = brille_b200.PinnedArray((NQ, wl.modes), np.float64)
+        hq2.array[:] = Q
+        grid.ir_structure_factor(hq2.array, out=(hv2.array, hs2.array))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            grid.ir_structure_factor(hq2.array, out=(hv2.array, hs2.array))
+        torch.cuda.synchronize(dev)
+        c_e2e_s = (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([c_ms, c_e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c_ms, c_e2e_s = float(t[0].item()), float(t[1].item())
+        consumer = {
+            "what": "ir_structure_factor: the path + |sum_k c_k e^{2 pi i Q.r_k} (TQ . eps_k^*)|^2 per (Q, mode) on the device",
+            "device_resident": {"value": world * NQ / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms, "consumer_kernel_ms": c_kernel_ms},
+            "e2e": {"value": world * NQ / c_e2e_s, "unit": UNIT, "q_per_step": NQ, "h2d_bytes_per_step": 24 * NQ,
+                    "d2h_bytes_per_step": (8 * wl.modes + 8 * wl.modes) * NQ, "checksum": float(hs2.array[:1000].sum())},
+        }
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -297,6 +341,7 @@ def run_ours(args):
                          "kernel_ms": int_ms, "locate_kernel_ms": loc_ms, "bucket_sort_ms": sort_ms,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},
             "cpu_baseline": cpu,
+            "consumer": consumer,
         }
         print(json.dumps(line))
     if world > 1:
@@ -313,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-consumer", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -18,6 +18,7 @@ SOURCES = {
     "interp.cu": [],
     "cellinterp.cu": [],
     "cellinterp_tma.cu": [],
+    "consumer.cu": [],
     "sortpairs.cu": ["-fmad=false"],  # cost matrices in the reference's rounding (x86-64 baseline: no fused multiply-add)
     "capi.cu": [],
 }

@@ -33,6 +33,9 @@ EXPORTS = (
     "b200_grid_row_bytes",
     "b200_grid_set_option",
     "b200_grid_sort_pairs",
+    "b200_grid_set_structure_factor",
+    "b200_ir_structure_factor",
+    "b200_ir_structure_factor_device",
 )
 
 
@@ -44,6 +47,19 @@ class SortConfig(C.Structure):
         ("vectors_costmult", C.c_double * 3),
         ("values_vector_cost", C.c_int32),
         ("vectors_vector_cost", C.c_int32),
+    ]
+
+
+class SFConfig(C.Structure):
+    """``b200_sf_config_t``"""
+
+    _fields_ = [
+        ("n_atoms", C.c_uint32),
+        ("coef", C.c_void_p),
+        ("positions", C.c_void_p),
+        ("debye_waller", C.c_void_p),
+        ("q_transform", C.c_double * 9),
+        ("conjugate", C.c_int32),
     ]
 
 
@@ -100,6 +116,12 @@ def lib():
     L.b200_grid_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.b200_grid_sort_pairs.restype = C.c_int
     L.b200_grid_sort_pairs.argtypes = [vp, vp, C.c_size_t, C.POINTER(SortConfig), vp, vp, vp]
+    L.b200_grid_set_structure_factor.restype = C.c_int
+    L.b200_grid_set_structure_factor.argtypes = [vp, C.POINTER(SFConfig)]
+    L.b200_ir_structure_factor.restype = C.c_int
+    L.b200_ir_structure_factor.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp]
+    L.b200_ir_structure_factor_device.restype = C.c_int
+    L.b200_ir_structure_factor_device.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
     L.b200_grid_row_bytes.restype = C.c_int
     L.b200_grid_row_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L

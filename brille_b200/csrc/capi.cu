@@ -10,6 +10,7 @@
 
 #include "brille_b200.h"
 #include "device_tables.cuh"
+#include "consumer.cuh"
 
 
 using namespace b200;
@@ -153,6 +154,7 @@ struct HostStage {  // device-side staging buffers of one pipeline slot of the h
   double* dQ = nullptr;
   double* dvals = nullptr;
   double* dvecs = nullptr;
+  double* dsf = nullptr;  // structure factor rows of the chunk (b200_ir_structure_factor)
   Workspace ws;
   unsigned long long* d_fail = nullptr;  // 3 counters
   unsigned long long* h_fail = nullptr;  // pinned mirror (keeps the D2H of the counters asynchronous)
@@ -184,9 +186,15 @@ struct b200_grid {
   CellTableDev ct{};
   bool cell_table_refused = false;      // did not fit: do not try again until the data changes
   SortWorkspace sort_ws;                // device work space of b200_grid_sort_pairs
+  // device-resident consumer (consumer.cu): configuration, and the eigenvector scratch of the device-buffer entry point
+  DevPool sf_pool;
+  SFDev sf{};
+  bool has_sf = false;
+  void* sf_scratch = nullptr;
+  size_t sf_scratch_bytes = 0;
   uint64_t launches = 0;
   bool timing = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
 };
 
@@ -549,7 +557,7 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
         cudaHostAlloc(&g->stage[s].h_fail, 3 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
       rc = fail(B200_E_CUDA, "stream/counter creation failed");
   }
-  for (int i = 0; i < 4 && rc == B200_OK; ++i)
+  for (int i = 0; i < 6 && rc == B200_OK; ++i)
     if (cudaEventCreate(&g->ev[i]) != cudaSuccess) rc = fail(B200_E_CUDA, "event creation failed");
   if (rc != B200_OK) {
     b200_grid_destroy(g);
@@ -568,6 +576,8 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
   drop_cell_table(g);
   g->sort_ws.release();
   g->ws.release();
+  g->sf_pool.release();
+  if (g->sf_scratch) cudaFree(g->sf_scratch);
   if (g->d_fail) cudaFree(g->d_fail);
   for (int s = 0; s < 2; ++s) {
     HostStage& h = g->stage[s];
@@ -575,11 +585,12 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
     if (h.dQ) cudaFree(h.dQ);
     if (h.dvals) cudaFree(h.dvals);
     if (h.dvecs) cudaFree(h.dvecs);
+    if (h.dsf) cudaFree(h.dsf);
     if (h.d_fail) cudaFree(h.d_fail);
     if (h.h_fail) cudaFreeHost(h.h_fail);
     if (h.stream) cudaStreamDestroy(h.stream);
   }
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;
 }
@@ -681,7 +692,8 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
-                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call, bool want_probe) {
+                   bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call, bool want_probe,
+                   bool reset_fail = true) {
   const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
@@ -728,7 +740,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : 0u;
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
   CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes : ws.n_nodes));
-  CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
+  if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
   lo.tau = ws.tau;
@@ -851,7 +863,7 @@ extern "C" int b200_ir_interpolate_at_device(b200_grid_t* g, const double* dQ, s
 // host-pointer pipeline: chunks alternate between two stages (stream + staging buffers) so that the H2D copy of
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i
 static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
-                         b200_probe_t* probe) {
+                         b200_probe_t* probe, double* sf_out = nullptr) {
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
   const size_t per_q = 24 + (interp ? g->vals_row_bytes + g->vecs_row_bytes : 0) + 200;
@@ -877,7 +889,8 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       if (h.dQ) cudaFree(h.dQ);
       if (h.dvals) cudaFree(h.dvals);
       if (h.dvecs) cudaFree(h.dvecs);
-      h.dQ = h.dvals = h.dvecs = nullptr;
+      if (h.dsf) cudaFree(h.dsf);
+      h.dQ = h.dvals = h.dvecs = h.dsf = nullptr;
       h.capacity = 0;
       CU(cudaMalloc(&h.dQ, n * 3 * sizeof(double)));
       if (interp) {
@@ -889,12 +902,20 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       CU(cudaMalloc(&h.dvals, std::max<size_t>(h.capacity * g->vals_row_bytes, 8)));
       CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
     }
+    const size_t sf_row = (size_t)g->dd.vectors.branches * sizeof(double);
+    if (sf_out && !h.dsf) CU(cudaMalloc(&h.dsf, std::max<size_t>(h.capacity * sf_row, 8)));
     CU(cudaMemcpyAsync(h.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h.stream));
     int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ, probe != nullptr);
     if (rc) return rc;
     if (interp) {
       CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
-      CU(cudaMemcpyAsync(static_cast<char*>(vecs) + lo * g->vecs_row_bytes, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+      if (sf_out) {  // the eigenvectors of the chunk are reduced where they are: only `modes` doubles per Q go back
+        CU(launch_structure_factor(g->sf, h.dQ, h.dvecs, n, g->dd.vectors.branches, h.dsf, g->sm_count, h.stream));
+        g->launches += 1;
+        CU(cudaMemcpyAsync(reinterpret_cast<char*>(sf_out) + lo * sf_row, h.dsf, n * sf_row, cudaMemcpyDeviceToHost, h.stream));
+      } else {
+        CU(cudaMemcpyAsync(static_cast<char*>(vecs) + lo * g->vecs_row_bytes, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+      }
     }
     if (probe) {
       const LocateOut& w = h.ws.lo;
@@ -946,6 +967,106 @@ extern "C" int b200_moveinto(b200_grid_t* g, const double* Q, size_t nQ, int ir,
   if (nQ && (!Q || !probe)) return fail(B200_E_INVALID, "NULL buffer");
   if (nQ == 0) return B200_OK;
   return host_pipeline(g, Q, nQ, MODE_NO_LOCATE | (ir ? MODE_IR : 0u), false, ir, nullptr, nullptr, probe);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// device-resident consumer: structure factor (consumer.cu)
+// ----------------------------------------------------------------------------------------------------
+extern "C" int b200_grid_set_structure_factor(b200_grid_t* g, const b200_sf_config_t* c) {
+  if (!g || !c) return fail(B200_E_INVALID, "NULL argument");
+  if (!c->n_atoms || !c->coef) return fail(B200_E_INVALID, "structure factor: n_atoms and coef are required");
+  CU(cudaSetDevice(g->device));
+  CU(cudaDeviceSynchronize());
+  g->sf_pool.release();
+  g->has_sf = false;
+  SFDev d{};
+  d.n_atoms = c->n_atoms;
+  CU(g->sf_pool.upload(c->coef, (size_t)c->n_atoms * 2, &d.coef));
+  if (c->positions) CU(g->sf_pool.upload(c->positions, (size_t)c->n_atoms * 3, &d.pos));
+  if (c->debye_waller) CU(g->sf_pool.upload(c->debye_waller, (size_t)c->n_atoms * 9, &d.dw));
+  for (int i = 0; i < 9; ++i) d.T[i] = c->q_transform[i];
+  d.conjugate = c->conjugate ? 1 : 0;
+  g->sf = d;
+  g->has_sf = true;
+  return B200_OK;
+}
+
+static int check_sf_ready(b200_grid* g) {
+  int rc = check_ready(g, true, 1);
+  if (rc) return rc;
+  if (!g->has_sf) return fail(B200_E_INVALID, "structure factor: call b200_grid_set_structure_factor first");
+  const InterpDev& v = g->dd.vectors;
+  if (!v.is_complex || v.no0 != 0 || v.no2 != 0 || v.no1 != g->sf.n_atoms)
+    return fail(B200_E_UNSUPPORTED, "structure factor: the eigenvector data must be complex 3-vectors, one per atom (" +
+                                        std::to_string(g->sf.n_atoms) + " atoms configured)");
+  return B200_OK;
+}
+
+extern "C" int b200_ir_structure_factor(b200_grid_t* g, const double* Q, size_t nQ, uint32_t flags, void* vals, double* sf_out) {
+  int rc = check_sf_ready(g);
+  if (rc) return rc;
+  if (nQ && (!Q || !vals || !sf_out)) return fail(B200_E_INVALID, "NULL buffer");
+  if (nQ == 0) return B200_OK;
+  uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
+  return host_pipeline(g, Q, nQ, mode, true, 1, vals, nullptr, nullptr, sf_out);
+}
+
+extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ, size_t nQ, uint32_t flags, void* dvals, double* dsf,
+                                               void* dscratch, void* stream_, uint64_t* n_failed) {
+  int rc = check_sf_ready(g);
+  if (rc) return rc;
+  if (nQ && (!dQ || !dvals || !dsf)) return fail(B200_E_INVALID, "NULL buffer");
+  if (n_failed) *n_failed = 0;
+  if (nQ == 0) return B200_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CU(cudaSetDevice(g->device));
+  if (g->timing) g->kernel_ms.clear();
+  size_t chunk = nQ;
+  char* scratch = static_cast<char*>(dscratch);
+  if (!scratch) {  // the library's own scratch: as many points as fit a third of the free memory (kept between calls)
+    const size_t want = nQ * g->vecs_row_bytes;
+    if (g->sf_scratch_bytes < want) {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      const size_t cap = std::max<size_t>((free_b + g->sf_scratch_bytes) / 3, g->vecs_row_bytes);
+      const size_t bytes = std::min(want, cap / g->vecs_row_bytes * g->vecs_row_bytes);
+      if (bytes > g->sf_scratch_bytes) {
+        CU(cudaStreamSynchronize(stream));
+        if (g->sf_scratch) cudaFree(g->sf_scratch);
+        g->sf_scratch = nullptr;
+        g->sf_scratch_bytes = 0;
+        CU(cudaMalloc(&g->sf_scratch, bytes));
+        g->sf_scratch_bytes = bytes;
+      }
+    }
+    scratch = static_cast<char*>(g->sf_scratch);
+    chunk = std::min(nQ, g->sf_scratch_bytes / g->vecs_row_bytes);
+  }
+  uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
+  const size_t M = g->dd.vectors.branches;
+  for (size_t lo = 0; lo < nQ; lo += chunk) {
+    const size_t n = std::min(chunk, nQ - lo);
+    // (the failure counters accumulate over the chunks of a call)
+    rc = enqueue(g, g->ws, g->d_fail, dQ + 3 * lo, n, mode, true, 1, reinterpret_cast<double*>(static_cast<char*>(dvals) + lo * g->vals_row_bytes),
+                 reinterpret_cast<double*>(scratch), stream, nQ, false, lo == 0);
+    if (rc) return rc;
+    if (g->timing) cudaEventRecord(g->ev[4], stream);
+    CU(launch_structure_factor(g->sf, dQ + 3 * lo, reinterpret_cast<const double*>(scratch), n, (uint32_t)M, dsf + lo * M, g->sm_count, stream));
+    g->launches += 1;
+    if (g->timing) {
+      cudaEventRecord(g->ev[5], stream);
+      cudaEventSynchronize(g->ev[5]);
+      note_time(g, "consumer", g->ev[4], g->ev[5]);
+    }
+  }
+  if (n_failed) {
+    unsigned long long c[3];
+    CU(cudaMemcpyAsync(c, g->d_fail, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    *n_failed = c[0] + c[1] + c[2];
+    return status_error(c, nQ);
+  }
+  return B200_OK;
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -250,6 +250,78 @@ class B200Grid:
         capi.check(rc)
         return vals_out, vecs_out
 
+    # ------------------------------------------------------------------ device-resident consumer
+    def set_structure_factor(self, coef, positions=None, q_transform=None, debye_waller=None, conjugate=True):
+        """Configure the one-phonon structure factor reduction ``|sum_k coef_k e^{-qv.W_k.qv} e^{2 pi i Q.r_k} (qv . eps_k^*)|^2``
+        (``b200_grid_set_structure_factor``): ``coef`` complex (n_atoms,), ``positions`` fractional (n_atoms,3) or None,
+        ``q_transform`` 3x3 with ``qv = q_transform @ Q`` (default identity), ``debye_waller`` (n_atoms,3,3) or None."""
+        coef = np.ascontiguousarray(coef, dtype=np.complex128).reshape(-1)
+        cfg = capi.SFConfig()
+        cfg.n_atoms = coef.size
+        keep = [coef]
+        cfg.coef = coef.ctypes.data
+        if positions is not None:
+            pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(coef.size, 3)
+            keep.append(pos)
+            cfg.positions = pos.ctypes.data
+        if debye_waller is not None:
+            dw = np.ascontiguousarray(debye_waller, dtype=np.float64).reshape(coef.size, 9)
+            keep.append(dw)
+            cfg.debye_waller = dw.ctypes.data
+        T_ = np.eye(3) if q_transform is None else np.asarray(q_transform, dtype=np.float64).reshape(3, 3)
+        cfg.q_transform[:] = [float(x) for x in T_.reshape(-1)]
+        cfg.conjugate = 1 if conjugate else 0
+        capi.check(capi.lib().b200_grid_set_structure_factor(self._handle, C.byref(cfg)))
+
+    def ir_structure_factor(self, Q, do_not_move_points=False, *, pinned=False, out=None):
+        """``(vals, sf)``: the eigenvalues of ``ir_interpolate_at`` and ``sf (nQ, modes)``, the structure factor of the interpolated,
+        rotated eigenvectors, which stay on the device (``b200_ir_structure_factor``).  Host arrays in and out."""
+        Q = self._check_q(Q)
+        n = Q.shape[0]
+        if self._vals_shape is None:
+            raise RuntimeError("The interpolation data must be filled before interpolating.")
+        M = int(self._data_tables.vectors.branches)
+        if out is not None:
+            vals, sf = out
+            if vals.shape != (n,) + self._vals_shape or sf.shape != (n, M) or sf.dtype != np.float64 or vals.dtype != self._vals_dtype:
+                raise RuntimeError("out buffers have the wrong shape or dtype")
+            keep = None
+        elif pinned:
+            pv, ps = PinnedArray((n,) + self._vals_shape, self._vals_dtype), PinnedArray((n, M), np.float64)
+            vals, sf, keep = pv.array, ps.array, (pv, ps)
+        else:
+            vals, sf, keep = np.empty((n,) + self._vals_shape, self._vals_dtype), np.empty((n, M), np.float64), None
+        capi.check(capi.lib().b200_ir_structure_factor(self._handle, Q.ctypes.data, n, T.FLAG_NO_MOVE if do_not_move_points else 0,
+                                                       vals.ctypes.data, sf.ctypes.data))
+        if keep is not None:
+            vals, sf = _Owned(vals, keep[0]), _Owned(sf, keep[1])
+        return vals, sf
+
+    def ir_structure_factor_device(self, dQ, vals_out=None, sf_out=None, scratch=None, do_not_move_points=False, check=True, stream=None):
+        """torch CUDA tensors in and out; ``scratch``: optional complex128 tensor with room for the eigenvectors of all points."""
+        import torch
+
+        if not dQ.is_cuda or dQ.dtype != torch.float64 or dQ.dim() != 2 or dQ.shape[1] != 3:
+            raise RuntimeError("dQ must be a CUDA float64 tensor of shape (n,3)")
+        dQ = dQ.contiguous()
+        n = int(dQ.shape[0])
+        if self._vals_shape is None:
+            raise RuntimeError("The interpolation data must be filled before interpolating.")
+        M = int(self._data_tables.vectors.branches)
+        tv = torch.complex128 if self._vals_dtype == np.complex128 else torch.float64
+        if vals_out is None:
+            vals_out = torch.empty((n,) + self._vals_shape, dtype=tv, device=dQ.device)
+        if sf_out is None:
+            sf_out = torch.empty((n, M), dtype=torch.float64, device=dQ.device)
+        if scratch is not None and scratch.numel() * scratch.element_size() < n * self.row_bytes[1]:
+            raise RuntimeError("scratch is too small for the eigenvectors of all points")
+        s = stream if stream is not None else torch.cuda.current_stream(dQ.device)
+        nf = C.c_uint64(0)
+        capi.check(capi.lib().b200_ir_structure_factor_device(
+            self._handle, dQ.data_ptr(), n, T.FLAG_NO_MOVE if do_not_move_points else 0, vals_out.data_ptr(), sf_out.data_ptr(),
+            scratch.data_ptr() if scratch is not None else None, s.cuda_stream, C.byref(nf) if check else None))
+        return vals_out, sf_out
+
     # ------------------------------------------------------------------ introspection
     @property
     def launch_count(self):

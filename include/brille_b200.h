@@ -244,6 +244,35 @@ typedef struct b200_sort_config {
 int b200_grid_sort_pairs(b200_grid_t* grid, const uint32_t* pairs, size_t n_pairs, const b200_sort_config_t* config,
                          int32_t* row_out, int32_t* col_out, double* cost_out);
 
+/* ---- device-resident consumer: one-phonon structure factor ----------------------------------
+ * What brille's callers do with the output of ir_interpolate_at straight away (Euphonic's BrilleInterpolator /
+ * QpointPhononModes.calculate_structure_factor, brilleu's s_qw -- the loop validation/profiling.md:30-67 times; the
+ * commented-out ir_interpolate_at_dw of wrap/_common_grid.hpp:343-405 fuses the same kind of per-atom Debye-Waller
+ * reduction behind the interpolation):
+ *
+ *     F(Q,nu) = sum_k coef_k exp(-qv^T W_k qv) exp(2 pi i Q.r_k) (qv . eps_{nu,k}(Q)^[*]),     sf(Q,nu) = |F(Q,nu)|^2
+ *
+ * with eps the interpolated, rotated eigenvectors exactly as ir_interpolate_at returns them, Q the input point (rlu)
+ * and qv = q_transform Q.  The eigenvectors stay in HBM: per Q only the eigenvalue row and `modes` doubles leave the
+ * device instead of 16*modes*3*atoms bytes.  Requires complex eigenvector data made of 3-vectors only, one per atom
+ * (vectors.elements = {0, 3*n_atoms, 0}); anything else is B200_E_UNSUPPORTED.  The arrays are copied by set.        */
+typedef struct b200_sf_config {
+  uint32_t n_atoms;
+  const double* coef;        /* (n_atoms,2) complex coefficient per atom (re,im), e.g. b_k/sqrt(m_k)                   */
+  const double* positions;   /* (n_atoms,3) fractional atom positions r_k, or NULL: no exp(2 pi i Q.r_k) factor         */
+  const double* debye_waller;/* (n_atoms,9) symmetric W_k in the basis of qv, or NULL: no Debye-Waller factor           */
+  double q_transform[9];     /* row-major: identity when the eigenvectors are in lattice units, B for Cartesian ones   */
+  int32_t conjugate;         /* 1: qv . conj(eps) (Euphonic), 0: qv . eps                                              */
+} b200_sf_config_t;
+int b200_grid_set_structure_factor(b200_grid_t* grid, const b200_sf_config_t* config);
+/* HOST buffers: vals_out as in b200_ir_interpolate_at, sf_out (nQ, vectors.branches) doubles.                         */
+int b200_ir_structure_factor(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t flags, void* vals_out, double* sf_out);
+/* DEVICE buffers, enqueued on `stream`.  d_vecs_scratch: room for the eigenvectors of all nQ points
+ * (nQ * vectors row bytes), or NULL: the library keeps a scratch of its own (sized to at most a third of the free
+ * memory) and walks the points in as few chunks as fit.  Synchronises only if n_failed is non-NULL.                 */
+int b200_ir_structure_factor_device(b200_grid_t* grid, const double* dQ, size_t nQ, uint32_t flags, void* d_vals_out,
+                                    double* d_sf_out, void* d_vecs_scratch, void* stream, uint64_t* n_failed);
+
 /* Page-locked host memory for Q / output buffers: with pinned buffers the chunked copies of the host-buffer
  * entry points overlap the kernels (pageable memory works too but serialises the copies).                  */
 void* b200_alloc_pinned(size_t bytes);

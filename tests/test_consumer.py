@@ -1,0 +1,120 @@
+"""Device-resident consumer: the structure-factor reduction behind ir_interpolate_at.
+
+CPU part: the numpy oracle of the reduction against a literal loop.  GPU part: b200_ir_structure_factor[_device] against the
+oracle applied to the REFERENCE's eigenvectors (golden fixtures / the reference run on the spot)."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, assert_values_close, load_golden
+from oracle.consumer import structure_factor
+
+
+def sf_config(n_atoms, seed, cartesian=False, dw=True, pos=True):
+    rng = np.random.default_rng(seed)
+    cfg = {"coef": rng.normal(size=n_atoms) + 1j * rng.normal(size=n_atoms)}
+    cfg["positions"] = rng.uniform(0, 1, (n_atoms, 3)) if pos else None
+    cfg["q_transform"] = rng.normal(size=(3, 3)) if cartesian else None
+    if dw:
+        a = rng.normal(size=(n_atoms, 3, 3)) * 0.05
+        cfg["debye_waller"] = a @ a.transpose(0, 2, 1)
+    else:
+        cfg["debye_waller"] = None
+    return cfg
+
+
+def test_oracle_consumer_against_literal_loop():
+    rng = np.random.default_rng(0)
+    nq, M, K = 7, 5, 3
+    Q = rng.uniform(-2, 2, (nq, 3))
+    vecs = rng.normal(size=(nq, M, K, 3)) + 1j * rng.normal(size=(nq, M, K, 3))
+    for conj in (True, False):
+        cfg = sf_config(K, 4, cartesian=True)
+        got = structure_factor(Q, vecs, conjugate=conj, **cfg)
+        want = np.zeros((nq, M))
+        for i in range(nq):
+            qv = cfg["q_transform"] @ Q[i]
+            for m in range(M):
+                F = 0j
+                for k in range(K):
+                    e = np.conj(vecs[i, m, k]) if conj else vecs[i, m, k]
+                    F += cfg["coef"][k] * np.exp(-qv @ cfg["debye_waller"][k] @ qv) * np.exp(2j * np.pi * Q[i] @ cfg["positions"][k]) * (qv @ e)
+                want[i, m] = abs(F) ** 2
+        assert np.allclose(got, want, rtol=1e-13, atol=0)
+    # without the optional factors: |sum_k c_k Q.eps_k|^2
+    got = structure_factor(Q, vecs, np.ones(K), conjugate=False)
+    assert np.allclose(got, np.abs(np.einsum("qmkc,qc->qm", vecs, Q)) ** 2, rtol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_atoms", [("p63mmc_trellis.npz", 4), ("nacl_prim_trellis.npz", 2), ("nacl_prim_trellis_sorted.npz", 2),
+                                          ("p63mmc_nest.npz", 4), ("p63mmc_mesh.npz", 4), ("nacl_gamma.npz", 8)])
+@pytest.mark.parametrize("variant", ["full", "plain"])
+def test_structure_factor_on_reference_eigenvectors(name, n_atoms, variant):
+    import brille_b200
+
+    s, d, _, rest = load_golden(name)
+    g = brille_b200.B200Grid(None, structure=s, data=d)
+    cfg = sf_config(n_atoms, 7, cartesian=variant == "full", dw=variant == "full", pos=variant == "full")
+    conj = variant == "full"
+    g.set_structure_factor(conjugate=conj, **cfg)
+    Q = rest["Q"]
+    vals, sf = g.ir_structure_factor(Q)
+    assert_values_close(vals, rest["ref_values"])
+    want = structure_factor(Q, rest["ref_vectors"], conjugate=conj, **cfg)
+    assert sf.shape == want.shape
+    assert_values_close(sf, want)
+    g.close()
+
+
+@pytest.mark.gpu
+def test_structure_factor_device_chunks_and_errors(host):
+    import torch
+
+    import brille_b200
+    from brille_b200 import workloads as W
+
+    wl = W.BUILDERS["C3"](host)
+    g = brille_b200.accelerate(wl.grid)
+    Q = wl.make_q(300000, 21)
+    with pytest.raises(RuntimeError, match="set_structure_factor"):
+        g.ir_structure_factor(Q[:10])
+    cfg = sf_config(wl.n_atoms, 3, cartesian=True)
+    g.set_structure_factor(**cfg)
+    vals, vecs = g.ir_interpolate_at(Q)
+    want = structure_factor(Q, vecs, **cfg)
+    m = 20000
+    rv, rw = wl.grid.ir_interpolate_at(Q[:m], True, 8)  # the reference itself
+    want_ref = structure_factor(Q[:m], rw, **cfg)
+    v1, sf1 = g.ir_structure_factor(Q)
+    assert np.array_equal(v1, vals)
+    assert_values_close(sf1, want)
+    assert_values_close(sf1[:m], want_ref)
+    # the chunking of the host pipeline is invisible
+    g.set_option("host_chunk", 70001)
+    v2, sf2 = g.ir_structure_factor(Q, pinned=True)
+    assert np.array_equal(sf2, sf1) and np.array_equal(v2, v1)
+    g.set_option("host_chunk", 0)
+    # device buffers: library scratch, caller scratch
+    dQ = torch.from_numpy(Q).cuda()
+    dv, dsf = g.ir_structure_factor_device(dQ)
+    assert np.array_equal(dsf.cpu().numpy(), sf1) and np.array_equal(dv.cpu().numpy(), vals)
+    scratch = torch.empty((Q.shape[0], wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
+    dv, dsf = g.ir_structure_factor_device(dQ, scratch=scratch)
+    assert np.array_equal(dsf.cpu().numpy(), sf1)
+    assert np.array_equal(scratch.cpu().numpy().reshape(vecs.shape), vecs)  # the scratch holds the eigenvectors of the call
+    with pytest.raises(RuntimeError, match="too small"):
+        g.ir_structure_factor_device(dQ, scratch=scratch[:10])
+    # a Q outside the gridded zone fails the whole call like ir_interpolate_at
+    with pytest.raises(RuntimeError):
+        g.ir_structure_factor(np.full((3, 3), 7.3), do_not_move_points=True)
+    # wrong atom count / data that is not made of per-atom 3-vectors
+    g.set_structure_factor(np.ones(3))
+    with pytest.raises(RuntimeError, match="3-vectors"):
+        g.ir_structure_factor(Q[:10])
+    g.close()
+    s, d, _, rest = load_golden("fd3m_scalar_trellis.npz")
+    g = brille_b200.B200Grid(None, structure=s, data=d)
+    g.set_structure_factor(np.ones(1))
+    with pytest.raises(RuntimeError, match="3-vectors"):
+        g.ir_structure_factor(rest["Q"])
+    g.close()
