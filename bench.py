@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -217,9 +217,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # sampled from the warm-up on: the timed region of 10 steps is shorter than one 200 ms sample
+    sampler = ClockSampler(local)  # every rank samples its own GPU, from the warm-up until the per-kernel timing pass is over
+    sampler.start()                # (the same steps as the timed region, which alone is shorter than two samples)
     for i in range(max(args.warmup, 3)):
         step(check=(i == 0))  # the first warm-up step also verifies that every Q was placed
     barrier()
@@ -233,10 +232,14 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = grid.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        per_rank[0] = t.clone()
+    per_rank_ms = [float(x.item()) / args.steps for x in per_rank]
     ms_max = float(t.item())
     value = world * NQ * args.steps / (ms_max * 1e-3)
 
@@ -251,9 +254,17 @@ def run_ours(args):
     grid.enable_timing(False)
     torch.cuda.synchronize(dev)
     loc_ms, int_ms, sort_ms = float(np.mean(k_loc)), float(np.mean(k_int)), float(np.mean(k_sort))
+    clocks = sampler.stop()
+    if world > 1:  # slowest GPU's clock and the union of the throttle reasons over the ranks
+        all_clocks = [None] * world
+        dist.all_gather_object(all_clocks, clocks)
+        if rank == 0:
+            sm = [c["sm_mhz"] for c in all_clocks if c.get("sm_mhz")]
+            clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clocks.get("sm_max_mhz"), "samples": sum(c.get("samples", 0) for c in all_clocks),
+                      "reasons": sorted(set(r for c in all_clocks for r in c.get("reasons", []))), "per_rank_sm_mhz": [c.get("sm_mhz") for c in all_clocks]}
 
     # end to end through the host-buffer C-ABI call: pinned host Q in, pinned host results out, every step
-    ne = E2E_NQ
+    ne = E2E_NQ if world <= 2 else E2E_NQ // 2  # (page-locked host memory of all ranks together: 2.4 GB per 1e6 Q)
     hq = brille_b200.PinnedArray((ne, 3), np.float64)
     hv = brille_b200.PinnedArray((ne, wl.modes, 1), np.float64)
     hw = brille_b200.PinnedArray((ne, wl.modes, wl.n_atoms, 3), np.complex128)
@@ -271,6 +282,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ne * args.steps / float(t.item())
     checksum = float(hv.array[:1000].sum())
+    del hq, hv, hw  # (page-locked memory back before the next leg takes its own)
 
     # device-resident consumer: the same path followed by the structure-factor reduction on the device; the
     # eigenvectors never leave HBM, 8*modes bytes per Q of |F|^2 go back instead of 16*modes*3*atoms.  Reported beside the
@@ -294,10 +306,11 @@ def run_ours(args):
         grid.ir_structure_factor_device(dQ, vals, dsf, scratch=vecs, check=False, stream=stream)
         c_kernel_ms = grid.kernel_ms("consumer")
         grid.enable_timing(False)
-        hq2 = brille_b200.PinnedArray((NQ, 3), np.float64)
-        hv2 = brille_b200.PinnedArray((NQ, wl.modes, 1), np.float64)
-        hs2 = brille_b200.PinnedArray((NQ, wl.modes), np.float64)
-        hq2.array[:] = Q
+        nc = NQ if world <= 2 else NQ // 2
+        hq2 = brille_b200.PinnedArray((nc, 3), np.float64)
+        hv2 = brille_b200.PinnedArray((nc, wl.modes, 1), np.float64)
+        hs2 = brille_b200.PinnedArray((nc, wl.modes), np.float64)
+        hq2.array[:] = Q[:nc]
         grid.ir_structure_factor(hq2.array, out=(hv2.array, hs2.array))
         barrier()
         t0 = time.perf_counter()
@@ -312,8 +325,8 @@ def run_ours(args):
         consumer = {
             "what": "ir_structure_factor: the path + |sum_k c_k e^{2 pi i Q.r_k} (TQ . eps_k^*)|^2 per (Q, mode) on the device",
             "device_resident": {"value": world * NQ / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms, "consumer_kernel_ms": c_kernel_ms},
-            "e2e": {"value": world * NQ / c_e2e_s, "unit": UNIT, "q_per_step": NQ, "h2d_bytes_per_step": 24 * NQ,
-                    "d2h_bytes_per_step": (8 * wl.modes + 8 * wl.modes) * NQ, "checksum": float(hs2.array[:1000].sum())},
+            "e2e": {"value": world * nc / c_e2e_s, "unit": UNIT, "q_per_step": nc, "h2d_bytes_per_step": 24 * nc,
+                    "d2h_bytes_per_step": (8 * wl.modes + 8 * wl.modes) * nc, "checksum": float(hs2.array[:1000].sum())},
         }
 
     line = None
@@ -329,7 +342,7 @@ def run_ours(args):
                    "sample": f"{CPU_SAMPLE_NQ} Q of the same workload in one call of the unmodified reference (oracle/_ref) ir_interpolate_at(Q, True, {cores}): {secs:.1f} s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "per_rank_ms_per_step": per_rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(wl, {"e2e_q_per_step": ne, "parallelism": f"q-shard x{world}"}),
             "clocks": clocks,

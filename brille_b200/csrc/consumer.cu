@@ -12,36 +12,43 @@
 // reduction behind the interpolation.  With the reduction on the device the 16*modes*3*atoms bytes per Q of eigenvectors never
 // cross PCIe: 8*modes bytes per Q do.
 //
-// k_structure_factor: a CTA takes QB points at a time; every (point, atom) factor c_k e^{-W} e^{2 pi i Q.r_k} is evaluated
-// once into shared memory, then one thread per (point, mode) streams its row of 3*atoms complex numbers (read once:
-// ld.global.cs) and writes |F|^2.  HBM-read bound: 16*3*atoms*modes bytes per Q.
+// k_structure_factor: a CTA takes QB points at a time.  (1) every (point, atom) factor c_k e^{-W} e^{2 pi i Q.r_k} is evaluated
+// once into shared memory; (2) one thread per (point, mode, atom) loads its complex 3-vector -- consecutive lanes own
+// consecutive 48-byte pieces, fetched as one aligned 32-byte + one 16-byte streaming load, so a warp reads 1536 contiguous bytes
+// with two instructions -- and leaves factor * (qv . eps) in shared memory; (3) one thread per (point, mode) sums the atoms and
+// writes |F|^2 (coalesced).  HBM-read bound: 16*3*atoms*modes bytes per Q.
 #include "consumer.cuh"
 
 namespace b200 {
 
-constexpr int SF_QB = 64;  // points per CTA round
-
-__device__ __forceinline__ double2 ld_stream(const double2* p) {
-  double2 v;
-  asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
+__device__ __forceinline__ void load48_stream(const double2* p, double2& a, double2& b, double2& c) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(c.x), "=d"(c.y) : "l"(p + 2));
+  } else {
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "l"(p));
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(b.x), "=d"(b.y), "=d"(c.x), "=d"(c.y) : "l"(p + 1));
+  }
 }
 
 __global__ void __launch_bounds__(256) k_structure_factor(const double* __restrict__ Q, const double2* __restrict__ vecs, size_t n,
-                                                          uint32_t M, uint32_t NAT, const __grid_constant__ SFDev c,
+                                                          uint32_t M, uint32_t NAT, uint32_t QB, const __grid_constant__ SFDev c,
                                                           double* __restrict__ sf) {
   extern __shared__ __align__(16) unsigned char sf_smem[];
-  double2* const PH = reinterpret_cast<double2*>(sf_smem);              // [SF_QB][NAT]
-  double* const QV = reinterpret_cast<double*>(PH + (size_t)SF_QB * NAT);  // [SF_QB][3]
+  double2* const PH = reinterpret_cast<double2*>(sf_smem);  // [QB][NAT] per (point, atom) factor
+  double2* const FP = PH + (size_t)QB * NAT;                // [QB][M][NAT] per (point, mode, atom) term
+  double* const QV = reinterpret_cast<double*>(FP + (size_t)QB * M * NAT);  // [QB][3]
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const size_t n_blocks = (n + SF_QB - 1) / SF_QB;
-  const size_t S = 3 * (size_t)NAT;
+  const size_t n_blocks = (n + QB - 1) / QB;
+  const uint32_t MN = M * NAT;
+  const uint32_t nat_magic = 0xffffffffu / NAT + 1u, mn_magic = 0xffffffffu / MN + 1u;  // exact for u * d < 2^32
+  const double sgn = c.conjugate ? -1.0 : 1.0;
   for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    const size_t q0 = blk * SF_QB;
-    const uint32_t nq = (uint32_t)min((size_t)SF_QB, n - q0);
-    // ---- per (point, atom) factor -------------------------------------------------------------------------------
+    const size_t q0 = blk * QB;
+    const uint32_t nq = (uint32_t)min((size_t)QB, n - q0);
+    // ---- (1) per (point, atom) factor ------------------------------------------------------------------------------
     for (uint32_t u = tid; u < nq * NAT; u += nthr) {
-      const uint32_t t = u / NAT, k = u - t * NAT;
+      const uint32_t t = NAT == 1u ? u : __umulhi(u, nat_magic), k = u - t * NAT;
       const double* qr = Q + 3 * (q0 + t);
       const double q[3] = {qr[0], qr[1], qr[2]};
       double v[3];
@@ -72,21 +79,26 @@ __global__ void __launch_bounds__(256) k_structure_factor(const double* __restri
       PH[u] = f;
     }
     __syncthreads();
-    // ---- per (point, mode) reduction over the atoms ----------------------------------------------------------------
-    const double sgn = c.conjugate ? -1.0 : 1.0;
-    for (uint32_t p = tid; p < nq * M; p += nthr) {
-      const uint32_t t = p / M;
-      const double2* row = vecs + (q0 * M + p) * S;
+    // ---- (2) per (point, mode, atom) term ------------------------------------------------------------------------------
+    const double2* base = vecs + q0 * MN * 3;
+    for (uint32_t u = tid; u < nq * MN; u += nthr) {
+      const uint32_t t = __umulhi(u, mn_magic), k = u - (NAT == 1u ? u : __umulhi(u, nat_magic)) * NAT;
+      double2 e0, e1, e2;
+      load48_stream(base + 3 * (size_t)u, e0, e1, e2);
       const double v0 = QV[3 * t], v1 = QV[3 * t + 1], v2 = QV[3 * t + 2];
-      const double2* ph = PH + (size_t)t * NAT;
+      const double dr = v0 * e0.x + v1 * e1.x + v2 * e2.x;
+      const double di = sgn * (v0 * e0.y + v1 * e1.y + v2 * e2.y);
+      const double2 f = PH[t * NAT + k];
+      FP[u] = make_double2(f.x * dr - f.y * di, f.x * di + f.y * dr);
+    }
+    __syncthreads();
+    // ---- (3) per (point, mode): sum over the atoms ----------------------------------------------------------------------
+    for (uint32_t p = tid; p < nq * M; p += nthr) {
+      const double2* fp = FP + (size_t)p * NAT;
       double Fr = 0.0, Fi = 0.0;
       for (uint32_t k = 0; k < NAT; ++k) {
-        const double2 e0 = ld_stream(row + 3 * k), e1 = ld_stream(row + 3 * k + 1), e2 = ld_stream(row + 3 * k + 2);
-        const double dr = v0 * e0.x + v1 * e1.x + v2 * e2.x;
-        const double di = sgn * (v0 * e0.y + v1 * e1.y + v2 * e2.y);
-        const double2 f = ph[k];
-        Fr += f.x * dr - f.y * di;
-        Fi += f.x * di + f.y * dr;
+        Fr += fp[k].x;
+        Fi += fp[k].y;
       }
       sf[q0 * M + p] = Fr * Fr + Fi * Fi;
     }
@@ -97,16 +109,20 @@ __global__ void __launch_bounds__(256) k_structure_factor(const double* __restri
 cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const double* dvecs, size_t n, uint32_t M, double* dsf, int sm_count,
                                     cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  const size_t smem = (size_t)SF_QB * c.n_atoms * 16 + (size_t)SF_QB * 24;
+  // points per CTA round: about 2048 (point, mode, atom) terms (32 KB of shared memory), at least one point
+  const uint32_t MN = M * c.n_atoms;
+  uint32_t QB = 2048u / (MN ? MN : 1u);
+  QB = QB < 1u ? 1u : (QB > 64u ? 64u : QB);
+  const size_t smem = (size_t)QB * c.n_atoms * 16 + (size_t)QB * MN * 16 + (size_t)QB * 24;
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_structure_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const size_t blocks = (n + SF_QB - 1) / SF_QB, cap = (size_t)sm_count * 8;
+  const size_t blocks = (n + QB - 1) / QB, cap = (size_t)sm_count * 6;
   k_structure_factor<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, stream>>>(dQ, reinterpret_cast<const double2*>(dvecs), n, M,
-                                                                                     c.n_atoms, c, dsf);
+                                                                                     c.n_atoms, QB, c, dsf);
   return cudaGetLastError();
 }
 
