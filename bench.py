@@ -46,9 +46,26 @@ def build_workload():
     return W.c3_p63mmc(ref.host())
 
 
+WORKLOAD_TEXT = {
+    "C3": "C3: P6_3/mmc 4-atom cell, BZTrellisQdc V_ir/2000 (hybrid cube/tetrahedron), 12 modes eigvals+eigvecs (Gamma), 1e7 uniform random Q per GPU per step",
+    "C5": "C5: powder-average sweep (|Q| in U(0.1,10) 1/angstrom, isotropic directions) on the C3 P6_3/mmc 12-mode trellis, 1e7 Q per GPU per step, Q sharded across the GPUs",
+}
+WORKLOAD = "C3"
+
+
+def make_q(wl, n, seed):
+    """uniform random Q (C3, the default) or the powder-average Q of BASELINE configs[4] (--workload C5)"""
+    if WORKLOAD == "C5":
+        from brille_b200 import workloads as W
+        from brille_b200 import _bridge
+
+        return np.ascontiguousarray(W.powder_q(np.asarray(_bridge.flatten_bz(wl.bz)["to_xyz"]), n, seed))
+    return wl.make_q(n, seed)
+
+
 def workload_config(wl, extra=None):
     cfg = {
-        "workload": "C3: P6_3/mmc 4-atom cell, BZTrellisQdc V_ir/2000 (hybrid cube/tetrahedron), 12 modes eigvals+eigvecs (Gamma), 1e7 uniform random Q per GPU per step",
+        "workload": WORKLOAD_TEXT[WORKLOAD],
         "q_per_gpu_per_step": NQ,
         "modes": wl.modes,
         "atoms": wl.n_atoms,
@@ -140,7 +157,7 @@ def profiled_traffic():
 
 def cpu_reference_rate(wl, nq, threads, repeats=1):
     """The reference's own ir_interpolate_at (oracle/_ref, unmodified brille) on the host cores."""
-    Q = wl.make_q(nq, Q_SEED + 100)
+    Q = make_q(wl, nq, Q_SEED + 100)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -157,7 +174,7 @@ def run_reference(args):
     wl = build_workload()
     cores = os.cpu_count() or 1
     nq = CPU_SAMPLE_NQ
-    Q = wl.make_q(nq, Q_SEED + 100)
+    Q = make_q(wl, nq, Q_SEED + 100)
     for _ in range(args.warmup):
         wl.grid.ir_interpolate_at(Q[: nq // 10], True, cores)
     t0 = time.perf_counter()
@@ -203,7 +220,7 @@ def run_ours(args):
     assert bpq == wl.bytes_per_q
 
     # this rank's shard of the (world * NQ)-point job; different points on every rank
-    Q = wl.make_q(NQ, Q_SEED + 1000 * rank)
+    Q = make_q(wl, NQ, Q_SEED + 1000 * rank)
     dQ = torch.from_numpy(Q).to(dev)
     vals = torch.empty((NQ, wl.modes, 1), dtype=torch.float64, device=dev)
     vecs = torch.empty((NQ, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device=dev)
@@ -372,7 +389,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consumer", action="store_true")
+    ap.add_argument("--workload", default="C3", choices=["C3", "C5"], help="C3 (default, the headline configuration) or the C5 powder-average Q on the same grid")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

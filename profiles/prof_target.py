@@ -21,7 +21,15 @@ grid = brille_b200.accelerate(wl.grid)
 dQ = torch.from_numpy(wl.make_q(nq, Q_SEED)).cuda()
 vals = torch.empty((nq, wl.modes, 1), dtype=torch.float64, device="cuda")
 vecs = torch.empty((nq, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
-for _ in range(steps):
-    grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
+if len(sys.argv) > 3 and sys.argv[3] == "sf":  # the structure-factor consumer behind the path (k_structure_factor)
+    rng = np.random.default_rng(5)
+    grid.set_structure_factor(rng.normal(size=wl.n_atoms) + 1j * rng.normal(size=wl.n_atoms), positions=rng.uniform(0, 1, (wl.n_atoms, 3)),
+                              q_transform=rng.normal(size=(3, 3)))
+    sf = torch.empty((nq, wl.modes), dtype=torch.float64, device="cuda")
+    for _ in range(steps):
+        grid.ir_structure_factor_device(dQ, vals, sf, scratch=vecs, check=False)
+else:
+    for _ in range(steps):
+        grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
 torch.cuda.synchronize()
 print("done", steps, nq)

@@ -432,3 +432,31 @@ def test_degenerate_point_sets(host, bridge):
         # (the general and the cell-batched kernel agree to rounding, not bitwise)
         assert rel_close(v, ref_v[:n]) <= 1e-12 and rel_close(w, ref_w[:n]) <= 1e-12, n
     g.close()
+
+
+def test_c5_powder_q_sharded(host, bridge):
+    """BASELINE config 5 at reduced size: powder-average Q (|Q| up to 10 1/angstrom: large tau) on the C3 trellis, Q sharded in
+    contiguous row blocks (here: two shards on the one device through ShardedGrid) -- decisions bit-identical to the oracle,
+    the sharded call bit-identical to the single call, the reference itself on a slice."""
+    from brille_b200.sharding import ShardedGrid
+
+    wl = W.c3_p63mmc(host, density=500)
+    B = np.asarray(bridge.flatten_bz(wl.bz)["to_xyz"])
+    Q = W.powder_q(B, 200001, 77)
+    g = brille_b200.accelerate(wl.grid)
+    vals, vecs, pr = g.ir_interpolate_at(Q, probe=True)
+    assert np.abs(pr.tau).max() >= 3
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rc, ov, ow, opr = orc.interpolate_at(Q)
+    assert rc == 0
+    assert_decisions_equal(pr, probe_dict(opr), "cuda vs oracle")
+    assert_values_close(vals, ov)
+    assert_values_close(vecs, ow)
+    rv, rw = wl.grid.ir_interpolate_at(Q[:20000], True, 8)
+    assert_values_close(vals[:20000], rv)
+    assert_values_close(vecs[:20000], rw)
+    sg = ShardedGrid(wl.grid, [0, 0])
+    sv, sw = sg.ir_interpolate_at(Q)
+    assert np.array_equal(sv, vals) and np.array_equal(sw, vecs)
+    sg.close()
+    g.close()
