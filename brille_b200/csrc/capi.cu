@@ -149,14 +149,27 @@ struct Workspace {
   }
 };
 
+constexpr int N_FAIL = 4;  // per-call counters: outside BZ, outside wedge, not found, rows beyond the compact scratch of the fused consumer
+
+// fused structure-factor finish (enqueue): where |F|^2 goes and the compact scratch for the eigenvectors of the few points that
+// take the general interpolation kernel
+struct SfFuse {
+  double* dsf;
+  double* gscratch;
+  uint32_t gcap;  // rows of gscratch
+};
+constexpr int RC_NOT_FUSABLE = 1;  // enqueue: the pipelined cell kernel is not available for this call; nothing was launched
+
 struct HostStage {  // device-side staging buffers of one pipeline slot of the host-pointer API
   size_t capacity = 0;
   double* dQ = nullptr;
   double* dvals = nullptr;
   double* dvecs = nullptr;
   double* dsf = nullptr;  // structure factor rows of the chunk (b200_ir_structure_factor)
+  double* dgs = nullptr;  // fused consumer: compact eigenvector rows of the points that take the general kernel
+  uint32_t gcap = 0;
   Workspace ws;
-  unsigned long long* d_fail = nullptr;  // 3 counters
+  unsigned long long* d_fail = nullptr;  // N_FAIL counters
   unsigned long long* h_fail = nullptr;  // pinned mirror (keeps the D2H of the counters asynchronous)
   cudaStream_t stream = nullptr;
 };
@@ -192,6 +205,9 @@ struct b200_grid {
   bool has_sf = false;
   void* sf_scratch = nullptr;
   size_t sf_scratch_bytes = 0;
+  int sf_fused = 1;             // 1: reduce inside the pipelined cell kernel whenever possible (the eigenvectors never reach HBM)
+  double* sf_gscratch = nullptr;  // device-buffer entry point: compact rows of the general-kernel points
+  uint32_t sf_gcap = 0;
   uint64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -549,12 +565,12 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
     else if (kind == B200_GRID_NEST) rc = build_nest(g, static_cast<const b200_nest_tables_t*>(structure));
     else rc = build_mesh(g, static_cast<const b200_mesh_tables_t*>(structure));
   }
-  if (rc == B200_OK && cudaMalloc(&g->d_fail, 3 * sizeof(unsigned long long)) != cudaSuccess)
+  if (rc == B200_OK && cudaMalloc(&g->d_fail, N_FAIL * sizeof(unsigned long long)) != cudaSuccess)
     rc = fail(B200_E_CUDA, "cudaMalloc failed");
   for (int s = 0; s < 2 && rc == B200_OK; ++s) {
     if (cudaStreamCreateWithFlags(&g->stage[s].stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&g->stage[s].d_fail, 3 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaHostAlloc(&g->stage[s].h_fail, 3 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
+        cudaMalloc(&g->stage[s].d_fail, N_FAIL * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc(&g->stage[s].h_fail, N_FAIL * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
       rc = fail(B200_E_CUDA, "stream/counter creation failed");
   }
   for (int i = 0; i < 6 && rc == B200_OK; ++i)
@@ -578,6 +594,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
   g->ws.release();
   g->sf_pool.release();
   if (g->sf_scratch) cudaFree(g->sf_scratch);
+  if (g->sf_gscratch) cudaFree(g->sf_gscratch);
   if (g->d_fail) cudaFree(g->d_fail);
   for (int s = 0; s < 2; ++s) {
     HostStage& h = g->stage[s];
@@ -586,6 +603,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
     if (h.dvals) cudaFree(h.dvals);
     if (h.dvecs) cudaFree(h.dvecs);
     if (h.dsf) cudaFree(h.dsf);
+    if (h.dgs) cudaFree(h.dgs);
     if (h.d_fail) cudaFree(h.d_fail);
     if (h.h_fail) cudaFreeHost(h.h_fail);
     if (h.stream) cudaStreamDestroy(h.stream);
@@ -693,7 +711,7 @@ static void note_time(b200_grid* g, const char* name, cudaEvent_t a, cudaEvent_t
 // enqueue locate (+ interpolate) for n points that are already on the device; no synchronisation
 static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, const double* dQ, size_t n, uint32_t mode,
                    bool interp, int ir, double* dvals, double* dvecs, cudaStream_t stream, size_t n_call, bool want_probe,
-                   bool reset_fail = true) {
+                   bool reset_fail = true, const SfFuse* fz = nullptr) {
   const uint32_t nb = g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
   // cell-batched path: worthwhile once the cells hold several points each; always correct when eligible
   bool cell = interp && g->interp_path != 1 && cell_path_eligible(g->dd) && n < 0xffffffffull;
@@ -703,7 +721,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   bool tma = false;
   if (cell && g->cell_kernel != 1) {
     // pipelined kernel: needs the per-cell records, built once per fill (synchronously: the two host-pipeline streams share it)
-    const uint32_t ch = cell_tma_pick(g->dd, g->gd.cells.n_cubes > 0, g->chunk, (g->tile == 2 ? 72 : 108) * 1024, &mpp);
+    const uint32_t ch = cell_tma_pick(g->dd, g->gd.cells.n_cubes > 0, g->chunk, (g->tile == 2 ? 72 : 108) * 1024, &mpp, fz != nullptr);
     if (ch && mpp) {
       if (g->cell_table && g->ct.mpp == mpp) {
         tma = true;
@@ -726,8 +744,9 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
       }
       if (tma) chunk = ch;
     }
-    if (!tma && g->cell_kernel == 2) return fail(B200_E_CUDA, "the cell table of the pipelined kernel does not fit in device memory");
+    if (!tma && g->cell_kernel == 2 && !fz) return fail(B200_E_CUDA, "the cell table of the pipelined kernel does not fit in device memory");
   }
+  if (fz && !tma) return RC_NOT_FUSABLE;
   if (cell && !tma) {
     chunk = cell_pick_chunk(g->dd, g->gd.cells.n_cubes > 0, g->chunk, 100 * 1024, &mpp);
     if (chunk == 0 || mpp == 0) {
@@ -740,7 +759,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : 0u;
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
   CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes : ws.n_nodes));
-  if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, 3 * sizeof(unsigned long long), stream));
+  if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, N_FAIL * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
   lo.tau = ws.tau;
@@ -784,10 +803,22 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     a.vecs_out = dvecs;
     a.ir = ir;
     a.modes_per_pass = mpp;
+    if (fz) {  // fused structure factor: |F|^2 instead of the eigenvectors
+      a.Q = dQ;
+      a.sf_out = fz->dsf;
+      a.sf = g->sf;
+      a.vecs_out = nullptr;
+    }
     if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile));
     else CU(launch_interp_cell(a, n, stream));
     // points that are not generic members of their cell (and failed points): general kernel over the last bucket
-    CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, ws.bk.order, ws.bk.n_items));
+    if (fz) {  // ... into compact scratch rows, reduced by the list mode of the consumer kernel
+      CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, fz->gscratch, g->sm_count, stream, ws.bk.order, ws.bk.n_items, fz->gcap, d_fail + 3));
+      CU(launch_structure_factor(g->sf, dQ, fz->gscratch, n, g->dd.vectors.branches, fz->dsf, g->sm_count, stream, ws.bk.order, ws.bk.n_items, fz->gcap));
+      g->launches += 1;
+    } else {
+      CU(launch_interp(g->dd, as_input(g, lo), n, ir, dvals, dvecs, g->sm_count, stream, ws.bk.order, ws.bk.n_items));
+    }
     g->launches += 2;
     if (g->timing) cudaEventRecord(g->ev[3], stream);
   } else if (interp) {
@@ -861,12 +892,16 @@ extern "C" int b200_ir_interpolate_at_device(b200_grid_t* g, const double* dQ, s
 }
 
 // host-pointer pipeline: chunks alternate between two stages (stream + staging buffers) so that the H2D copy of
-// chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i
+// chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
+// sf_out != nullptr: the structure-factor consumer -- fused into the pipelined cell kernel when `fuse` (the eigenvectors then
+// exist nowhere; the staging buffer for them is not even allocated), otherwise reduced from the staging buffer by k_structure_factor.
 static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
-                         b200_probe_t* probe, double* sf_out = nullptr) {
+                         b200_probe_t* probe, double* sf_out = nullptr, bool fuse = false) {
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
-  const size_t per_q = 24 + (interp ? g->vals_row_bytes + g->vecs_row_bytes : 0) + 200;
+  const size_t sf_row = (size_t)g->dd.vectors.branches * sizeof(double);
+  const size_t vecs_per_q = fuse ? g->vecs_row_bytes / 16 + 1 : g->vecs_row_bytes;  // fused: only the compact scratch (1/16 of the rows)
+  const size_t per_q = 24 + (interp ? g->vals_row_bytes + vecs_per_q : 0) + (sf_out ? sf_row : 0) + 200;
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = std::min<size_t>(free_b / 4, (size_t)6 << 30);  // both stages together
@@ -874,44 +909,49 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
   chunk = std::min(chunk, (size_t)1 << 22);
   if (g->host_chunk) chunk = std::min(chunk, g->host_chunk);
   if (chunk > nQ) chunk = std::max<size_t>(nQ, 1);
-  unsigned long long total[3] = {0, 0, 0};
+  unsigned long long total[N_FAIL] = {0, 0, 0, 0};
   bool pending[2] = {false, false};
   size_t nchunks = (nQ + chunk - 1) / chunk;
   for (size_t c = 0; c < nchunks; ++c) {
     HostStage& h = g->stage[c & 1];
     if (pending[c & 1]) {  // staging buffers of this slot are reused: wait for its previous chunk
       CU(cudaStreamSynchronize(h.stream));
-      for (int k = 0; k < 3; ++k) total[k] += h.h_fail[k];
+      for (int k = 0; k < N_FAIL; ++k) total[k] += h.h_fail[k];
       pending[c & 1] = false;
     }
     const size_t lo = c * chunk, n = std::min(chunk, nQ - lo);
     if (h.capacity < n) {
-      if (h.dQ) cudaFree(h.dQ);
-      if (h.dvals) cudaFree(h.dvals);
-      if (h.dvecs) cudaFree(h.dvecs);
-      if (h.dsf) cudaFree(h.dsf);
-      h.dQ = h.dvals = h.dvecs = h.dsf = nullptr;
-      h.capacity = 0;
-      CU(cudaMalloc(&h.dQ, n * 3 * sizeof(double)));
-      if (interp) {
-        CU(cudaMalloc(&h.dvals, std::max<size_t>(n * g->vals_row_bytes, 8)));
-        CU(cudaMalloc(&h.dvecs, std::max<size_t>(n * g->vecs_row_bytes, 8)));
+      for (double** p : {&h.dQ, &h.dvals, &h.dvecs, &h.dsf, &h.dgs}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
       }
+      h.capacity = 0;
+      h.gcap = 0;
+      CU(cudaMalloc(&h.dQ, n * 3 * sizeof(double)));
       h.capacity = n;
-    } else if (interp && !h.dvals) {
-      CU(cudaMalloc(&h.dvals, std::max<size_t>(h.capacity * g->vals_row_bytes, 8)));
-      CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
     }
-    const size_t sf_row = (size_t)g->dd.vectors.branches * sizeof(double);
+    if (interp && !h.dvals) CU(cudaMalloc(&h.dvals, std::max<size_t>(h.capacity * g->vals_row_bytes, 8)));
+    if (interp && !fuse && !h.dvecs) CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
     if (sf_out && !h.dsf) CU(cudaMalloc(&h.dsf, std::max<size_t>(h.capacity * sf_row, 8)));
+    if (fuse && !h.dgs) {
+      h.gcap = (uint32_t)std::max<size_t>(1024, h.capacity / 16);
+      CU(cudaMalloc(&h.dgs, (size_t)h.gcap * g->vecs_row_bytes));
+    }
     CU(cudaMemcpyAsync(h.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h.stream));
-    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ, probe != nullptr);
+    SfFuse fz{h.dsf, h.dgs, h.gcap};
+    int rc = enqueue(g, h.ws, h.d_fail, h.dQ, n, mode, interp, ir, h.dvals, h.dvecs, h.stream, nQ, probe != nullptr, true, fuse ? &fz : nullptr);
+    if (rc == RC_NOT_FUSABLE) {  // (decided on the size of the call: always on the first chunk) start again without the fusion
+      for (int st = 0; st < 2; ++st) CU(cudaStreamSynchronize(g->stage[st].stream));
+      return host_pipeline(g, Q, nQ, mode, interp, ir, vals, vecs, probe, sf_out, false);
+    }
     if (rc) return rc;
     if (interp) {
       CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
-      if (sf_out) {  // the eigenvectors of the chunk are reduced where they are: only `modes` doubles per Q go back
-        CU(launch_structure_factor(g->sf, h.dQ, h.dvecs, n, g->dd.vectors.branches, h.dsf, g->sm_count, h.stream));
-        g->launches += 1;
+      if (sf_out) {  // only `modes` doubles per Q go back
+        if (!fuse) {  // the eigenvectors of the chunk are reduced where they are
+          CU(launch_structure_factor(g->sf, h.dQ, h.dvecs, n, g->dd.vectors.branches, h.dsf, g->sm_count, h.stream));
+          g->launches += 1;
+        }
         CU(cudaMemcpyAsync(reinterpret_cast<char*>(sf_out) + lo * sf_row, h.dsf, n * sf_row, cudaMemcpyDeviceToHost, h.stream));
       } else {
         CU(cudaMemcpyAsync(static_cast<char*>(vecs) + lo * g->vecs_row_bytes, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
@@ -930,15 +970,18 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       }
 #undef CP
     }
-    CU(cudaMemcpyAsync(h.h_fail, h.d_fail, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h.stream));
+    CU(cudaMemcpyAsync(h.h_fail, h.d_fail, N_FAIL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h.stream));
     pending[c & 1] = true;
   }
   for (int s = 0; s < 2; ++s)
     if (pending[s]) {
       CU(cudaStreamSynchronize(g->stage[s].stream));
-      for (int k = 0; k < 3; ++k) total[k] += g->stage[s].h_fail[k];
+      for (int k = 0; k < N_FAIL; ++k) total[k] += g->stage[s].h_fail[k];
     }
-  return status_error(total, nQ);
+  int rc = status_error(total, nQ);
+  if (rc == B200_OK && fuse && total[3])  // more general-kernel points than compact rows in some chunk (a degenerate point set)
+    return host_pipeline(g, Q, nQ, mode, interp, ir, vals, vecs, probe, sf_out, false);
+  return rc;
 }
 
 extern "C" int b200_ir_interpolate_at(b200_grid_t* g, const double* Q, size_t nQ, uint32_t flags, void* vals, void* vecs,
@@ -1008,7 +1051,7 @@ extern "C" int b200_ir_structure_factor(b200_grid_t* g, const double* Q, size_t 
   if (nQ && (!Q || !vals || !sf_out)) return fail(B200_E_INVALID, "NULL buffer");
   if (nQ == 0) return B200_OK;
   uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
-  return host_pipeline(g, Q, nQ, mode, true, 1, vals, nullptr, nullptr, sf_out);
+  return host_pipeline(g, Q, nQ, mode, true, 1, vals, nullptr, nullptr, sf_out, g->sf_fused && cell_sf_fusable(g->dd, g->sf));
 }
 
 extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ, size_t nQ, uint32_t flags, void* dvals, double* dsf,
@@ -1021,6 +1064,33 @@ extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
+  const uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
+  // Fused into the pipelined cell kernel when the caller does not ask for the eigenvectors (no scratch of theirs) and lets the
+  // call synchronise (n_failed): the rows-beyond-the-compact-scratch counter has to be read back before the result is final.
+  if (g->sf_fused && !dscratch && n_failed && nQ < 0xffffffffull && cell_sf_fusable(g->dd, g->sf)) {
+    const uint32_t want = (uint32_t)std::max<size_t>(1024, nQ / 16);
+    if (g->sf_gcap < want) {
+      CU(cudaStreamSynchronize(stream));
+      if (g->sf_gscratch) cudaFree(g->sf_gscratch);
+      g->sf_gscratch = nullptr;
+      g->sf_gcap = 0;
+      CU(cudaMalloc(&g->sf_gscratch, (size_t)want * g->vecs_row_bytes));
+      g->sf_gcap = want;
+    }
+    const SfFuse fz{dsf, g->sf_gscratch, g->sf_gcap};
+    rc = enqueue(g, g->ws, g->d_fail, dQ, nQ, mode, true, 1, static_cast<double*>(dvals), nullptr, stream, nQ, false, true, &fz);
+    if (rc != RC_NOT_FUSABLE) {
+      if (rc) return rc;
+      unsigned long long c[N_FAIL];
+      CU(cudaMemcpyAsync(c, g->d_fail, sizeof(c), cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      if (c[3] == 0) {
+        *n_failed = c[0] + c[1] + c[2];
+        return status_error(c, nQ);
+      }
+      // a degenerate point set (more general-kernel points than compact rows): once more, through the scratch
+    }
+  }
   size_t chunk = nQ;
   char* scratch = static_cast<char*>(dscratch);
   if (!scratch) {  // the library's own scratch: as many points as fit a third of the free memory (kept between calls)
@@ -1042,7 +1112,6 @@ extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ,
     scratch = static_cast<char*>(g->sf_scratch);
     chunk = std::min(nQ, g->sf_scratch_bytes / g->vecs_row_bytes);
   }
-  uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
   const size_t M = g->dd.vectors.branches;
   for (size_t lo = 0; lo < nQ; lo += chunk) {
     const size_t n = std::min(chunk, nQ - lo);
@@ -1139,6 +1208,8 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   } else if (n == "chunk") {
     if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
+  } else if (n == "sf_fused") {
+    g->sf_fused = value != 0;
   } else if (n == "host_chunk") {
     if (value < 0) return fail(B200_E_INVALID, "host_chunk must be >= 0");
     g->host_chunk = (size_t)value;

@@ -104,6 +104,11 @@ struct CellPass {
   double* vals_out;
   double* vecs_out;
   uint32_t* task_ctr;  // shared counter (zero at the start of the pass) for the dynamic deal of tasks, or nullptr
+  // fused structure-factor finish (cell_sf_pass): PH then holds the combined per-(point, SOURCE atom) factor
+  //   coef_l e^{-W_l} e^{2 pi i Q.r_l} * [conj](Gamma phase)   with l = F0(k, R) the destination atom,
+  const double* QV;   // [CH][3] g = (T Q)^T R of every point (R the point's rotation): the finish is g . a
+  double* sf_out;     // (n, M) |F|^2
+  int conjugate;
 };
 
 // TQ consecutive doubles / 32-bit words of a shared-memory array (TQ = 2 or 4, 8- resp. 16-byte aligned)
@@ -277,6 +282,104 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
         }
       }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused structure-factor finish: the same weighted sum and rotation as cell_compute_pass, but instead of
+// storing the rotated 3-vector u_l = ph * R a_k of (mode b, atom k -> l) its term of
+//     F(Q, b) = sum_l c_l e^{-W_l} e^{2 pi i Q.r_l} (qv . u_l^[*])
+// is formed in registers and summed over the atoms with shuffles inside the NAT consecutive lanes that hold the atoms of one
+// mode (NAT a power of two <= 32: lane groups are aligned because the tasks of a tile are dealt r = b * NAT + k fastest and both
+// the thread count and the tasks per tile are multiples of NAT).  The scalar Gamma phase commutes with the dot product, so it is
+// folded into the per-(point, atom) factor PH: one complex multiply per term instead of three.  One code path for every
+// point (the rotation is looked up per point), so the result does not depend on the composition of a tile or an item: it is
+// bit-reproducible across chunkings.  The eigenvectors are never written: 8 bytes per (Q, mode) leave the SM.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int TQ>
+__device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nthr) {
+  const double2* D = c.D;
+  const double* V = c.V;
+  const double* W = c.W;
+  const double2* PH = c.PH;
+  const double* QV = c.QV;
+  const uint32_t* QI = c.QI;
+  const uint32_t CH = c.CH, mpp = c.mpp, mb = c.mb, b0 = c.b0, M = c.M, S = c.S, NAT = c.NAT, no0v = c.no0v;
+  const int NV = c.NV;
+  const size_t vrow = (size_t)M * no0v;
+  const uint32_t len = c.len;
+  const uint32_t ntile = (len + TQ - 1) / TQ;
+  {  // eigenvalues: as in cell_compute_pass
+    const uint32_t per_v = mb * no0v;
+    for (uint32_t task = tid; task < ntile * per_v; task += nthr) {
+      const uint32_t tile = task / per_v, r = task - tile * per_v, t0 = tile * TQ;
+      double acc[TQ];
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) acc[t] = 0.0;
+      for (int i = 0; i < NV; ++i) {
+        const double v = V[(size_t)i * mpp * no0v + r];
+        double w[TQ];
+        load_tile<TQ>(W + (size_t)i * CH + t0, w);
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) acc[t] = __fma_rn(w[t], v, acc[t]);
+      }
+      const uint32_t nt = min((uint32_t)TQ, len - t0);
+      uint32_t qis[TQ];
+      load_tile<TQ>(QI + t0, qis);
+#pragma unroll
+      for (int t = 0; t < TQ; ++t)
+        if ((uint32_t)t < nt) c.vals_out[(size_t)qis[t] * vrow + (size_t)b0 * no0v + r] = acc[t];
+    }
+  }
+  const uint32_t per_q = mb * NAT;
+  const uint32_t step_tile = (uint32_t)nthr / per_q, step_r = (uint32_t)nthr - step_tile * per_q;
+  const uint32_t nat_magic = 0xffffffffu / NAT + 1u;
+  const uint32_t n_task = ntile * per_q;
+  const unsigned lane = (unsigned)tid & 31u;
+  const unsigned gmask = NAT >= 32u ? 0xffffffffu : (((1u << NAT) - 1u) << (lane & ~(NAT - 1u)));
+  const double sgn = c.conjugate ? -1.0 : 1.0;
+  uint32_t tile = (uint32_t)tid / per_q, r = (uint32_t)tid - tile * per_q;
+  for (uint32_t task = tid; task < n_task; task += nthr, tile += step_tile, r += step_r) {
+    if (r >= per_q) { r -= per_q; ++tile; }
+    const uint32_t b = NAT == 1u ? r : __umulhi(r, nat_magic), k = r - b * NAT;
+    const uint32_t t0 = tile * TQ;
+    const double2* src = D + (size_t)b * S + 3 * k;
+    double2 acc[TQ][3];
+#pragma unroll
+    for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
+    for (int i = 0; i < NV; ++i) {
+      const double2* x = src + (size_t)i * mpp * S;
+      const double2 x0 = x[0], x1 = x[1], x2 = x[2];
+      double w[TQ];
+      load_tile<TQ>(W + (size_t)i * CH + t0, w);
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) {
+        acc[t][0].x = __fma_rn(w[t], x0.x, acc[t][0].x); acc[t][0].y = __fma_rn(w[t], x0.y, acc[t][0].y);
+        acc[t][1].x = __fma_rn(w[t], x1.x, acc[t][1].x); acc[t][1].y = __fma_rn(w[t], x1.y, acc[t][1].y);
+        acc[t][2].x = __fma_rn(w[t], x2.x, acc[t][2].x); acc[t][2].y = __fma_rn(w[t], x2.y, acc[t][2].y);
+      }
+    }
+    const uint32_t nt = min((uint32_t)TQ, len - t0);  // the same for all lanes of an atom group (they share the tile)
+    uint32_t qis[TQ];
+    load_tile<TQ>(QI + t0, qis);
+#pragma unroll
+    for (int t = 0; t < TQ; ++t) {
+      if ((uint32_t)t >= nt) break;
+      // qv . (R a) = (qv^T R) . a: the row vector g = qv^T R is per point and comes ready from the item's tables
+      const double* gp = QV + 3 * (size_t)(t0 + t);
+      const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+      const double dr = __fma_rn(g2, acc[t][2].x, __fma_rn(g1, acc[t][1].x, __dmul_rn(g0, acc[t][0].x)));
+      const double di = sgn * __fma_rn(g2, acc[t][2].y, __fma_rn(g1, acc[t][1].y, __dmul_rn(g0, acc[t][0].y)));
+      const double2 f = PH[(size_t)(t0 + t) * NAT + k];
+      double Fr = __fma_rn(-f.y, di, __dmul_rn(f.x, dr));
+      double Fi = __fma_rn(f.y, dr, __dmul_rn(f.x, di));
+      for (uint32_t o = 1; o < NAT; o <<= 1) {  // butterfly over the atoms of the mode: every lane ends with the same sum
+        Fr += __shfl_xor_sync(gmask, Fr, o);
+        Fi += __shfl_xor_sync(gmask, Fi, o);
+      }
+      if (k == 0) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
+    }
+  }
 }
 
 }  // namespace b200

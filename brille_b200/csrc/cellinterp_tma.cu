@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(256) k_build_cell_table(DataDev dd, const uint
 // shared memory plan of the pipelined kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct TmaPlan {
-  uint32_t D0, D1, RW, W, PH, RS, F0, GV, QI, RI, BAR, per_set, total;
+  uint32_t D0, D1, RW, W, PH, RS, F0, GV, QI, RI, QV, BAR, per_set, total;
 };
 __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk,
-                                                 uint32_t n_at, uint32_t G, bool gamma) {
+                                                 uint32_t n_at, uint32_t G, bool gamma, bool sf = false) {
   TmaPlan p;
   uint32_t o = 0;
   auto take = [&](size_t bytes) { uint32_t at = o; o += (uint32_t)((bytes + 15) / 16 * 16); return at; };
@@ -136,6 +136,7 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
   p.PH = take(gamma ? (size_t)chunk * n_at * 16 : 0);
   p.QI = take((size_t)chunk * 4);
   p.RI = take((size_t)chunk * 4);
+  p.QV = take(sf ? (size_t)chunk * 24 : 0);  // fused structure factor: g = (T Q)^T R of every point
   p.per_set = o - set0;
   o += p.per_set;
   p.RS = take((size_t)G * 9 * 8);
@@ -152,7 +153,8 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
 constexpr uint32_t NO_ITEM = 0xffffffffu;
 constexpr uint32_t ITEM_BLOCK = 8;
 
-template <int TQ>
+// SF: fused structure-factor finish (cell_sf_pass): |F|^2 per (Q, mode) instead of the eigenvectors (a.sf_out, a.Q, a.sf)
+template <int TQ, bool SF>
 __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
                                                             const unsigned char* __restrict__ table, const __grid_constant__ TmaPlan pl) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -246,12 +248,57 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
   };
   // this thread's point of an item: raw record -> transposed weights, Gamma phases, indices in table set `set`.
   // The sort already ordered the points of a cell by operation: position in the item == position in the tables.
-  auto make_tables = [&](uint32_t len, int nv, int set) {
+  auto make_tables = [&](uint32_t len, int nv, int set, double qx, double qy, double qz) {
     unsigned char* const base = smem + (set ? pl.per_set : 0);
     double* const W = reinterpret_cast<double*>(base + pl.W);
     double2* const PH = reinterpret_cast<double2*>(base + pl.PH);
     uint32_t* const QI = reinterpret_cast<uint32_t*>(base + pl.QI);
     uint32_t* const RI = reinterpret_cast<uint32_t*>(base + pl.RI);
+    if (SF) {
+      // Fused structure factor.  A point is shared by nthr / CH threads (t = tid % CH; all of them hold its input point in
+      // registers, loaded an item ahead), which split its atoms.  Per SOURCE atom k (destination l = F0(k, R)) the combined factor
+      //     coef_l e^{-qv.W_l.qv} e^{2 pi i (Q.r_l -/+ q_ir.(R^-1 r_l - r_k))}
+      // -- the Gamma phase of interpolator_gamma.tpp:18-32,56-58 (conjugated when the eigenvectors are) and the atom's own phase
+      // share one sincos -- and, once per point, the row vector g = qv^T R, so that the finish is a plain dot product g . a.
+      const uint32_t t = (uint32_t)tid % CH, part = (uint32_t)tid / CH, nrep = (uint32_t)nthr / CH;
+      if (t < len) {
+        const double* rec = RW + REC_DOUBLES * (size_t)t;
+        const uint32_t rot = *reinterpret_cast<const uint32_t*>(rec + 11);
+        const uint32_t mi = (kind == 0 || kind == 1) ? (rot & 0xffffu) : (rot >> 16);
+        const double* T = a.sf.T;
+        const double v0 = T[0] * qx + T[1] * qy + T[2] * qz, v1 = T[3] * qx + T[4] * qy + T[5] * qz, v2 = T[6] * qx + T[7] * qy + T[8] * qz;
+        if (part == 0) {
+          double* const QV = reinterpret_cast<double*>(base + pl.QV);
+          const double* R = RS + 9 * mi;
+          QV[3 * t] = __fma_rn(v2, R[6], __fma_rn(v1, R[3], __dmul_rn(v0, R[0])));
+          QV[3 * t + 1] = __fma_rn(v2, R[7], __fma_rn(v1, R[4], __dmul_rn(v0, R[1])));
+          QV[3 * t + 2] = __fma_rn(v2, R[8], __fma_rn(v1, R[5], __dmul_rn(v0, R[2])));
+        }
+        for (uint32_t k = part; k < NAT; k += nrep) {
+          const uint32_t l = F0[k * G + mi];
+          const double* gv = GV + 3 * ((size_t)k * G + mi);
+          const double gdot = rec[8] * gv[0] + rec[9] * gv[1] + rec[10] * gv[2];
+          double arg = a.sf.conjugate ? -gdot : gdot;
+          if (a.sf.pos) {
+            const double* r = a.sf.pos + 3 * l;
+            arg += qx * r[0] + qy * r[1] + qz * r[2];
+          }
+          double sn, cs;
+          sincos(6.283185307179586476925286766559 * arg, &sn, &cs);
+          const double cr = a.sf.coef[2 * l], ci = a.sf.coef[2 * l + 1];
+          double2 f = make_double2(cr * cs - ci * sn, cr * sn + ci * cs);
+          if (a.sf.dw) {
+            const double* Wl = a.sf.dw + 9 * l;
+            const double w = v0 * (Wl[0] * v0 + Wl[1] * v1 + Wl[2] * v2) + v1 * (Wl[3] * v0 + Wl[4] * v1 + Wl[5] * v2) +
+                             v2 * (Wl[6] * v0 + Wl[7] * v1 + Wl[8] * v2);
+            const double e = exp(-w);
+            f.x *= e;
+            f.y *= e;
+          }
+          PH[(size_t)t * NAT + k] = f;
+        }
+      }
+    }
     if ((uint32_t)tid < len) {
       const double* rec = RW + REC_DOUBLES * (size_t)tid;  // weight[8] | q_ir[3] | rot, index
       const uint2 ri2 = *reinterpret_cast<const uint2*>(rec + 11);
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
       QI[tid] = 0;
       RI[tid] = 0;
     }
-    if (gamma) {
+    if (gamma && !SF) {
       // e^{2 pi i q_ir . (R^-1 r_l - r_k)} once per (point, atom)   interpolator_gamma.tpp:18-32,56-58.  The (point, atom)
       // pairs are dealt to ALL threads (every record of the item is visible once its mbarrier phase completed), so that
       // short items do not leave most warps idle here.
@@ -308,17 +355,28 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
   uint32_t n_done = 0;  // passes done by this CTA (selects the task counter)
   if (tid == 0) issue_tile(cur_key, 0, 0);
   // prologue: tables of the first item
-  issue_raw((uint32_t)tid < cur_len ? a.bk.order[cur_start + tid] : 0u, cur_len, 0u);
-  uint32_t q_nx = (uint32_t)tid < nxt_len ? a.bk.order[nxt_start + tid] : 0u;
+  double qx = 0.0, qy = 0.0, qz = 0.0;  // (SF) the input point of this thread's point of the next item, loaded an item ahead
+  {
+    // (SF: thread tid also serves point tid % CH, see make_tables; only the threads tid < len issue the record copies)
+    const uint32_t tp = SF ? (uint32_t)tid % CH : (uint32_t)tid;
+    const uint32_t q0 = tp < cur_len ? a.bk.order[cur_start + tp] : 0u;
+    issue_raw(q0, cur_len, 0u);
+    if (SF && tp < cur_len) { qx = a.Q[3 * (size_t)q0]; qy = a.Q[3 * (size_t)q0 + 1]; qz = a.Q[3 * (size_t)q0 + 2]; }
+  }
+  const uint32_t tp = SF ? (uint32_t)tid % CH : (uint32_t)tid;
+  uint32_t q_nx = tp < nxt_len ? a.bk.order[nxt_start + tp] : 0u;
   wait_raw(0u);
-  make_tables(cur_len, cur_key < a.n_cubes ? 8 : 4, 0);
+  make_tables(cur_len, cur_key < a.n_cubes ? 8 : 4, 0, qx, qy, qz);
   __syncthreads();
   (void)nxt_start;
 
   for (uint32_t it = 0; cur_key != NO_ITEM; ++it) {
     const int NV = cur_key < a.n_cubes ? 8 : 4;
     unsigned char* const tbase = smem + (set ? pl.per_set : 0);
-    if (nxt_key != NO_ITEM) issue_raw(q_nx, nxt_len, it + 1);
+    if (nxt_key != NO_ITEM) {
+      issue_raw(q_nx, nxt_len, it + 1);
+      if (SF && tp < nxt_len) { qx = a.Q[3 * (size_t)q_nx]; qy = a.Q[3 * (size_t)q_nx + 1]; qz = a.Q[3 * (size_t)q_nx + 2]; }
+    }
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const uint32_t b0 = pass * mpp, mb = min(mpp, M - b0);
       // ---- prefetch the next tile into the other buffer (its last readers finished before the previous barrier) ------
@@ -346,13 +404,20 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
       cp.NV = NV; cp.kind = kind; cp.gamma = gamma; cp.rot_det = a.dd.rot_det; cp.vals_out = a.vals_out; cp.vecs_out = a.vecs_out;
       cp.task_ctr = s_task_ctr + (n_done & 1u);
       if (tid == 0) s_task_ctr[(n_done + 1u) & 1u] = 0u;  // the counter of the next pass: idle since the previous barrier
-      cell_compute_pass<TQ>(cp, tid, nthr);
+      if (SF) {
+        cp.QV = reinterpret_cast<const double*>(tbase + pl.QV);
+        cp.sf_out = a.sf_out;
+        cp.conjugate = a.sf.conjugate;
+        cell_sf_pass<TQ>(cp, tid, nthr);
+      } else {
+        cell_compute_pass<TQ>(cp, tid, nthr);
+      }
       if (pass + 1 == n_pass) {
         if (nxt_key != NO_ITEM) {  // tables of item n+1 into the other set
           wait_raw(it + 1);
-          make_tables(nxt_len, nxt_key < a.n_cubes ? 8 : 4, set ^ 1);
+          make_tables(nxt_len, nxt_key < a.n_cubes ? 8 : 4, set ^ 1, qx, qy, qz);
         }
-        q_nx = (uint32_t)tid < nn_len ? a.bk.order[nn_start + tid] : 0u;
+        q_nx = tp < nn_len ? a.bk.order[nn_start + tp] : 0u;
       }
       __syncthreads();  // every reader of this tile, this table set and the raw records is done; the other set is complete
       if (load_next) buf ^= 1;
@@ -370,12 +435,18 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // modes per pass / points per item of the pipelined kernel for `budget` bytes of dynamic shared memory
-uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out) {
+bool cell_sf_fusable(const DataDev& dd, const SFDev& sf) {
+  const InterpDev& v = dd.vectors;
+  const uint32_t n = sf.n_atoms;
+  return v.rot_kind >= 3 && v.is_complex && v.no0 == 0 && v.no2 == 0 && v.no1 == n && n >= 1 && n <= 32 && (n & (n - 1)) == 0;
+}
+
+uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out, bool sf) {
   const bool gamma = dd.vectors.rot_kind >= 3;
   const uint32_t M = dd.vectors.branches;
   auto modes_that_fit = [&](uint32_t chunk) {
     for (uint32_t m = M; m >= 1; --m)
-      if (plan_smem_tma(has_cubes ? 8u : 4u, m, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma).total <= budget) return m;
+      if (plan_smem_tma(has_cubes ? 8u : 4u, m, dd.vectors.span, dd.values.span, chunk, dd.vectors.no1, dd.n_ops, gamma, sf).total <= budget) return m;
     return 0u;
   };
   uint32_t best_chunk = 0, best_mpp = 0;
@@ -416,13 +487,13 @@ cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vert
   return cudaGetLastError();
 }
 
-template <int TQ>
+template <int TQ, bool SF>
 static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n, int sm_count,
                                    const TmaPlan& plan, cudaStream_t stream) {
   const size_t smem = plan.total;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -430,7 +501,7 @@ static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct,
   static int ctas_per_sm = 0;
   static size_t occ_smem = 0;
   if (occ_smem != smem) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ>, 256, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ, SF>, 256, smem);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
     occ_smem = smem;
@@ -439,7 +510,7 @@ static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct,
   const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
   if (grid > max_blocks) grid = max_blocks;
   if (grid == 0) return cudaSuccess;
-  k_interp_cell_tma<TQ><<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
+  k_interp_cell_tma<TQ, SF><<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
   return cudaGetLastError();
 }
 
@@ -447,9 +518,11 @@ cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct,
                                    int sm_count, cudaStream_t stream, int tile) {
   const DataDev& dd = args.dd;
   const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
-  const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma);
-  if (tile == 2) return launch_tma_tile<2>(args, ct, table, n, sm_count, plan, stream);
-  return launch_tma_tile<4>(args, ct, table, n, sm_count, plan, stream);
+  const bool sf = args.sf_out != nullptr;
+  const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma, sf);
+  if (sf) return tile == 2 ? launch_tma_tile<2, true>(args, ct, table, n, sm_count, plan, stream) : launch_tma_tile<4, true>(args, ct, table, n, sm_count, plan, stream);
+  if (tile == 2) return launch_tma_tile<2, false>(args, ct, table, n, sm_count, plan, stream);
+  return launch_tma_tile<4, false>(args, ct, table, n, sm_count, plan, stream);
 }
 
 #undef LOAD_ITEM

@@ -33,7 +33,13 @@ __device__ __forceinline__ void load48_stream(const double2* p, double2& a, doub
 
 __global__ void __launch_bounds__(256) k_structure_factor(const double* __restrict__ Q, const double2* __restrict__ vecs, size_t n,
                                                           uint32_t M, uint32_t NAT, uint32_t QB, const __grid_constant__ SFDev c,
-                                                          double* __restrict__ sf) {
+                                                          double* __restrict__ sf, const uint32_t* __restrict__ order,
+                                                          const uint32_t* __restrict__ segment, uint32_t cap) {
+  // list mode (order != NULL; the points of the fused path that the cell kernel does not take): row j of vecs belongs to the
+  // point order[segment[1] + j], j < min(segment[2], cap) -- the compact rows the general interpolation kernel wrote
+  if (order) n = segment[2] < cap ? segment[2] : cap;
+  if (n == 0) return;
+  const uint32_t* const list = order ? order + segment[1] : nullptr;
   extern __shared__ __align__(16) unsigned char sf_smem[];
   double2* const PH = reinterpret_cast<double2*>(sf_smem);  // [QB][NAT] per (point, atom) factor
   double2* const FP = PH + (size_t)QB * NAT;                // [QB][M][NAT] per (point, mode, atom) term
@@ -42,6 +48,7 @@ __global__ void __launch_bounds__(256) k_structure_factor(const double* __restri
   const size_t n_blocks = (n + QB - 1) / QB;
   const uint32_t MN = M * NAT;
   const uint32_t nat_magic = 0xffffffffu / NAT + 1u, mn_magic = 0xffffffffu / MN + 1u;  // exact for u * d < 2^32
+  const uint32_t m_magic = 0xffffffffu / M + 1u;
   const double sgn = c.conjugate ? -1.0 : 1.0;
   for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const size_t q0 = blk * QB;
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(256) k_structure_factor(const double* __restri
     // ---- (1) per (point, atom) factor ------------------------------------------------------------------------------
     for (uint32_t u = tid; u < nq * NAT; u += nthr) {
       const uint32_t t = NAT == 1u ? u : __umulhi(u, nat_magic), k = u - t * NAT;
-      const double* qr = Q + 3 * (q0 + t);
+      const double* qr = Q + 3 * (list ? (size_t)list[q0 + t] : q0 + t);
       const double q[3] = {qr[0], qr[1], qr[2]};
       double v[3];
 #pragma unroll
@@ -100,14 +107,20 @@ __global__ void __launch_bounds__(256) k_structure_factor(const double* __restri
         Fr += fp[k].x;
         Fi += fp[k].y;
       }
-      sf[q0 * M + p] = Fr * Fr + Fi * Fi;
+      const double v = Fr * Fr + Fi * Fi;
+      if (list) {
+        const uint32_t t = M == 1u ? p : __umulhi(p, m_magic);
+        sf[(size_t)list[q0 + t] * M + (p - t * M)] = v;
+      } else {
+        sf[q0 * M + p] = v;
+      }
     }
     __syncthreads();
   }
 }
 
 cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const double* dvecs, size_t n, uint32_t M, double* dsf, int sm_count,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, const uint32_t* order, const uint32_t* segment, uint32_t cap) {
   if (n == 0) return cudaSuccess;
   // points per CTA round: about 2048 (point, mode, atom) terms (32 KB of shared memory), at least one point
   const uint32_t MN = M * c.n_atoms;
@@ -120,9 +133,9 @@ cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const doub
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const size_t blocks = (n + QB - 1) / QB, cap = (size_t)sm_count * 6;
-  k_structure_factor<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, stream>>>(dQ, reinterpret_cast<const double2*>(dvecs), n, M,
-                                                                                     c.n_atoms, QB, c, dsf);
+  const size_t blocks = (n + QB - 1) / QB, grid_cap = (size_t)sm_count * (order ? 2 : 6);  // list mode: normally (almost) empty
+  k_structure_factor<<<(unsigned)(blocks < grid_cap ? blocks : grid_cap), 256, smem, stream>>>(dQ, reinterpret_cast<const double2*>(dvecs), n, M,
+                                                                                               c.n_atoms, QB, c, dsf, order, segment, cap);
   return cudaGetLastError();
 }
 

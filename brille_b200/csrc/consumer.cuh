@@ -2,20 +2,11 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "device_tables.cuh"
 
 namespace b200 {
 
-// one-phonon structure factor configuration (device copy of b200_sf_config_t)
-struct SFDev {
-  uint32_t n_atoms;
-  const double* coef;  // (n_atoms,2) complex coefficient per atom
-  const double* pos;   // (n_atoms,3) fractional positions, or null: no exp(2 pi i Q.r) factor
-  const double* dw;    // (n_atoms,9) Debye-Waller matrices in the basis of qv, or null
-  double T[9];         // qv = T Q (row-major)
-  int conjugate;       // 1: qv . conj(eps)
-};
-
 cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const double* dvecs, size_t n, uint32_t M, double* dsf, int sm_count,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, const uint32_t* order = nullptr, const uint32_t* segment = nullptr, uint32_t cap = 0);
 
 }  // namespace b200

@@ -203,6 +203,16 @@ struct BucketDev {
   uint32_t* order;             // (n) point indices in bucket order
 };
 
+// one-phonon structure factor configuration (device copy of b200_sf_config_t)
+struct SFDev {
+  uint32_t n_atoms;
+  const double* coef;  // (n_atoms,2) complex coefficient per atom
+  const double* pos;   // (n_atoms,3) fractional positions, or null: no exp(2 pi i Q.r) factor
+  const double* dw;    // (n_atoms,9) Debye-Waller matrices in the basis of qv, or null
+  double T[9];         // qv = T Q (row-major)
+  int conjugate;       // 1: qv . conj(eps)
+};
+
 struct CellArgs {
   DataDev dd;
   const uint32_t* cube_vertices;
@@ -217,6 +227,10 @@ struct CellArgs {
   double* vecs_out;
   int ir;
   uint32_t modes_per_pass;  // modes staged per pass (<= branches)
+  // fused structure-factor finish of the pipelined kernel (sf_out != nullptr): vecs_out is not written
+  const double* Q;          // (n,3) the input points
+  double* sf_out;           // (n, branches)
+  SFDev sf;
 };
 
 // pre-aligned per-cell records of the pipelined cell kernel (cellinterp_tma.cu)
@@ -241,19 +255,21 @@ cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, 
 cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n, uint32_t mode, const LocateOut& out, const uint32_t* order,
                                   unsigned long long* fail_count, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
-                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment);
+                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment, uint32_t compact_cap = 0,
+                          unsigned long long* overflow = nullptr);
 bool cell_path_eligible(const DataDev& dd);
 uint32_t cell_modes_per_pass(const DataDev& dd, bool has_cubes, uint32_t chunk, size_t budget);
 uint32_t cell_pick_chunk(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
 cudaError_t launch_bucket_sort(const BucketDev& bk, const uint32_t* key, const uint32_t* rank, size_t n, int sm_count,
                                cudaStream_t stream, const uint32_t* index = nullptr);
 cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stream);
-uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out);
+uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out, bool sf = false);
 CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_tets, uint32_t mpp);
 cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vertices, const uint32_t* tet_vertices,
                                     const CellTableDev& ct, unsigned char* table, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
                                    int sm_count, cudaStream_t stream, int tile);
+bool cell_sf_fusable(const DataDev& dd, const SFDev& sf);
 
 // device work space of sort() (sortpairs.cu), kept by the grid between calls
 struct SortWorkspace {

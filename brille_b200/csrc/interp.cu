@@ -255,11 +255,17 @@ __device__ __forceinline__ Rot make_rot(const InterpDev& id, const DataDev& dd, 
 template <int LANES>
 __global__ void __launch_bounds__(256)
 k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_out, double* __restrict__ vecs_out,
-         const uint32_t* __restrict__ order, const uint32_t* __restrict__ segment) {
+         const uint32_t* __restrict__ order, const uint32_t* __restrict__ segment, uint32_t compact_cap, unsigned long long* overflow) {
   // list mode (order != NULL): only the points order[segment[1] .. segment[1]+segment[2]) are processed -- the last
   // bucket of the counting sort in cellinterp.cu, whose population is only known on the device
+  // compact mode (compact_cap != 0, list mode only; fused structure factor): the vectors row of the j-th listed point goes to row
+  // j of vecs_out, a scratch of compact_cap rows; points beyond the scratch are counted in *overflow and skipped
   if (order) n = segment[2];
   if (n == 0) return;
+  if (compact_cap && n > compact_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = n - compact_cap;
+    n = compact_cap;
+  }
   const uint32_t B = dd.values.branches;
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = LANES >= 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
@@ -310,7 +316,7 @@ k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_ou
     double qir[3] = {in.q_ir[3 * q], in.q_ir[3 * q + 1], in.q_ir[3 * q + 2]};
     if (!live) nv = 0;  // keep the warp converged for the shuffles, write nothing useful
     double* vrow_p = vals_out + q * vrow;
-    double* wrow_p = vecs_out + q * wrow;
+    double* wrow_p = vecs_out + (compact_cap ? u / B : q) * wrow;
     if (nv == 0) {
       if (live) {  // failed point: zero row (the reference's outputs are zero-initialised)
         const uint32_t sv = dd.values.span * (dd.values.is_complex ? 2 : 1), sw = dd.vectors.span * (dd.vectors.is_complex ? 2 : 1);
@@ -332,29 +338,31 @@ k_interp(DataDev dd, LocateIn in, size_t n, int ir, double* __restrict__ vals_ou
 
 template <int LANES>
 static cudaError_t launch_lanes(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs,
-                                int sm_count, cudaStream_t stream, const uint32_t* order, const uint32_t* segment) {
+                                int sm_count, cudaStream_t stream, const uint32_t* order, const uint32_t* segment, uint32_t compact_cap,
+                                unsigned long long* overflow) {
   const int threads = 256;
   const size_t units = n * (size_t)dd.values.branches;
   size_t want = (units * LANES + threads - 1) / threads;
   size_t cap = (size_t)sm_count * (order ? 2 : 32);  // list mode: the segment is normally (almost) empty
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  k_interp<LANES><<<blocks, threads, 0, stream>>>(dd, in, n, ir, vals, vecs, order, segment);
+  k_interp<LANES><<<blocks, threads, 0, stream>>>(dd, in, n, ir, vals, vecs, order, segment, compact_cap, overflow);
   return cudaGetLastError();
 }
 
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
-                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment) {
+                          cudaStream_t stream, const uint32_t* order, const uint32_t* segment, uint32_t compact_cap,
+                          unsigned long long* overflow) {
   if (n == 0) return cudaSuccess;
   // lanes per (Q, mode) unit: enough to cover the items of the widest segment of the vectors' mode
   uint32_t items = dd.vectors.no1 > dd.vectors.no2 ? dd.vectors.no1 : dd.vectors.no2;
   if (dd.vectors.no0 > items) items = dd.vectors.no0;
-  if (items <= 1) return launch_lanes<1>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
-  if (items <= 2) return launch_lanes<2>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
-  if (items <= 4) return launch_lanes<4>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
-  if (items <= 8) return launch_lanes<8>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
-  if (items <= 16) return launch_lanes<16>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
-  return launch_lanes<32>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment);
+  if (items <= 1) return launch_lanes<1>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
+  if (items <= 2) return launch_lanes<2>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
+  if (items <= 4) return launch_lanes<4>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
+  if (items <= 8) return launch_lanes<8>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
+  if (items <= 16) return launch_lanes<16>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
+  return launch_lanes<32>(dd, in, n, ir, vals, vecs, sm_count, stream, order, segment, compact_cap, overflow);
 }
 
 }  // namespace b200

@@ -255,7 +255,13 @@ int b200_grid_sort_pairs(b200_grid_t* grid, const uint32_t* pairs, size_t n_pair
  * with eps the interpolated, rotated eigenvectors exactly as ir_interpolate_at returns them, Q the input point (rlu)
  * and qv = q_transform Q.  The eigenvectors stay in HBM: per Q only the eigenvalue row and `modes` doubles leave the
  * device instead of 16*modes*3*atoms bytes.  Requires complex eigenvector data made of 3-vectors only, one per atom
- * (vectors.elements = {0, 3*n_atoms, 0}); anything else is B200_E_UNSUPPORTED.  The arrays are copied by set.        */
+ * (vectors.elements = {0, 3*n_atoms, 0}); anything else is B200_E_UNSUPPORTED.  The arrays are copied by set.
+ * When the pipelined cell kernel runs (Gamma-rotated data, a power-of-two number of atoms <= 32, enough points) the reduction
+ * is FUSED into its finish: the eigenvectors are formed in registers, reduced with warp shuffles and never written anywhere;
+ * the few points that sit on cell faces take the general kernel into a compact scratch (nQ/16 rows) and the list mode of the
+ * reduction kernel.  Otherwise the path writes the eigenvectors to a device scratch and k_structure_factor reduces them.
+ * Both give the same numbers to rounding (the fused finish sums in a different order); each is bit-reproducible across
+ * chunkings.  Option "sf_fused" (b200_grid_set_option) 1 (default) / 0 selects.                                           */
 typedef struct b200_sf_config {
   uint32_t n_atoms;
   const double* coef;        /* (n_atoms,2) complex coefficient per atom (re,im), e.g. b_k/sqrt(m_k)                   */
@@ -269,7 +275,9 @@ int b200_grid_set_structure_factor(b200_grid_t* grid, const b200_sf_config_t* co
 int b200_ir_structure_factor(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t flags, void* vals_out, double* sf_out);
 /* DEVICE buffers, enqueued on `stream`.  d_vecs_scratch: room for the eigenvectors of all nQ points
  * (nQ * vectors row bytes), or NULL: the library keeps a scratch of its own (sized to at most a third of the free
- * memory) and walks the points in as few chunks as fit.  Synchronises only if n_failed is non-NULL.                 */
+ * memory) and walks the points in as few chunks as fit.  Synchronises only if n_failed is non-NULL.  The fused finish is
+ * used when d_vecs_scratch is NULL and n_failed is not (the call must read a counter back to know that the compact scratch
+ * sufficed); a caller who passes a scratch gets the eigenvectors of the call in it.                                  */
 int b200_ir_structure_factor_device(b200_grid_t* grid, const double* dQ, size_t nQ, uint32_t flags, void* d_vals_out,
                                     double* d_sf_out, void* d_vecs_scratch, void* stream, uint64_t* n_failed);
 
@@ -286,7 +294,8 @@ int b200_device_count(void);
 uint64_t b200_grid_launch_count(const b200_grid_t* grid);
 /* average device time in ms of the kernels launched by the last *_device call, measured with CUDA events
  * on the launching stream when timing was enabled with b200_grid_enable_timing(grid, 1).
- * names: "locate", "sort", "interpolate"; returns <0 if unknown / not timed.                                      */
+ * names: "locate", "sort", "interpolate", "consumer" (k_structure_factor of the unfused device-buffer call); returns <0 if
+ * unknown / not timed.                                                                                              */
 int b200_grid_enable_timing(b200_grid_t* grid, int on);
 double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
 /* tuning knobs: "interp_path" 0 auto | 1 general per-(Q,mode) kernel | 2 cell-batched kernel whenever the data layout
@@ -295,7 +304,8 @@ double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
  * the vertex rows on the fly | 2 persistent pipelined cell kernel fed from the per-cell record table (built once per
  * fill; auto uses it whenever the table fits in a quarter of the free device memory); "tile" points per register tile
  * of the pipelined kernel (4: 124 registers, 2 CTAs/SM, default; 2: 80 registers, 3 CTAs/SM - measured slower); "host_chunk" upper bound on
- * the points per chunk of the host-buffer pipeline (0 = sized from free device memory)                          */
+ * the points per chunk of the host-buffer pipeline (0 = sized from free device memory); "sf_fused" 1 (default) / 0: structure
+ * factor reduced inside the pipelined cell kernel whenever possible / always through the eigenvector scratch           */
 int b200_grid_set_option(b200_grid_t* grid, const char* name, double value);
 /* output row sizes in bytes for one Q (values, vectors) and algorithmic HBM bytes per Q of the path          */
 int b200_grid_row_bytes(const b200_grid_t* grid, size_t* vals_bytes, size_t* vecs_bytes);

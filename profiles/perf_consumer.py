@@ -24,12 +24,32 @@ for chunk in [0, 250_000, 500_000, 1_000_000, 2_000_000, 4_000_000]:
         g.ir_structure_factor(hq.array, out=(hv.array, hs.array))
     dt = (time.perf_counter() - t0) / 5
     print(f"host_chunk {chunk:>8}: {dt*1e3:7.2f} ms  {NQ/dt:.3e} Q/s  D2H {NQ*192/dt/1e9:.1f} GB/s", flush=True)
+g.set_option("host_chunk", 0)
 dQ = torch.from_numpy(Q).cuda()
 vals = torch.empty((NQ, wl.modes, 1), dtype=torch.float64, device="cuda")
 sf = torch.empty((NQ, wl.modes), dtype=torch.float64, device="cuda")
-scratch = torch.empty((NQ, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
-g.enable_timing(True)
-for _ in range(3):
-    g.ir_structure_factor_device(dQ, vals, sf, scratch=scratch, check=False)
-    print("device: locate %.2f sort %.2f interpolate %.2f consumer %.2f ms" % tuple(g.kernel_ms(k) for k in ("locate", "sort", "interpolate", "consumer")))
-print("consumer kernel: %.0f GB/s read" % (NQ * 2304 / g.kernel_ms("consumer") / 1e6))
+out = {}
+for fused in (1, 0):
+    g.set_option("sf_fused", fused)
+    for _ in range(2):
+        g.ir_structure_factor_device(dQ, vals, sf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        g.ir_structure_factor_device(dQ, vals, sf)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out[fused] = sf.clone()
+    g.enable_timing(True)
+    g.ir_structure_factor_device(dQ, vals, sf)
+    print("fused=%d: %.2f ms per step (%.3e Q/s); locate %.2f sort %.2f interpolate %.2f consumer %.2f ms" % (
+        (fused, ms, NQ / ms * 1e3) + tuple(g.kernel_ms(k) for k in ("locate", "sort", "interpolate", "consumer"))), flush=True)
+    g.enable_timing(False)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        g.ir_structure_factor(hq.array, out=(hv.array, hs.array))
+    dt = (time.perf_counter() - t0) / 3
+    print(f"fused={fused}: host buffers {dt*1e3:.2f} ms  {NQ/dt:.3e} Q/s", flush=True)
+d = (out[1] - out[0]).abs().max().item() / out[0].abs().max().item()
+print("fused vs unfused: max rel diff %.2e, bitwise equal: %s" % (d, bool(torch.equal(out[0], out[1]))))

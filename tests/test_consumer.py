@@ -85,28 +85,46 @@ def test_structure_factor_device_chunks_and_errors(host):
     m = 20000
     rv, rw = wl.grid.ir_interpolate_at(Q[:m], True, 8)  # the reference itself
     want_ref = structure_factor(Q[:m], rw, **cfg)
+    # fused into the pipelined cell kernel (the default) ...
     v1, sf1 = g.ir_structure_factor(Q)
     assert np.array_equal(v1, vals)
     assert_values_close(sf1, want)
     assert_values_close(sf1[:m], want_ref)
-    # the chunking of the host pipeline is invisible
-    g.set_option("host_chunk", 70001)
-    v2, sf2 = g.ir_structure_factor(Q, pinned=True)
-    assert np.array_equal(sf2, sf1) and np.array_equal(v2, v1)
-    g.set_option("host_chunk", 0)
-    # device buffers: library scratch, caller scratch
-    dQ = torch.from_numpy(Q).cuda()
-    dv, dsf = g.ir_structure_factor_device(dQ)
-    assert np.array_equal(dsf.cpu().numpy(), sf1) and np.array_equal(dv.cpu().numpy(), vals)
+    # ... and reduced from the eigenvector scratch by the separate kernel: the same numbers to rounding
+    g.set_option("sf_fused", 0)
+    v0, sf0 = g.ir_structure_factor(Q)
+    assert np.array_equal(v0, vals)
+    assert_values_close(sf0, want)
+    assert_values_close(sf0, sf1, rtol=1e-12)
+    for fused, ref_sf in ((1, sf1), (0, sf0)):
+        g.set_option("sf_fused", fused)
+        # the chunking of the host pipeline is invisible
+        g.set_option("host_chunk", 70001)
+        v2, sf2 = g.ir_structure_factor(Q, pinned=True)
+        assert np.array_equal(sf2, ref_sf) and np.array_equal(v2, v1)
+        g.set_option("host_chunk", 0)
+        # device buffers with the library's own scratch
+        dQ = torch.from_numpy(Q).cuda()
+        dv, dsf = g.ir_structure_factor_device(dQ)
+        assert np.array_equal(dsf.cpu().numpy(), ref_sf) and np.array_equal(dv.cpu().numpy(), vals)
+    # caller scratch: never fused, the scratch holds the eigenvectors of the call
+    g.set_option("sf_fused", 1)
     scratch = torch.empty((Q.shape[0], wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
     dv, dsf = g.ir_structure_factor_device(dQ, scratch=scratch)
-    assert np.array_equal(dsf.cpu().numpy(), sf1)
-    assert np.array_equal(scratch.cpu().numpy().reshape(vecs.shape), vecs)  # the scratch holds the eigenvectors of the call
+    assert np.array_equal(dsf.cpu().numpy(), sf0)
+    assert np.array_equal(scratch.cpu().numpy().reshape(vecs.shape), vecs)
     with pytest.raises(RuntimeError, match="too small"):
         g.ir_structure_factor_device(dQ, scratch=scratch[:10])
+    # a call too small for the cell-batched kernels takes the general kernel + the separate reduction
+    vs, sfs = g.ir_structure_factor(Q[:500])
+    assert_values_close(sfs, want[:500])
     # a Q outside the gridded zone fails the whole call like ir_interpolate_at
     with pytest.raises(RuntimeError):
         g.ir_structure_factor(np.full((3, 3), 7.3), do_not_move_points=True)
+    Qbad = Q.copy()
+    Qbad[123456] = 7.3
+    with pytest.raises(RuntimeError):
+        g.ir_structure_factor(Qbad, do_not_move_points=True)
     # wrong atom count / data that is not made of per-atom 3-vectors
     g.set_structure_factor(np.ones(3))
     with pytest.raises(RuntimeError, match="3-vectors"):
@@ -117,4 +135,69 @@ def test_structure_factor_device_chunks_and_errors(host):
     g.set_structure_factor(np.ones(1))
     with pytest.raises(RuntimeError, match="3-vectors"):
         g.ir_structure_factor(rest["Q"])
+    g.close()
+
+
+@pytest.mark.gpu
+def test_structure_factor_fused_on_degenerate_point_sets(host):
+    """Points on cell faces / edges / vertices do not take the cell kernel: their eigenvectors go to the compact scratch and are
+    reduced by the list mode of the consumer kernel; when there are more of them than compact rows the call falls back to the
+    unfused reduction.  Powder Q (large tau), sorted data (permutations) and a Nest grid run fused as well."""
+    import brille_b200
+    from brille_b200 import workloads as W
+
+    wl = W.c3_p63mmc(host, density=300, seed=5)
+    wl.grid.sort()
+    g = brille_b200.accelerate(wl.grid)
+    cfg = sf_config(wl.n_atoms, 11, cartesian=True)
+    g.set_structure_factor(**cfg)
+    rng = np.random.default_rng(5)
+    line = np.outer(np.linspace(-2.0, 2.0, 200_001), np.array([1.0, 0.0, 0.0]))  # node faces and edges all along
+    rational = rng.integers(-8, 9, (100_000, 3)) / 8.0                           # many exactly on cell faces
+    mixed = np.vstack([wl.make_q(150_000, 4), rational[:5000]])                  # a few general-kernel points among many
+    one = np.tile(np.array([[0.137, 0.211, 0.303]]), (100_000, 1))
+    for name, Q in (("line", line), ("rational", rational), ("mixed", mixed), ("identical", one)):
+        vals, vecs = g.ir_interpolate_at(Q)
+        want = structure_factor(Q, vecs, **cfg)
+        v1, sf1 = g.ir_structure_factor(Q)
+        assert np.array_equal(v1, vals), name
+        assert_values_close(sf1, want)
+        import torch
+
+        dv, dsf = g.ir_structure_factor_device(torch.from_numpy(Q).cuda())
+        assert np.array_equal(dsf.cpu().numpy(), sf1), name
+    g.close()
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    hg = host.BZNestQdc(bz, bz.ir_polyhedron.volume / 500, 5)
+    W._gamma_fill(hg, 12, 4, 17)
+    g = brille_b200.accelerate(hg)
+    g.set_structure_factor(**cfg)
+    Q = rng.uniform(-3, 3, (100_000, 3))
+    vals, vecs = g.ir_interpolate_at(Q)
+    v1, sf1 = g.ir_structure_factor(Q)
+    assert_values_close(sf1, structure_factor(Q, vecs, **cfg))
+    g.set_option("sf_fused", 0)
+    v0, sf0 = g.ir_structure_factor(Q)
+    assert_values_close(sf1, sf0, rtol=1e-12)
+    g.close()
+
+
+@pytest.mark.gpu
+def test_structure_factor_c4_72_modes(host):
+    """BASELINE config 4 (24 atoms: not a power of two, so never fused; mode-tiled cell kernel + separate reduction)."""
+    import brille_b200
+    from brille_b200 import workloads as W
+
+    wl = W.c4_p21c_nest(host, density=300)
+    g = brille_b200.accelerate(wl.grid)
+    cfg = sf_config(wl.n_atoms, 13, cartesian=True)
+    g.set_structure_factor(**cfg)
+    Q = wl.make_q(20000, 21)
+    vals, vecs = g.ir_interpolate_at(Q)
+    v1, sf1 = g.ir_structure_factor(Q)
+    assert np.array_equal(v1, vals)
+    assert_values_close(sf1, structure_factor(Q, vecs, **cfg))
+    rv, rw = wl.grid.ir_interpolate_at(Q[:3000], True, 8)
+    assert_values_close(sf1[:3000], structure_factor(Q[:3000], rw, **cfg))
     g.close()
