@@ -335,14 +335,18 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
   const uint32_t step_tile = (uint32_t)nthr / per_q, step_r = (uint32_t)nthr - step_tile * per_q;
   const uint32_t nat_magic = 0xffffffffu / NAT + 1u;
   const uint32_t n_task = ntile * per_q;
-  const unsigned lane = (unsigned)tid & 31u;
-  const unsigned gmask = NAT >= 32u ? 0xffffffffu : (((1u << NAT) - 1u) << (lane & ~(NAT - 1u)));
+  const uint32_t lane = (uint32_t)tid & 31u;
   const double sgn = c.conjugate ? -1.0 : 1.0;
   uint32_t tile = (uint32_t)tid / per_q, r = (uint32_t)tid - tile * per_q;
-  for (uint32_t task = tid; task < n_task; task += nthr, tile += step_tile, r += step_r) {
+  // The loop is WARP-uniform (it runs while the first lane of the warp has a task; lanes past the end redo task 0 and store
+  // nothing) and so is everything inside it (the points past the end of the last tile carry zero weights and are only kept from
+  // storing): the shuffles can name the full warp, which costs one instruction each instead of a guarded sequence.
+  for (uint32_t task = tid; task - lane < n_task; task += nthr, tile += step_tile, r += step_r) {
     if (r >= per_q) { r -= per_q; ++tile; }
-    const uint32_t b = NAT == 1u ? r : __umulhi(r, nat_magic), k = r - b * NAT;
-    const uint32_t t0 = tile * TQ;
+    const bool live = task < n_task;
+    const uint32_t tl = live ? tile : 0u, rl = live ? r : 0u;
+    const uint32_t b = NAT == 1u ? rl : __umulhi(rl, nat_magic), k = rl - b * NAT;
+    const uint32_t t0 = tl * TQ;
     const double2* src = D + (size_t)b * S + 3 * k;
     double2 acc[TQ][3];
 #pragma unroll
@@ -359,12 +363,11 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
         acc[t][2].x = __fma_rn(w[t], x2.x, acc[t][2].x); acc[t][2].y = __fma_rn(w[t], x2.y, acc[t][2].y);
       }
     }
-    const uint32_t nt = min((uint32_t)TQ, len - t0);  // the same for all lanes of an atom group (they share the tile)
+    const uint32_t nt = live ? min((uint32_t)TQ, len - t0) : 0u;
     uint32_t qis[TQ];
     load_tile<TQ>(QI + t0, qis);
 #pragma unroll
     for (int t = 0; t < TQ; ++t) {
-      if ((uint32_t)t >= nt) break;
       // qv . (R a) = (qv^T R) . a: the row vector g = qv^T R is per point and comes ready from the item's tables
       const double* gp = QV + 3 * (size_t)(t0 + t);
       const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
@@ -374,10 +377,10 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
       double Fr = __fma_rn(-f.y, di, __dmul_rn(f.x, dr));
       double Fi = __fma_rn(f.y, dr, __dmul_rn(f.x, di));
       for (uint32_t o = 1; o < NAT; o <<= 1) {  // butterfly over the atoms of the mode: every lane ends with the same sum
-        Fr += __shfl_xor_sync(gmask, Fr, o);
-        Fi += __shfl_xor_sync(gmask, Fi, o);
+        Fr += __shfl_xor_sync(0xffffffffu, Fr, o);
+        Fi += __shfl_xor_sync(0xffffffffu, Fi, o);
       }
-      if (k == 0) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
+      if (k == 0 && (uint32_t)t < nt) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
     }
   }
 }

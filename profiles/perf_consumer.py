@@ -46,6 +46,7 @@ for fused in (1, 0):
     print("fused=%d: %.2f ms per step (%.3e Q/s); locate %.2f sort %.2f interpolate %.2f consumer %.2f ms" % (
         (fused, ms, NQ / ms * 1e3) + tuple(g.kernel_ms(k) for k in ("locate", "sort", "interpolate", "consumer"))), flush=True)
     g.enable_timing(False)
+    g.ir_structure_factor(hq.array, out=(hv.array, hs.array))
     t0 = time.perf_counter()
     for _ in range(3):
         g.ir_structure_factor(hq.array, out=(hv.array, hs.array))

@@ -21,13 +21,16 @@ grid = brille_b200.accelerate(wl.grid)
 dQ = torch.from_numpy(wl.make_q(nq, Q_SEED)).cuda()
 vals = torch.empty((nq, wl.modes, 1), dtype=torch.float64, device="cuda")
 vecs = torch.empty((nq, wl.modes, wl.n_atoms, 3), dtype=torch.complex128, device="cuda")
-if len(sys.argv) > 3 and sys.argv[3] == "sf":  # the structure-factor consumer behind the path (k_structure_factor)
+if len(sys.argv) > 3 and sys.argv[3] in ("sf", "sf0"):  # the structure-factor consumer: fused finish (sf) / k_structure_factor (sf0)
     rng = np.random.default_rng(5)
     grid.set_structure_factor(rng.normal(size=wl.n_atoms) + 1j * rng.normal(size=wl.n_atoms), positions=rng.uniform(0, 1, (wl.n_atoms, 3)),
                               q_transform=rng.normal(size=(3, 3)))
     sf = torch.empty((nq, wl.modes), dtype=torch.float64, device="cuda")
     for _ in range(steps):
-        grid.ir_structure_factor_device(dQ, vals, sf, scratch=vecs, check=False)
+        if sys.argv[3] == "sf":
+            grid.ir_structure_factor_device(dQ, vals, sf)
+        else:
+            grid.ir_structure_factor_device(dQ, vals, sf, scratch=vecs, check=False)
 else:
     for _ in range(steps):
         grid.ir_interpolate_at_device(dQ, vals, vecs, check=False)
