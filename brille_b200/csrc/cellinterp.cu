@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, 2) k_interp_cell(CellArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   if (blockIdx.x >= a.bk.n_items[0]) return;
   const CellItem item = a.bk.items[blockIdx.x];
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const InterpDev& vals = a.dd.values;
   const InterpDev& vecs = a.dd.vectors;
   const uint32_t M = vecs.branches, S = vecs.span, NAT = vecs.no1, no0v = vals.span, G = a.dd.n_ops;

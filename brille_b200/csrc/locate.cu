@@ -337,7 +337,6 @@ __device__ __forceinline__ uint32_t trellis_in_node(const BZDev& bz, const Trell
     if (all) {
       vo[0] = make_uint4(vb.w, vb.z, vb.y, vb.x);  // vertex_indices[7], [6], [5], [4]
       vo[1] = make_uint4(va.w, va.z, va.y, va.x);  // vertex_indices[3], [2], [1], [0]
-#pragma unroll
       st32(e.w, w[0], w[1], w[2], w[3]);
       st32(e.w + 4, w[4], w[5], w[6], w[7]);
       e.n = 8;
