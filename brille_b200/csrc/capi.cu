@@ -1009,7 +1009,15 @@ extern "C" int b200_moveinto(b200_grid_t* g, const double* Q, size_t nQ, int ir,
   if (rc) return rc;
   if (nQ && (!Q || !probe)) return fail(B200_E_INVALID, "NULL buffer");
   if (nQ == 0) return B200_OK;
-  return host_pipeline(g, Q, nQ, MODE_NO_LOCATE | (ir ? MODE_IR : 0u), false, ir, nullptr, nullptr, probe);
+  uint32_t mode = MODE_NO_LOCATE;
+  switch (ir) {
+    case 0: break;                                          // moveinto
+    case 1: mode |= MODE_IR; break;                         // ir_moveinto
+    case 2: mode |= MODE_IR | MODE_NO_TAU; break;           // ir_moveinto_wedge
+    case 3: mode |= MODE_NO_MOVE | MODE_ISINSIDE; break;    // isinside
+    default: return fail(B200_E_INVALID, "b200_moveinto: ir must be 0 (moveinto), 1 (ir_moveinto), 2 (ir_moveinto_wedge) or 3 (isinside)");
+  }
+  return host_pipeline(g, Q, nQ, mode, false, ir, nullptr, nullptr, probe);
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -246,6 +246,8 @@ constexpr uint32_t MODE_NO_MOVE = 1u;    // skip moveinto/ir_moveinto (do_not_mo
 constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather than moveinto
 constexpr uint32_t MODE_NO_LOCATE = 4u;  // moveinto only (b200_moveinto)
 constexpr uint32_t MODE_SPLIT_A = 8u;    // trellis: stop after the node is found and park the point (two-kernel location)
+constexpr uint32_t MODE_NO_TAU = 16u;    // with MODE_IR: wedge rotation only, no translation (BrillouinZone::ir_moveinto_wedge)
+constexpr uint32_t MODE_ISINSIDE = 32u;  // only test the point against the first-zone planes (BrillouinZone::isinside): status bit, no failure
 
 
 // launchers (one per .cu file)

@@ -705,8 +705,14 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     uint32_t st = 0;
     if (mode & MODE_NO_MOVE) {
       q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
+      // BrillouinZone::isinside (bz.hpp:631-640): the conventional-lattice plane test moveinto re-checks its result with
+      if ((mode & MODE_ISINSIDE) && !inside_planes(bz, false, q, eps_o)) st = B200_ST_OUTSIDE_BZ;
     } else {
-      st = moveinto_one(bz, eps_w, eps_o, Qi, q, tau);
+      if (mode & MODE_NO_TAU) {  // ir_moveinto_wedge (bz_move.cpp:299-356): the rotation search on Q itself
+        q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
+      } else {
+        st = moveinto_one(bz, eps_w, eps_o, Qi, q, tau);
+      }
       if (mode & MODE_IR) {
         // ---- wedge rotation: bz_move.cpp:257-285 ----
         // fast path: signs of q on the distinct wedge-bounding planes -> operation index through a lookup table
@@ -804,7 +810,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       out.key[i] = key;
       out.rank[i] = atomicAdd(out.cell_count + key, 1u);
     }
-    f_bz += (st & B200_ST_OUTSIDE_BZ) != 0;
+    f_bz += (st & B200_ST_OUTSIDE_BZ) != 0 && !(mode & MODE_ISINSIDE);  // (isinside reports, it does not fail)
     f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
     f_find += (st & B200_ST_NOT_FOUND) != 0;
   }

@@ -224,6 +224,21 @@ class B200Grid:
         capi.check(capi.lib().b200_moveinto(self._handle, Q.ctypes.data, Q.shape[0], 0, pr.byref()))
         return pr.q_ir, pr.tau
 
+    def ir_moveinto_wedge(self, Q, threads=0):
+        """(q_ir, Ridx) like ``BrillouinZone.ir_moveinto_wedge`` (wrap/_bz.cpp:498-520): the rotation into the irreducible wedge of
+        Q itself (no translation), with the operation INDEX instead of the matrix (Q = R[Ridx] q_ir)."""
+        Q = self._check_q(Q)
+        pr = T.ProbeArrays(Q.shape[0], fields=("q_ir", "tau", "ridx", "invridx", "status"))
+        capi.check(capi.lib().b200_moveinto(self._handle, Q.ctypes.data, Q.shape[0], 2, pr.byref()))
+        return pr.q_ir, pr.ridx
+
+    def isinside(self, Q):
+        """bool per point like ``BrillouinZone.isinside`` (wrap/_bz.cpp:378-384): inside (or on the surface of) the first zone."""
+        Q = self._check_q(Q)
+        pr = T.ProbeArrays(Q.shape[0], fields=("q_ir", "tau", "ridx", "invridx", "status"))
+        capi.check(capi.lib().b200_moveinto(self._handle, Q.ctypes.data, Q.shape[0], 3, pr.byref()))
+        return (pr.status & T.ST_OUTSIDE_BZ) == 0
+
     # ------------------------------------------------------------------ device-resident variant
     def ir_interpolate_at_device(self, dQ, vals_out=None, vecs_out=None, do_not_move_points=False, check=True, stream=None):
         """torch CUDA tensors in and out (no host copies).  ``dQ``: float64 (n,3) on this grid's device."""

@@ -221,7 +221,10 @@ int b200_ir_interpolate_at_device(b200_grid_t* grid, const double* dQ, size_t nQ
 int b200_interpolate_at(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t flags,
                         void* vals_out, void* vecs_out, b200_probe_t* probe);
 /* BrillouinZone.ir_moveinto (wrap/_bz.cpp:434-463) / moveinto (:378-405) on the device; host buffers;
- * fills probe->q_ir, tau, ridx, invridx, status (x_ir if requested).  ir=0 selects moveinto.                */
+ * fills probe->q_ir, tau, ridx, invridx, status (x_ir if requested).  ir = 1 ir_moveinto, 0 moveinto,
+ * 2 ir_moveinto_wedge (wrap/_bz.cpp:498-520, bz_move.cpp:299-356: the wedge rotation of Q itself, no translation; ridx is
+ * the operation with Q = R q_ir), 3 isinside (wrap/_bz.cpp:378-384, bz.hpp:631-640: probe->status gets B200_ST_OUTSIDE_BZ
+ * for the points outside the first Brillouin zone; never fails).                                             */
 int b200_moveinto(b200_grid_t* grid, const double* Q, size_t nQ, int ir, b200_probe_t* probe);
 
 /* ---- sort() on the device --------------------------------------------------------------

@@ -460,3 +460,34 @@ def test_c5_powder_q_sharded(host, bridge):
     assert np.array_equal(sv, vals) and np.array_equal(sw, vecs)
     sg.close()
     g.close()
+
+
+@pytest.mark.parametrize("which", ["C3", "C2", "F23", "P3_timereversal"])
+def test_bz_methods_against_reference(host, bridge, which):
+    """BrillouinZone.isinside / moveinto / ir_moveinto / ir_moveinto_wedge (wrap/_bz.cpp:378-520) routed to the locate kernel
+    (SURVEY 8f rank 3), against the reference's own methods: booleans, tau and q bit for bit, the same rotation matrices."""
+    wl = W.BUILDERS[which](host) if which in W.BUILDERS else W.zoo_grid(host, which)
+    g = brille_b200.accelerate(wl.grid)
+    bz = wl.bz
+    rng = np.random.default_rng(8)
+    Q = np.vstack([rng.uniform(-1.5, 1.5, (50000, 3)), rng.integers(-4, 5, (2000, 3)) / 4.0, np.zeros((1, 3))])
+    # isinside
+    inside = g.isinside(Q)
+    assert inside.dtype == bool and np.array_equal(inside, np.asarray(bz.isinside(Q), dtype=bool))
+    assert 0 < inside.sum() < len(Q)
+    # moveinto
+    q, tau = g.moveinto(Q)
+    rq, rtau = bz.moveinto(Q)
+    assert np.array_equal(tau, rtau) and np.array_equal(q, rq)
+    assert g.isinside(q).all()
+    # ir_moveinto: q, tau, and the rotation matrices of the returned indices
+    rots = np.asarray(bridge.flatten_bz(bz)["rotations"]).reshape(-1, 3, 3)
+    q, tau, ridx, invridx = g.ir_moveinto(Q)
+    rq, rtau, rR, rinvR = bz.ir_moveinto(Q)
+    assert np.array_equal(tau, rtau) and np.array_equal(q, rq)
+    assert np.array_equal(rots[ridx], rR) and np.array_equal(rots[invridx], rinvR)
+    # ir_moveinto_wedge: no translation
+    qw, rw = g.ir_moveinto_wedge(Q)
+    rqw, rRw = bz.ir_moveinto_wedge(Q)
+    assert np.array_equal(qw, rqw) and np.array_equal(rots[rw], rRw)
+    g.close()
