@@ -907,6 +907,11 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
   size_t budget = std::min<size_t>(free_b / 4, (size_t)6 << 30);  // both stages together
   size_t chunk = std::max<size_t>(1024, budget / 2 / per_q);
   chunk = std::min(chunk, (size_t)1 << 22);
+  {  // at least ~8 chunks per call, so that the copies of one chunk hide the kernels of the next (a call that is a single chunk is
+     // H2D, kernels and D2H in series), but never so small that the cells hold only a handful of points per chunk
+    const size_t nb = (size_t)g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
+    chunk = std::min(chunk, std::max<size_t>(std::max<size_t>(32 * nb, (nQ + 7) / 8), 65536));
+  }
   if (g->host_chunk) chunk = std::min(chunk, g->host_chunk);
   if (chunk > nQ) chunk = std::max<size_t>(nQ, 1);
   unsigned long long total[N_FAIL] = {0, 0, 0, 0};

@@ -290,8 +290,8 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
 // storing the rotated 3-vector u_l = ph * R a_k of (mode b, atom k -> l) its term of
 //     F(Q, b) = sum_l c_l e^{-W_l} e^{2 pi i Q.r_l} (qv . u_l^[*])
 // is formed in registers and summed over the atoms with shuffles inside the NAT consecutive lanes that hold the atoms of one
-// mode (NAT a power of two <= 32: lane groups are aligned because the tasks of a tile are dealt r = b * NAT + k fastest and both
-// the thread count and the tasks per tile are multiples of NAT).  The scalar Gamma phase commutes with the dot product, so it is
+// mode (NAT <= 32, padded to a power of two NATP with idle lanes: lane groups are aligned because the tasks of a tile are dealt
+// r = b * NATP + k fastest and both the thread count and the tasks per tile are multiples of NATP).  The scalar Gamma phase commutes with the dot product, so it is
 // folded into the per-(point, atom) factor PH: one complex multiply per term instead of three.  One code path for every
 // point (the rotation is looked up per point), so the result does not depend on the composition of a tile or an item: it is
 // bit-reproducible across chunkings.  The eigenvectors are never written: 8 bytes per (Q, mode) leave the SM.
@@ -331,9 +331,13 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
         if ((uint32_t)t < nt) c.vals_out[(size_t)qis[t] * vrow + (size_t)b0 * no0v + r] = acc[t];
     }
   }
-  const uint32_t per_q = mb * NAT;
+  // atoms per mode padded to a power of two (NATP lanes per mode; the lanes k >= NAT idle): the lane groups stay aligned for
+  // any number of atoms <= 32
+  uint32_t NATP = 1;
+  while (NATP < NAT) NATP <<= 1;
+  const uint32_t natp_shift = 31u - (uint32_t)__clz(NATP);
+  const uint32_t per_q = mb * NATP;
   const uint32_t step_tile = (uint32_t)nthr / per_q, step_r = (uint32_t)nthr - step_tile * per_q;
-  const uint32_t nat_magic = 0xffffffffu / NAT + 1u;
   const uint32_t n_task = ntile * per_q;
   const uint32_t lane = (uint32_t)tid & 31u;
   const double sgn = c.conjugate ? -1.0 : 1.0;
@@ -345,7 +349,9 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
     if (r >= per_q) { r -= per_q; ++tile; }
     const bool live = task < n_task;
     const uint32_t tl = live ? tile : 0u, rl = live ? r : 0u;
-    const uint32_t b = NAT == 1u ? rl : __umulhi(rl, nat_magic), k = rl - b * NAT;
+    const uint32_t b = rl >> natp_shift, kp = rl & (NATP - 1u);
+    const bool atom = kp < NAT;  // (a padding lane: contributes zero)
+    const uint32_t k = atom ? kp : 0u;
     const uint32_t t0 = tl * TQ;
     const double2* src = D + (size_t)b * S + 3 * k;
     double2 acc[TQ][3];
@@ -374,13 +380,13 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
       const double dr = __fma_rn(g2, acc[t][2].x, __fma_rn(g1, acc[t][1].x, __dmul_rn(g0, acc[t][0].x)));
       const double di = sgn * __fma_rn(g2, acc[t][2].y, __fma_rn(g1, acc[t][1].y, __dmul_rn(g0, acc[t][0].y)));
       const double2 f = PH[(size_t)(t0 + t) * NAT + k];
-      double Fr = __fma_rn(-f.y, di, __dmul_rn(f.x, dr));
-      double Fi = __fma_rn(f.y, dr, __dmul_rn(f.x, di));
-      for (uint32_t o = 1; o < NAT; o <<= 1) {  // butterfly over the atoms of the mode: every lane ends with the same sum
+      double Fr = atom ? __fma_rn(-f.y, di, __dmul_rn(f.x, dr)) : 0.0;
+      double Fi = atom ? __fma_rn(f.y, dr, __dmul_rn(f.x, di)) : 0.0;
+      for (uint32_t o = 1; o < NATP; o <<= 1) {  // butterfly over the atoms of the mode: every lane ends with the same sum
         Fr += __shfl_xor_sync(0xffffffffu, Fr, o);
         Fi += __shfl_xor_sync(0xffffffffu, Fi, o);
       }
-      if (k == 0 && (uint32_t)t < nt) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
+      if (kp == 0 && (uint32_t)t < nt) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
     }
   }
 }

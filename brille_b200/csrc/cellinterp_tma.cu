@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
 bool cell_sf_fusable(const DataDev& dd, const SFDev& sf) {
   const InterpDev& v = dd.vectors;
   const uint32_t n = sf.n_atoms;
-  return v.rot_kind >= 3 && v.is_complex && v.no0 == 0 && v.no2 == 0 && v.no1 == n && n >= 1 && n <= 32 && (n & (n - 1)) == 0;
+  return v.rot_kind >= 3 && v.is_complex && v.no0 == 0 && v.no2 == 0 && v.no1 == n && n >= 1 && n <= 32;
 }
 
 uint32_t cell_tma_pick(const DataDev& dd, bool has_cubes, uint32_t preferred, size_t budget, uint32_t* mpp_out, bool sf) {

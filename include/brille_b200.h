@@ -259,7 +259,7 @@ int b200_grid_sort_pairs(b200_grid_t* grid, const uint32_t* pairs, size_t n_pair
  * and qv = q_transform Q.  The eigenvectors stay in HBM: per Q only the eigenvalue row and `modes` doubles leave the
  * device instead of 16*modes*3*atoms bytes.  Requires complex eigenvector data made of 3-vectors only, one per atom
  * (vectors.elements = {0, 3*n_atoms, 0}); anything else is B200_E_UNSUPPORTED.  The arrays are copied by set.
- * When the pipelined cell kernel runs (Gamma-rotated data, a power-of-two number of atoms <= 32, enough points) the reduction
+ * When the pipelined cell kernel runs (Gamma-rotated data, at most 32 atoms, enough points) the reduction
  * is FUSED into its finish: the eigenvectors are formed in registers, reduced with warp shuffles and never written anywhere;
  * the few points that sit on cell faces take the general kernel into a compact scratch (nQ/16 rows) and the list mode of the
  * reduction kernel.  Otherwise the path writes the eigenvectors to a device scratch and k_structure_factor reduces them.

@@ -48,8 +48,43 @@ for name in which:
     t = {k: grid.kernel_ms(k) for k in ("locate", "sort", "interpolate")}
     grid.enable_timing(False)
     bpq = grid.bytes_per_q
-    print(f"{name:7s} nQ={nq:.0e} bytes/Q={bpq:6d} step {ms:8.3f} ms  {nq/ms/1e3:.3e} Q/s  {bpq*nq/ms/1e6:7.1f} GB/s algorithmic | "
+    print(f"{name:7s} nQ={nq:.0e} bytes/Q={bpq:6d} step {ms:8.3f} ms  {nq/ms*1e3:.3e} Q/s  {bpq*nq/ms/1e6:7.1f} GB/s algorithmic | "
           + " ".join(f"{k} {v:.3f}" for k, v in t.items()), flush=True)
-    del vals, vecs, dQ
+    if name != "C1":  # the structure-factor consumer behind the path (fused where the atom count allows, else through a scratch)
+        import time
+
+        rng = np.random.default_rng(5)
+        grid.set_structure_factor(rng.normal(size=wl.n_atoms) + 1j * rng.normal(size=wl.n_atoms), positions=rng.uniform(0, 1, (wl.n_atoms, 3)),
+                                  q_transform=rng.normal(size=(3, 3)))
+        sf = torch.empty((nq, wl.modes), dtype=torch.float64, device="cuda")
+        del vecs
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            grid.ir_structure_factor_device(dQ, vals, sf)
+        e0.record()
+        for _ in range(steps):
+            grid.ir_structure_factor_device(dQ, vals, sf)
+        e1.record()
+        torch.cuda.synchronize()
+        cms = e0.elapsed_time(e1) / steps
+        grid.enable_timing(True)
+        grid.ir_structure_factor_device(dQ, vals, sf)
+        t = {k: grid.kernel_ms(k) for k in ("locate", "sort", "interpolate", "consumer")}
+        grid.enable_timing(False)
+        hq = brille_b200.PinnedArray((nq, 3), np.float64)
+        hq.array[:] = dQ.cpu().numpy()
+        hv = brille_b200.PinnedArray(tuple(vals.shape), np.float64)
+        hs = brille_b200.PinnedArray((nq, wl.modes), np.float64)
+        grid.ir_structure_factor(hq.array, out=(hv.array, hs.array))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            grid.ir_structure_factor(hq.array, out=(hv.array, hs.array))
+        dt = (time.perf_counter() - t0) / 3
+        print(f"{name:7s} structure factor: device-resident {cms:8.3f} ms  {nq/cms*1e3:.3e} Q/s | " + " ".join(f"{k} {v:.3f}" for k, v in t.items())
+              + f" | host buffers {dt*1e3:8.2f} ms  {nq/dt:.3e} Q/s ({16*wl.modes*nq/dt/1e9:.1f} GB/s D2H)", flush=True)
+        del sf, hq, hv, hs
+    else:
+        del vecs
+    del vals, dQ
     grid.close()
     torch.cuda.empty_cache()

@@ -185,7 +185,8 @@ def test_structure_factor_fused_on_degenerate_point_sets(host):
 
 @pytest.mark.gpu
 def test_structure_factor_c4_72_modes(host):
-    """BASELINE config 4 (24 atoms: not a power of two, so never fused; mode-tiled cell kernel + separate reduction)."""
+    """BASELINE config 4: 24 atoms (not a power of two: the lane groups of the fused finish are padded to 32), 72 modes staged in
+    several passes by the cell kernel, Nest grid; fused and unfused against the reference's eigenvectors."""
     import brille_b200
     from brille_b200 import workloads as W
 
@@ -193,11 +194,17 @@ def test_structure_factor_c4_72_modes(host):
     g = brille_b200.accelerate(wl.grid)
     cfg = sf_config(wl.n_atoms, 13, cartesian=True)
     g.set_structure_factor(**cfg)
-    Q = wl.make_q(20000, 21)
+    Q = wl.make_q(40000, 21)
     vals, vecs = g.ir_interpolate_at(Q)
+    want = structure_factor(Q, vecs, **cfg)
     v1, sf1 = g.ir_structure_factor(Q)
     assert np.array_equal(v1, vals)
-    assert_values_close(sf1, structure_factor(Q, vecs, **cfg))
+    assert_values_close(sf1, want)
     rv, rw = wl.grid.ir_interpolate_at(Q[:3000], True, 8)
     assert_values_close(sf1[:3000], structure_factor(Q[:3000], rw, **cfg))
+    g.set_option("sf_fused", 0)
+    v0, sf0 = g.ir_structure_factor(Q)
+    assert_values_close(sf0, want)
+    assert_values_close(sf1, sf0, rtol=1e-12)
+    assert not np.array_equal(sf1, sf0)  # (two different kernels did run)
     g.close()
