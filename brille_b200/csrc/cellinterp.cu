@@ -360,7 +360,8 @@ cudaError_t launch_interp_cell(const CellArgs& args, size_t n, cudaStream_t stre
   const DataDev& dd = args.dd;
   const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
   const size_t smem = plan_smem(args.n_cubes ? 8u : 4u, args.modes_per_pass, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma).total;
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_interp_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -491,15 +491,18 @@ template <int TQ, bool SF>
 static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n, int sm_count,
                                    const TmaPlan& plan, cudaStream_t stream) {
   const size_t smem = plan.total;
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   const size_t max_items = (n + args.bk.chunk - 1) / args.bk.chunk + (args.bk.n_buckets - 1);
-  static int ctas_per_sm = 0;
-  static size_t occ_smem = 0;
+  static int ctas_dev[MAX_DEVICES] = {};
+  static size_t occ_smem_dev[MAX_DEVICES] = {};
+  int& ctas_per_sm = ctas_dev[current_device_slot()];
+  size_t& occ_smem = occ_smem_dev[current_device_slot()];
   if (occ_smem != smem) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ, SF>, 256, smem);
     if (e != cudaSuccess) return e;

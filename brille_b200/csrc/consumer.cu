@@ -127,7 +127,9 @@ cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const doub
   uint32_t QB = 2048u / (MN ? MN : 1u);
   QB = QB < 1u ? 1u : (QB > 64u ? 64u : QB);
   const size_t smem = (size_t)QB * c.n_atoms * 16 + (size_t)QB * MN * 16 + (size_t)QB * 24;
-  static size_t configured = 48 * 1024;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
+  if (configured < 48 * 1024) configured = 48 * 1024;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_structure_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -250,6 +250,15 @@ constexpr uint32_t MODE_NO_TAU = 16u;    // with MODE_IR: wedge rotation only, n
 constexpr uint32_t MODE_ISINSIDE = 32u;  // only test the point against the first-zone planes (BrillouinZone::isinside): status bit, no failure
 
 
+// Function attributes (dynamic shared memory limit, occupancy) belong to a device: launchers that cache them index the cache by
+// the current device, so that one process can drive several GPUs (brille_b200/sharding.py: ShardedGrid).
+constexpr int MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+  return d;
+}
+
 // launchers (one per .cu file)
 cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, size_t n, uint32_t mode, double eps_w,
                           double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,

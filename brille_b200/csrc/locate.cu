@@ -939,7 +939,8 @@ static cudaError_t launch_kind(const BZDev* bzg, const GridDev& gd, const double
                                cudaStream_t stream) {
   const int threads = 128;
   const size_t smem = locate_smem_bytes(gd, mode);
-  static bool attr_set = false;
+  static bool attr_set_dev[MAX_DEVICES] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaFuncSetAttribute(k_locate<KIND, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;

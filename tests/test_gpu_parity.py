@@ -491,3 +491,31 @@ def test_bz_methods_against_reference(host, bridge, which):
     rqw, rRw = bz.ir_moveinto_wedge(Q)
     assert np.array_equal(qw, rqw) and np.array_equal(rots[rw], rRw)
     g.close()
+
+
+def test_sharded_grid_on_two_devices(host):
+    """One process driving two GPUs (ShardedGrid: a handle and a host thread per device, Q cut into contiguous row blocks, no
+    collective): bit-identical to the single-device call.  Needs two visible devices."""
+    import torch
+
+    from brille_b200.sharding import ShardedGrid
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    wl = W.c3_p63mmc(host, density=500)
+    Q = wl.make_q(400_001, 5)
+    g = brille_b200.accelerate(wl.grid, device=0)
+    vals, vecs = g.ir_interpolate_at(Q)
+    g.close()
+    sg = ShardedGrid(wl.grid, [0, 1])
+    sv, sw = sg.ir_interpolate_at(Q)
+    assert np.array_equal(sv, vals) and np.array_equal(sw, vecs)
+    sg.close()
+    g1 = brille_b200.accelerate(wl.grid, device=1)  # the second device on its own: structure factor, fused and not
+    rng = np.random.default_rng(1)
+    g1.set_structure_factor(rng.normal(size=4) + 1j * rng.normal(size=4), positions=rng.uniform(0, 1, (4, 3)))
+    v1, sf1 = g1.ir_structure_factor(Q)
+    g1.set_option("sf_fused", 0)
+    v0, sf0 = g1.ir_structure_factor(Q)
+    assert np.array_equal(v1, vals) and rel_close(sf1, sf0) <= 1e-12
+    g1.close()
