@@ -34,7 +34,7 @@ METRIC = "Q-points/sec interpolated (eigvals+eigvecs)"
 UNIT = "Q/s"
 NQ = 10_000_000           # Q per GPU per step (BASELINE.json configs[2])
 E2E_NQ = 2_000_000        # Q per e2e step (host buffers; the rate is flat in nQ, 24 GB of pinned output is not)
-CPU_SAMPLE_NQ = 200_000   # bounded sample for the CPU reference legs
+CPU_SAMPLE_NQ = int(os.environ.get("BENCH_CPU_SAMPLE_NQ", "200000"))  # bounded sample for the CPU reference legs
 Q_SEED = 3
 
 
