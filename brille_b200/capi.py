@@ -11,7 +11,7 @@ import os
 from . import tables as T
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbrille_b200.so")
+LIB_PATH = os.environ.get("BRILLE_B200_LIB") or os.path.join(HERE, "libbrille_b200.so")  # (the override is for A/B timing of builds)
 
 #: every symbol include/brille_b200.h declares
 EXPORTS = (

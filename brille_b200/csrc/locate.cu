@@ -830,34 +830,26 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
   const TrellisDev& tr = gd.tr;
   const BZDev& bz = *bzg;  // only the default tolerance pair is read
   unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
-  // software pipeline over the grid-stride loop: the sort order is loaded two trips ahead and the parked point one trip
-  // ahead, so that neither of the two dependent gathers is waited for
+  // software pipeline over the grid-stride loop: the sort order is loaded two trips ahead and the parked point of the next trip
+  // is pulled into L2 with a prefetch (no registers held across the trip: holding the prefetched point in registers made the
+  // compiler spill it, and the spill store waits for the load it was meant to hide)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t i_cur = p < n ? order[p] : 0u, i_nxt = p + stride < n ? order[p + stride] : 0u;
-  double2 pa = make_double2(0.0, 0.0), pb = pa;
-  if (p < n) {
-    const double2* src = reinterpret_cast<const double2*>(out.parked + i_cur);
-    pa = src[0];
-    pb = src[1];
-  }
   for (; p < n; p += stride) {
     const uint32_t i_nn = p + 2 * stride < n ? order[p + 2 * stride] : 0u;
-    double2 na = make_double2(0.0, 0.0), nb = na;
-    if (p + stride < n) {
-      const double2* src = reinterpret_cast<const double2*>(out.parked + i_nxt);
-      na = src[0];
-      nb = src[1];
-    }
+    if (p + stride < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(out.parked + i_nxt));
     const size_t i = i_cur;
     ParkedPoint pp;
-    pp.x[0] = pa.x; pp.x[1] = pa.y; pp.x[2] = pb.x;
-    pp.rot_st = (uint32_t)__double2loint(pb.y);
-    pp.cell = (uint32_t)__double2hiint(pb.y);
+    {
+      const double2* src = reinterpret_cast<const double2*>(out.parked + i);
+      const double2 pa = src[0], pb = src[1];
+      pp.x[0] = pa.x; pp.x[1] = pa.y; pp.x[2] = pb.x;
+      pp.rot_st = (uint32_t)__double2loint(pb.y);
+      pp.cell = (uint32_t)__double2hiint(pb.y);
+    }
     i_cur = i_nxt;
     i_nxt = i_nn;
-    pa = na;
-    pb = nb;
     uint32_t st = pp.rot_st >> 16;
     const uint32_t cell = pp.cell;
     const int invridx = (int)((pp.rot_st >> 8) & 0xffu);
