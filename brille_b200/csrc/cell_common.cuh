@@ -341,6 +341,7 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
   const uint32_t n_task = ntile * per_q;
   const uint32_t lane = (uint32_t)tid & 31u;
   const double sgn = c.conjugate ? -1.0 : 1.0;
+  const uint32_t dstep = mpp * S;  // elements between the rows of two corners
   uint32_t tile = (uint32_t)tid / per_q, r = (uint32_t)tid - tile * per_q;
   // The loop is WARP-uniform (it runs while the first lane of the warp has a task; lanes past the end redo task 0 and store
   // nothing) and so is everything inside it (the points past the end of the last tile carry zero weights and are only kept from
@@ -355,13 +356,25 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
     const uint32_t t0 = tl * TQ;
     const double2* src = D + (size_t)b * S + 3 * k;
     double2 acc[TQ][3];
-#pragma unroll
-    for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
-    for (int i = 0; i < NV; ++i) {
-      const double2* x = src + (size_t)i * mpp * S;
+    const double2* x = src;
+    const double* wp = W + t0;
+    {  // first corner: w * x (== fma(w, x, 0) up to the sign of a zero) instead of zeroing 6 * TQ accumulators first
       const double2 x0 = x[0], x1 = x[1], x2 = x[2];
       double w[TQ];
-      load_tile<TQ>(W + (size_t)i * CH + t0, w);
+      load_tile<TQ>(wp, w);
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) {
+        acc[t][0] = make_double2(__dmul_rn(w[t], x0.x), __dmul_rn(w[t], x0.y));
+        acc[t][1] = make_double2(__dmul_rn(w[t], x1.x), __dmul_rn(w[t], x1.y));
+        acc[t][2] = make_double2(__dmul_rn(w[t], x2.x), __dmul_rn(w[t], x2.y));
+      }
+    }
+    for (int i = 1; i < NV; ++i) {  // (running pointers: no multiplications in the loop)
+      x += dstep;
+      wp += CH;
+      const double2 x0 = x[0], x1 = x[1], x2 = x[2];
+      double w[TQ];
+      load_tile<TQ>(wp, w);
 #pragma unroll
       for (int t = 0; t < TQ; ++t) {
         acc[t][0].x = __fma_rn(w[t], x0.x, acc[t][0].x); acc[t][0].y = __fma_rn(w[t], x0.y, acc[t][0].y);
@@ -382,10 +395,11 @@ __device__ __forceinline__ void cell_sf_pass(const CellPass& c, int tid, int nth
       const double2 f = PH[(size_t)(t0 + t) * NAT + k];
       double Fr = atom ? __fma_rn(-f.y, di, __dmul_rn(f.x, dr)) : 0.0;
       double Fi = atom ? __fma_rn(f.y, dr, __dmul_rn(f.x, di)) : 0.0;
-      for (uint32_t o = 1; o < NATP; o <<= 1) {  // butterfly over the atoms of the mode: every lane ends with the same sum
-        Fr += __shfl_xor_sync(0xffffffffu, Fr, o);
-        Fi += __shfl_xor_sync(0xffffffffu, Fi, o);
-      }
+      // butterfly over the atoms of the mode (every lane ends with the same sum); the stages are spelled out, under uniform
+      // predicates, so that no loop counter lives next to the accumulators
+#define B200_SF_STAGE(o_) if (NATP > (o_)) { Fr += __shfl_xor_sync(0xffffffffu, Fr, (o_)); Fi += __shfl_xor_sync(0xffffffffu, Fi, (o_)); }
+      B200_SF_STAGE(1) B200_SF_STAGE(2) B200_SF_STAGE(4) B200_SF_STAGE(8) B200_SF_STAGE(16)
+#undef B200_SF_STAGE
       if (kp == 0 && (uint32_t)t < nt) c.sf_out[(size_t)qis[t] * M + b0 + b] = __fma_rn(Fi, Fi, __dmul_rn(Fr, Fr));
     }
   }

