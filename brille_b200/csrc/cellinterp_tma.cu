@@ -432,6 +432,48 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// diagnostic: the output stores of the kernel above on their own -- same grid, same deal of the work items, same rows, same
+// 48-byte pieces per lane in the same order, constants instead of results, nothing else (no staging, no tables, no barriers).
+// What it reaches is the ceiling of the store pattern; the difference to the real kernel is what the rest of the kernel costs.
+// (option "replay_stores"; profiles/README.md)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_store_replay(const __grid_constant__ CellArgs a) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const InterpDev& vecs = a.dd.vectors;
+  const uint32_t M = vecs.branches, S = vecs.span, NAT = vecs.no1;
+  const size_t wrow = (size_t)M * S;
+  const uint32_t n_items = a.bk.n_items[0];
+  const uint32_t per_q = M * NAT;
+  for (uint32_t l = 0;; ++l) {
+    const uint32_t gi = GLOBAL_ITEM(l);
+    if (gi >= n_items) break;
+    const CellItem it = a.bk.items[gi];
+    const uint32_t ntile = (it.len + 3) / 4;
+    for (uint32_t task = tid; task < ntile * per_q; task += nthr) {
+      const uint32_t tile = task / per_q, r = task - tile * per_q, t0 = tile * 4;
+      double2* const out_base = reinterpret_cast<double2*>(a.vecs_out) + 3 * (size_t)r;
+      const double2 c0 = make_double2((double)task, 1.0), c1 = make_double2(2.0, (double)l);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t0 + t >= it.len) break;
+        const uint32_t q = __ldg(a.bk.order + it.start + t0 + t);
+        store48(out_base + (size_t)q * wrow, c0, c1, c0);
+      }
+    }
+  }
+}
+
+cudaError_t launch_store_replay(const CellArgs& args, size_t n, int sm_count, cudaStream_t stream) {
+  const size_t max_items = (n + args.bk.chunk - 1) / args.bk.chunk + (args.bk.n_buckets - 1);
+  size_t grid = (size_t)sm_count * 2;
+  const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
+  if (grid > max_blocks) grid = max_blocks;
+  if (grid == 0) return cudaSuccess;
+  k_store_replay<<<(unsigned)grid, 256, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // modes per pass / points per item of the pipelined kernel for `budget` bytes of dynamic shared memory

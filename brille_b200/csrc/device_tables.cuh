@@ -281,6 +281,7 @@ cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vert
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
                                    int sm_count, cudaStream_t stream, int tile);
 bool cell_sf_fusable(const DataDev& dd, const SFDev& sf);
+cudaError_t launch_store_replay(const CellArgs& args, size_t n, int sm_count, cudaStream_t stream);
 
 // device work space of sort() (sortpairs.cu), kept by the grid between calls
 struct SortWorkspace {

@@ -73,6 +73,34 @@ class ShardedGrid:
             raise errors[0]
         return vals, vecs
 
+    def set_structure_factor(self, *args, **kwargs):
+        for g in self.grids:
+            g.set_structure_factor(*args, **kwargs)
+
+    def ir_structure_factor(self, Q, do_not_move_points=False):
+        """``(vals, sf)`` of :meth:`B200Grid.ir_structure_factor`, the shards reduced on their own devices."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        g0 = self.grids[0]
+        vals = np.empty((len(Q),) + g0._vals_shape, g0._vals_dtype)
+        sf = np.empty((len(Q), int(g0._data_tables.vectors.branches)), np.float64)
+        errors = []
+
+        def work(rank, grid):
+            lo, hi = shard_bounds(len(Q), rank, len(self.grids))
+            try:
+                grid.ir_structure_factor(Q[lo:hi], do_not_move_points=do_not_move_points, out=(vals[lo:hi], sf[lo:hi]))
+            except Exception as e:  # noqa: BLE001 - re-raised below, all-or-nothing like the reference
+                errors.append(e)
+
+        ts = [threading.Thread(target=work, args=(r, g)) for r, g in enumerate(self.grids)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errors:
+            raise errors[0]
+        return vals, sf
+
     def close(self):
         for g in self.grids:
             g.close()

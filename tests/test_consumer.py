@@ -212,3 +212,26 @@ def test_structure_factor_c4_72_modes(host):
     assert_values_close(sf1, sf0, rtol=1e-12)
     assert not np.array_equal(sf1, sf0)  # (two different kernels did run)
     g.close()
+
+
+@pytest.mark.gpu
+def test_structure_factor_sharded(host):
+    """Q cut into contiguous row blocks over several handles (here: twice the one device), each shard reduced where it was computed."""
+    import brille_b200
+    from brille_b200 import workloads as W
+    from brille_b200.sharding import ShardedGrid
+
+    wl = W.c3_p63mmc(host, density=500)
+    cfg = sf_config(wl.n_atoms, 5, cartesian=True)
+    Q = wl.make_q(250_001, 2)
+    g = brille_b200.accelerate(wl.grid)
+    g.set_structure_factor(**cfg)
+    vals, sf = g.ir_structure_factor(Q)
+    g.close()
+    sg = ShardedGrid(wl.grid, [0, 0])
+    sg.set_structure_factor(**cfg)
+    sv, ssf = sg.ir_structure_factor(Q)
+    assert np.array_equal(sv, vals) and np.array_equal(ssf, sf)
+    with pytest.raises(RuntimeError):
+        sg.ir_structure_factor(np.full((4, 3), 7.3), do_not_move_points=True)
+    sg.close()
