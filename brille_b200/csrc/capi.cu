@@ -205,7 +205,6 @@ struct b200_grid {
   bool has_sf = false;
   void* sf_scratch = nullptr;
   size_t sf_scratch_bytes = 0;
-  int staged_stores = 0;        // pipelined cell kernel: eigenvector rows through per-warp shared-memory buffers + bulk copies
   int replay_stores = 0;        // diagnostic: run k_store_replay after the pipelined cell kernel and time it ("replay")
   int sf_fused = 1;             // 1: reduce inside the pipelined cell kernel whenever possible (the eigenvectors never reach HBM)
   double* sf_gscratch = nullptr;  // device-buffer entry point: compact rows of the general-kernel points
@@ -811,13 +810,13 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
       a.sf = g->sf;
       a.vecs_out = nullptr;
     }
-    if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile, g->staged_stores));
+    if (tma) CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile));
     else CU(launch_interp_cell(a, n, stream));
     if (tma && !fz && g->replay_stores && g->timing) {  // diagnostic: the store pattern on its own, then the real kernel once more
       cudaEventRecord(g->ev[4], stream);
       CU(launch_store_replay(a, n, g->sm_count, stream));
       cudaEventRecord(g->ev[5], stream);
-      CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile, g->staged_stores));
+      CU(launch_interp_cell_tma(a, g->ct, g->cell_table, n, g->sm_count, stream, g->tile));
       cudaEventSynchronize(g->ev[5]);
       note_time(g, "replay", g->ev[4], g->ev[5]);
     }
@@ -1231,8 +1230,6 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   } else if (n == "chunk") {
     if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
-  } else if (n == "staged_stores") {
-    g->staged_stores = value != 0;
   } else if (n == "replay_stores") {
     g->replay_stores = value != 0;
   } else if (n == "sf_fused") {

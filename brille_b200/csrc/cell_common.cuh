@@ -104,7 +104,6 @@ struct CellPass {
   double* vals_out;
   double* vecs_out;
   uint32_t* task_ctr;  // shared counter (zero at the start of the pass) for the dynamic deal of tasks, or nullptr
-  unsigned char* stage;  // cell_compute_pass_staged: STAGE_BYTES_PER_WARP of shared memory per warp
   // fused structure-factor finish (cell_sf_pass): PH then holds the combined per-(point, SOURCE atom) factor
   //   coef_l e^{-W_l} e^{2 pi i Q.r_l} * [conj](Gamma phase)   with l = F0(k, R) the destination atom,
   const double* QV;   // [CH][3] g = (T Q)^T R of every point (R the point's rotation): the finish is g . a
@@ -285,177 +284,6 @@ __device__ __forceinline__ void cell_compute_pass(const CellPass& c, int tid, in
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Staged output (decoupled stores).  The pass above stores every rotated 3-vector with two store instructions per point, issued
-// by the warps that do the arithmetic.  Here a warp collects the 32 x 48 bytes it produces for a point in a private shared-memory
-// buffer -- contiguous in the output row: the 32 tasks of a round are consecutive (mode, atom) pairs, and the atom permutation
-// stays inside aligned groups of NAT lanes -- and one lane hands the span(s) to the bulk-copy engine (cp.async.bulk shared ->
-// global).  The arithmetic warps never wait for the memory system: a buffer is only waited for (wait_group.read) two points
-// later.  Same arithmetic, same bytes at the same addresses as the direct path; rounds in which some lane cannot take the
-// branch-free finish (a tile that straddles two operations, the last partial tile) use the direct path as they are.
-// Needs Gamma-rotated data, NAT a power of two <= 32 and at least 32 tasks per tile (else every round takes the direct path).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t STAGE_BYTES_PER_WARP = 2u * 32u * 48u;  // two buffers of one point each
-
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int TQ>
-__device__ __forceinline__ void cell_compute_pass_staged(const CellPass& c, int tid, int nthr) {
-  const double2* D = c.D;
-  const double* V = c.V;
-  const double* W = c.W;
-  const double2* PH = c.PH;
-  const double* RS = c.RS;
-  const uint32_t* F0 = c.F0;
-  const uint32_t* QI = c.QI;
-  const uint32_t* RI = c.RI;
-  const uint32_t CH = c.CH, mpp = c.mpp, mb = c.mb, b0 = c.b0, M = c.M, S = c.S, NAT = c.NAT, no0v = c.no0v, G = c.G;
-  const int NV = c.NV;
-  const size_t vrow = (size_t)M * no0v, wrow = (size_t)M * S;
-  const uint32_t len = c.len;
-  const uint32_t ntile = (len + TQ - 1) / TQ;
-  {  // eigenvalues: as in cell_compute_pass
-    const uint32_t per_v = mb * no0v;
-    for (uint32_t task = tid; task < ntile * per_v; task += nthr) {
-      const uint32_t tile = task / per_v, r = task - tile * per_v, t0 = tile * TQ;
-      double acc[TQ];
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) acc[t] = 0.0;
-      for (int i = 0; i < NV; ++i) {
-        const double v = V[(size_t)i * mpp * no0v + r];
-        double w[TQ];
-        load_tile<TQ>(W + (size_t)i * CH + t0, w);
-#pragma unroll
-        for (int t = 0; t < TQ; ++t) acc[t] = __fma_rn(w[t], v, acc[t]);
-      }
-      const uint32_t nt = min((uint32_t)TQ, len - t0);
-      uint32_t qis[TQ];
-      load_tile<TQ>(QI + t0, qis);
-#pragma unroll
-      for (int t = 0; t < TQ; ++t)
-        if ((uint32_t)t < nt) c.vals_out[(size_t)qis[t] * vrow + (size_t)b0 * no0v + r] = acc[t];
-    }
-  }
-  const uint32_t per_q = mb * NAT;
-  const uint32_t nat_magic = 0xffffffffu / NAT + 1u, pq_magic = 0xffffffffu / per_q + 1u;
-  const uint32_t n_task = ntile * per_q;
-  const uint32_t lane = (uint32_t)tid & 31u;
-  const bool stage_ok = per_q >= 32u && NAT <= 32u && (NAT & (NAT - 1u)) == 0u;
-  unsigned char* const stage = c.stage + (size_t)((uint32_t)tid >> 5) * STAGE_BYTES_PER_WARP;
-  double2* const vecs2 = reinterpret_cast<double2*>(c.vecs_out);
-  // warps draw rounds of 32 consecutive tasks from the shared counter (cf. cell_compute_pass); the round is executed by the whole
-  // warp: lanes past the end redo the round's first task and keep their result to themselves
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(c.task_ctr, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n_task) break;
-    const bool live = base + lane < n_task;
-    const uint32_t task = live ? base + lane : base;
-    const uint32_t tile = per_q == 1u ? task : __umulhi(task, pq_magic), r = task - tile * per_q;
-    const uint32_t b = NAT == 1u ? r : __umulhi(r, nat_magic), k = r - b * NAT;
-    const uint32_t t0 = tile * TQ;
-    const double2* src = D + (size_t)b * S + 3 * k;
-    double2 acc[TQ][3];
-#pragma unroll
-    for (int t = 0; t < TQ; ++t) acc[t][0] = acc[t][1] = acc[t][2] = make_double2(0.0, 0.0);
-    for (int i = 0; i < NV; ++i) {
-      const double2* x = src + (size_t)i * mpp * S;
-      const double2 x0 = x[0], x1 = x[1], x2 = x[2];
-      double w[TQ];
-      load_tile<TQ>(W + (size_t)i * CH + t0, w);
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) {
-        acc[t][0].x += w[t] * x0.x; acc[t][0].y += w[t] * x0.y;
-        acc[t][1].x += w[t] * x1.x; acc[t][1].y += w[t] * x1.y;
-        acc[t][2].x += w[t] * x2.x; acc[t][2].y += w[t] * x2.y;
-      }
-    }
-    const uint32_t nt = min((uint32_t)TQ, len - t0);
-    uint32_t rrs[TQ], qis[TQ];
-    load_tile<TQ>(RI + t0, rrs);
-    load_tile<TQ>(QI + t0, qis);
-    const bool fast = nt == TQ && (rrs[0] & 0xffffu) == (rrs[TQ - 1] & 0xffffu);
-    if (stage_ok && __all_sync(0xffffffffu, fast)) {
-      // geometry of the round: lanes [0, nA) are tasks rA.. of tile A, lanes [nA, nA + nB) are tasks 0.. of the next tile
-      const uint32_t tileA = __shfl_sync(0xffffffffu, tile, 0), rA = __shfl_sync(0xffffffffu, r, 0);
-      const uint32_t n_live = min(32u, n_task - base);
-      const uint32_t nA = min(n_live, per_q - rA), nB = n_live - nA;
-      const uint32_t ri = rrs[0] & 0xffffu;
-      const uint32_t dest = F0[k * G + ri];
-      const double* Rs = RS + 9 * ri;
-      const double R[9] = {Rs[0], Rs[1], Rs[2], Rs[3], Rs[4], Rs[5], Rs[6], Rs[7], Rs[8]};
-      const uint32_t slot = lane - k + dest;  // the destination atom's place inside the aligned group of NAT lanes
-      const double2* php = PH + (size_t)t0 * NAT + k;
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) {
-        double2 u0, u1, u2;
-        rotate_phase(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true, u0, u1, u2);
-        unsigned char* const buf = stage + (uint32_t)(t & 1) * (32u * 48u);
-        if (lane == 0) bulk_wait_read_1();  // the bulk copy that read this buffer two points ago is done with it
-        __syncwarp();
-        if (live) {
-          double2* const s2 = reinterpret_cast<double2*>(buf + slot * 48u);
-          s2[0] = u0;
-          s2[1] = u1;
-          s2[2] = u2;
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t qA = QI[tileA * TQ + t];
-          bulk_s2g(vecs2 + (size_t)qA * wrow + (size_t)b0 * S + 3 * (size_t)rA, buf, nA * 48u);
-          if (nB) {
-            const uint32_t qB = QI[(tileA + 1u) * TQ + t];
-            bulk_s2g(vecs2 + (size_t)qB * wrow + (size_t)b0 * S, buf + nA * 48u, nB * 48u);
-          }
-          bulk_commit();
-        }
-      }
-      continue;
-    }
-    if (!live) continue;
-    // ---- direct path (as in cell_compute_pass) ---------------------------------------------------------------------------------
-    double2* const out_base = vecs2 + (size_t)(b0 + b) * S;
-    if (fast && ((wrow & 1) == 0)) {
-      const uint32_t ri = rrs[0] & 0xffffu;
-      const uint32_t dest = F0[k * G + ri];
-      double2* const out0 = out_base + 3 * dest;
-      const bool even = (reinterpret_cast<uintptr_t>(out0) & 31u) == 0;
-      const double* Rs = RS + 9 * ri;
-      const double* r0 = Rs + (even ? 0 : 3);
-      const double* r1 = Rs + (even ? 3 : 6);
-      const double* r2 = Rs + (even ? 6 : 0);
-      const double R[9] = {r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]};
-      const uint32_t off32 = even ? 0u : 1u, off16 = even ? 2u : 0u;
-      const double2* php = PH + (size_t)t0 * NAT + k;
-#pragma unroll
-      for (int t = 0; t < TQ; ++t) {
-        double2 u0, u1, u2;
-        rotate_phase(R, acc[t][0], acc[t][1], acc[t][2], php[(size_t)t * NAT], true, u0, u1, u2);
-        double2* const o = out0 + (size_t)qis[t] * wrow;
-        store32(o + off32, u0, u1);
-        store16(o + off16, u2);
-      }
-      continue;
-    }
-#pragma unroll
-    for (int t = 0; t < TQ; ++t) {
-      if ((uint32_t)t >= nt) break;
-      const uint32_t ri = rrs[t] & 0xffffu;
-      const uint32_t dest = F0[k * G + ri];
-      rotate_phase_store(RS + 9 * ri, acc[t][0], acc[t][1], acc[t][2], PH[(size_t)(t0 + t) * NAT + k], true, out_base + (size_t)qis[t] * wrow + 3 * dest);
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fused structure-factor finish: the same weighted sum and rotation as cell_compute_pass, but instead of

@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(256) k_build_cell_table(DataDev dd, const uint
 // shared memory plan of the pipelined kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct TmaPlan {
-  uint32_t D0, D1, RW, W, PH, RS, F0, GV, QI, RI, QV, ST, BAR, per_set, total;
+  uint32_t D0, D1, RW, W, PH, RS, F0, GV, QI, RI, QV, BAR, per_set, total;
 };
 __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, uint32_t S, uint32_t no0v, uint32_t chunk,
-                                                 uint32_t n_at, uint32_t G, bool gamma, bool sf = false, bool staged = false) {
+                                                 uint32_t n_at, uint32_t G, bool gamma, bool sf = false) {
   TmaPlan p;
   uint32_t o = 0;
   auto take = [&](size_t bytes) { uint32_t at = o; o += (uint32_t)((bytes + 15) / 16 * 16); return at; };
@@ -142,7 +142,6 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
   p.RS = take((size_t)G * 9 * 8);
   p.F0 = take(gamma ? (size_t)n_at * G * 4 : 0);
   p.GV = take(gamma ? (size_t)n_at * G * 24 : 0);
-  p.ST = take(staged ? (size_t)(256 / 32) * STAGE_BYTES_PER_WARP : 0);  // staged output: per-warp buffers (256 threads)
   p.BAR = take(32);
   p.total = o;
   return p;
@@ -155,8 +154,7 @@ constexpr uint32_t NO_ITEM = 0xffffffffu;
 constexpr uint32_t ITEM_BLOCK = 8;
 
 // SF: fused structure-factor finish (cell_sf_pass): |F|^2 per (Q, mode) instead of the eigenvectors (a.sf_out, a.Q, a.sf)
-// STAGE: the eigenvector rows leave through per-warp shared-memory buffers and bulk copies (cell_compute_pass_staged)
-template <int TQ, bool SF, bool STAGE = false>
+template <int TQ, bool SF>
 __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const __grid_constant__ CellArgs a, const __grid_constant__ CellTableDev ct,
                                                             const unsigned char* __restrict__ table, const __grid_constant__ TmaPlan pl) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -411,9 +409,6 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
         cp.sf_out = a.sf_out;
         cp.conjugate = a.sf.conjugate;
         cell_sf_pass<TQ>(cp, tid, nthr);
-      } else if (STAGE) {
-        cp.stage = smem + pl.ST;
-        cell_compute_pass_staged<TQ>(cp, tid, nthr);
       } else {
         cell_compute_pass<TQ>(cp, tid, nthr);
       }
@@ -434,7 +429,6 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
     LOAD_ITEM(it + 3, nn_key, nn_start, nn_len);
     set ^= 1;
   }
-  if (STAGE && (tid & 31) == 0) bulk_wait_all();  // the last bulk stores of this warp have left shared memory and arrived
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -535,14 +529,14 @@ cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vert
   return cudaGetLastError();
 }
 
-template <int TQ, bool SF, bool STAGE = false>
+template <int TQ, bool SF>
 static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n, int sm_count,
                                    const TmaPlan& plan, cudaStream_t stream) {
   const size_t smem = plan.total;
   static size_t configured_dev[MAX_DEVICES] = {};
   size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ, SF, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_interp_cell_tma<TQ, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -552,7 +546,7 @@ static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct,
   int& ctas_per_sm = ctas_dev[current_device_slot()];
   size_t& occ_smem = occ_smem_dev[current_device_slot()];
   if (occ_smem != smem) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ, SF, STAGE>, 256, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_interp_cell_tma<TQ, SF>, 256, smem);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
     occ_smem = smem;
@@ -561,19 +555,15 @@ static cudaError_t launch_tma_tile(const CellArgs& args, const CellTableDev& ct,
   const size_t max_blocks = (max_items + ITEM_BLOCK - 1) / ITEM_BLOCK;
   if (grid > max_blocks) grid = max_blocks;
   if (grid == 0) return cudaSuccess;
-  k_interp_cell_tma<TQ, SF, STAGE><<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
+  k_interp_cell_tma<TQ, SF><<<(unsigned)grid, 256, smem, stream>>>(args, ct, table, plan);
   return cudaGetLastError();
 }
 
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
-                                   int sm_count, cudaStream_t stream, int tile, int staged) {
+                                   int sm_count, cudaStream_t stream, int tile) {
   const DataDev& dd = args.dd;
   const bool gamma = (args.ir ? dd.vectors.rot_kind : -1) >= 3;
   const bool sf = args.sf_out != nullptr;
-  if (staged && !sf && tile == 4 && gamma) {  // staged output: only if its buffers still fit next to everything else at 2 CTAs/SM
-    const TmaPlan ps = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma, false, true);
-    if (ps.total + 256 <= 113 * 1024) return launch_tma_tile<4, false, true>(args, ct, table, n, sm_count, ps, stream);
-  }
   const TmaPlan plan = plan_smem_tma(args.n_cubes ? 8u : 4u, ct.mpp, dd.vectors.span, dd.values.span, args.bk.chunk, dd.vectors.no1, dd.n_ops, gamma, sf);
   if (sf) return tile == 2 ? launch_tma_tile<2, true>(args, ct, table, n, sm_count, plan, stream) : launch_tma_tile<4, true>(args, ct, table, n, sm_count, plan, stream);
   if (tile == 2) return launch_tma_tile<2, false>(args, ct, table, n, sm_count, plan, stream);

@@ -279,7 +279,7 @@ CellTableDev cell_table_layout(const DataDev& dd, uint32_t n_cubes, uint32_t n_t
 cudaError_t launch_build_cell_table(const DataDev& dd, const uint32_t* cube_vertices, const uint32_t* tet_vertices,
                                     const CellTableDev& ct, unsigned char* table, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp_cell_tma(const CellArgs& args, const CellTableDev& ct, const unsigned char* table, size_t n,
-                                   int sm_count, cudaStream_t stream, int tile, int staged = 0);
+                                   int sm_count, cudaStream_t stream, int tile);
 bool cell_sf_fusable(const DataDev& dd, const SFDev& sf);
 cudaError_t launch_store_replay(const CellArgs& args, size_t n, int sm_count, cudaStream_t stream);
 
