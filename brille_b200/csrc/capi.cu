@@ -423,6 +423,27 @@ static void pack_tet(double* p, const double* c, double c3, const double* verts,
   p[17] = 0.0;
 }
 
+// uniform bins over the bounding box of the vertices (Nest / Mesh): the buckets of the two-kernel location
+static void build_bins(b200_grid* g, const double* vertices, size_t n_vertices) {
+  BinDev& b = g->gd.bins;
+  b = BinDev{};
+  if (!n_vertices) return;
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (size_t v = 0; v < n_vertices; ++v)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], vertices[3 * v + d]);
+      hi[d] = std::max(hi[d], vertices[3 * v + d]);
+    }
+  b.total = 1;
+  for (int d = 0; d < 3; ++d) {
+    const double ext = hi[d] - lo[d];
+    b.n[d] = ext > 0.0 ? 16 : 1;
+    b.lo[d] = lo[d];
+    b.inv[d] = ext > 0.0 ? b.n[d] / ext : 0.0;
+    b.total *= (uint32_t)b.n[d];
+  }
+}
+
 static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
   NestDev& d = g->gd.ne;
   DevPool& pool = g->structure_pool;
@@ -447,6 +468,7 @@ static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
   CU(pool.upload(t->child_end, (size_t)t->n_nodes, &d.child_end));
   g->n_vertices = t->n_vertices;
   g->gd.cells.n_cubes = 0;
+  build_bins(g, t->vertices, t->n_vertices);
   g->gd.cells.n_tets = t->n_nodes;  // bucket key = node index (only leaves ever receive points)
   g->gd.cells.tet_vertices = d.node_vertices;
   return B200_OK;
@@ -480,6 +502,7 @@ static int build_mesh(b200_grid* g, const b200_mesh_tables_t* t) {
   CU(pool.upload(t->tets, (size_t)ntot * 4, &d.tets));
   CU(pool.upload(t->conn_offset, (size_t)nconn + (L > 1 ? 1 : 0), &d.conn_offset));
   CU(pool.upload(t->conn_index, L > 1 ? (size_t)t->conn_offset[nconn] : 0, &d.conn_index));
+  build_bins(g, t->vertices + 3 * (size_t)t->vert_offset[L - 1], t->vert_offset[L] - t->vert_offset[L - 1]);
   g->n_vertices = t->vert_offset[L] - t->vert_offset[L - 1];  // data live on the finest layer's vertices
   g->gd.cells.n_cubes = 0;
   g->gd.cells.n_tets = d.n_tets_last;
@@ -757,7 +780,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   }
   const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
   // two-kernel trellis location (points regrouped by node between the halves): pays off once the nodes hold a few points each
-  const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : 0u;
+  const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : g->gd.bins.total;  // (nest / mesh: spatial bins)
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
   CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes : ws.n_nodes));
   if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, N_FAIL * sizeof(unsigned long long), stream));

@@ -93,8 +93,18 @@ struct CellsDev {
   const uint32_t* node_index;      // trellis only: payload index of a node
 };
 
+// Nest / Mesh: a uniform grid of bins over the bounding box of the vertices.  It plays the part of the trellis nodes in the
+// two-kernel location: the points are regrouped by bin between the kernels, so that the lanes of a warp descend the tree / the
+// layers next to each other (same branches, shared loads).  It only orders the work: the location itself is unchanged.
+struct BinDev {
+  double lo[3], inv[3];  // bin of x along d: floor((x[d] - lo[d]) * inv[d]), clamped
+  int n[3];
+  uint32_t total;        // 0: not available
+};
+
 struct GridDev {
   int kind;  // b200_grid_kind
+  BinDev bins;
   TrellisDev tr;
   NestDev ne;
   MeshDev me;
@@ -245,7 +255,7 @@ struct CellTableDev {
 constexpr uint32_t MODE_NO_MOVE = 1u;    // skip moveinto/ir_moveinto (do_not_move_points)
 constexpr uint32_t MODE_IR = 2u;         // ir_moveinto (wedge rotation) rather than moveinto
 constexpr uint32_t MODE_NO_LOCATE = 4u;  // moveinto only (b200_moveinto)
-constexpr uint32_t MODE_SPLIT_A = 8u;    // trellis: stop after the node is found and park the point (two-kernel location)
+constexpr uint32_t MODE_SPLIT_A = 8u;    // stop after the node (trellis) / spatial bin (nest, mesh) is found and park the point (two-kernel location)
 constexpr uint32_t MODE_NO_TAU = 16u;    // with MODE_IR: wedge rotation only, no translation (BrillouinZone::ir_moveinto_wedge)
 constexpr uint32_t MODE_ISINSIDE = 32u;  // only test the point against the first-zone planes (BrillouinZone::isinside): status bit, no failure
 

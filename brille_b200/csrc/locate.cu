@@ -757,9 +757,21 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     out.invridx[i] = invridx;
     uint32_t cell = 0xffffffffu;
     int tet = -1, n_emit = 0;
-    if (KIND == B200_GRID_TRELLIS && SPLIT) {
-      // two-kernel location: find the node, park the point, count it in its node's bucket; k_locate_in_node finishes it
-      st |= trellis_find_node(bz, tr, knots, x, cell);
+    if (SPLIT) {
+      // two-kernel location: find the node (trellis) / spatial bin (nest, mesh), park the point, count it in that bucket;
+      // k_locate_in_node finishes it
+      if (KIND == B200_GRID_TRELLIS) {
+        st |= trellis_find_node(bz, tr, knots, x, cell);
+      } else {
+        const BinDev& bn = gd.bins;
+        int ib[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double f = (x[d] - bn.lo[d]) * bn.inv[d];
+          ib[d] = f > 0.0 ? (f < (double)bn.n[d] ? (int)f : bn.n[d] - 1) : 0;  // (NaN -> 0)
+        }
+        cell = (uint32_t)(ib[0] + bn.n[0] * (ib[1] + bn.n[1] * ib[2]));
+      }
       ParkedPoint pp;
       pp.x[0] = x[0]; pp.x[1] = x[1]; pp.x[2] = x[2];
       pp.rot_st = (uint32_t)ridx | ((uint32_t)invridx << 8) | (st << 16);
@@ -768,7 +780,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       // third sector of the point's record (device_tables.cuh): q_ir, rotation indices, point index
       st32(out.weight + REC_DOUBLES * i + 8, q[0], q[1], q[2],
            __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
-      const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? tr.n_nodes : cell;
+      const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? (KIND == B200_GRID_TRELLIS ? tr.n_nodes : gd.bins.total) : cell;
       out.key[i] = bucket;
       if (pending_at) *pending_at = pending_rank;
       pending_rank = atomicAdd(out.node_count + bucket, 1u);
@@ -824,7 +836,8 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
 // Second kernel of the split trellis location: the points arrive sorted by node, so the lanes of a warp work in the same
 // node -- same branch (cube / triangulated), same tetrahedra, same trip counts, loads that broadcast.  Same arithmetic and
 // the same outputs as the tail of k_locate.
-__global__ void __launch_bounds__(128, 5)
+template <int KIND>
+__global__ void __launch_bounds__(128, KIND == B200_GRID_TRELLIS ? 5 : 3)
 k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t mode, LocateOut out, const uint32_t* __restrict__ order,
                  unsigned long long* __restrict__ fail_count) {
   const TrellisDev& tr = gd.tr;
@@ -851,7 +864,7 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
     i_cur = i_nxt;
     i_nxt = i_nn;
     uint32_t st = pp.rot_st >> 16;
-    const uint32_t cell = pp.cell;
+    uint32_t cell = pp.cell;  // trellis: the node; nest / mesh: the spatial bin (replaced by the containing tetrahedron below)
     const int invridx = (int)((pp.rot_st >> 8) & 0xffu);
     int tet = -1;
     __align__(16) uint32_t vtmp[8];  // the vertex list goes to memory only if somebody reads it (probe, general kernel)
@@ -860,7 +873,13 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
     e.w = out.weight + REC_DOUBLES * i;
     e.n = 0;
     e.slots = 0;
-    if (!(st & B200_ST_NOT_FOUND)) st |= trellis_in_node(bz, tr, pp.x, cell, e, tet);
+    if (KIND == B200_GRID_TRELLIS) {
+      if (!(st & B200_ST_NOT_FOUND)) st |= trellis_in_node(bz, tr, pp.x, cell, e, tet);
+    } else if (KIND == B200_GRID_NEST) {
+      st |= nest_locate(gd.ne, pp.x, e, cell, tet);
+    } else {
+      st |= mesh_locate(bz, gd.me, pp.x, e, cell, tet);
+    }
     if (e.n == 0) {  // not found: defined contents for the row
       for (int j = 0; j < 8; ++j) {
         e.v[j] = 0xffffffffu;
@@ -872,7 +891,7 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
     uint32_t key = general;
     if (!(st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND))) {
       if (tet >= 0 && n_emit == 4) key = gd.cells.n_cubes + (uint32_t)tet;
-      else if (tet < 0 && n_emit == 8) key = gd.cells.node_index[cell];
+      else if (KIND == B200_GRID_TRELLIS && tet < 0 && n_emit == 8) key = gd.cells.node_index[cell];
     }
     const bool in_cell_bucket = key != general;
     key = key * out.sub + (uint32_t)invridx;
@@ -915,7 +934,12 @@ cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n,
                                   unsigned long long* fail_count, int sm_count, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   const size_t want = (n + 127) / 128, cap = (size_t)sm_count * 32;
-  k_locate_in_node<<<(unsigned)(want < cap ? want : cap), 128, 0, stream>>>(bzg, gd, n, mode, out, order, fail_count);
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  switch (gd.kind) {
+    case B200_GRID_TRELLIS: k_locate_in_node<B200_GRID_TRELLIS><<<grid, 128, 0, stream>>>(bzg, gd, n, mode, out, order, fail_count); break;
+    case B200_GRID_NEST: k_locate_in_node<B200_GRID_NEST><<<grid, 128, 0, stream>>>(bzg, gd, n, mode, out, order, fail_count); break;
+    default: k_locate_in_node<B200_GRID_MESH><<<grid, 128, 0, stream>>>(bzg, gd, n, mode, out, order, fail_count); break;
+  }
   return cudaGetLastError();
 }
 
@@ -952,8 +976,12 @@ cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, 
     case B200_GRID_TRELLIS:
       if (mode & MODE_SPLIT_A) return launch_kind<B200_GRID_TRELLIS, true>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
       return launch_kind<B200_GRID_TRELLIS, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
-    case B200_GRID_NEST: return launch_kind<B200_GRID_NEST, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
-    default: return launch_kind<B200_GRID_MESH, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    case B200_GRID_NEST:
+      if (mode & MODE_SPLIT_A) return launch_kind<B200_GRID_NEST, true>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+      return launch_kind<B200_GRID_NEST, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+    default:
+      if (mode & MODE_SPLIT_A) return launch_kind<B200_GRID_MESH, true>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
+      return launch_kind<B200_GRID_MESH, false>(bzg, gd, Q, n, mode, eps_w, eps_o, out, fail_count, sm_count, stream);
   }
 }
 

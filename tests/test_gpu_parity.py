@@ -380,13 +380,23 @@ def test_device_sort_cost_functions_and_errors(host, bridge):
         gd.sort_pairs(np.array([[0, 1]], dtype=np.uint32), plan)
 
 
-@pytest.mark.parametrize("which", ["C2", "C3"])
+@pytest.mark.parametrize("which", ["C2", "C3", "C3nest", "C3mesh", "C4"])
 def test_two_kernel_location_is_bit_invisible(host, which):
-    """The trellis location in two kernels (points regrouped by node in between) and in one kernel: same decisions, same
-    weights, same results, bit for bit -- with and without the probe (the probe switches the lean outputs off)."""
-    wl = W.c2_nacl(host, density=300) if which == "C2" else W.c3_p63mmc(host, density=300, seed=5)
+    """The location in two kernels (points regrouped in between: by trellis node, or by a spatial bin for the Nest / Mesh descents)
+    and in one kernel: same decisions, same weights, same results, bit for bit -- with and without the probe (the probe switches
+    the lean outputs off)."""
+    if which in ("C3nest", "C3mesh"):
+        lat = W.p63mmc_lattice(host)
+        bz = host.BrillouinZone(lat)
+        hg = host.BZNestQdc(bz, bz.ir_polyhedron.volume / 500, 5) if which == "C3nest" else host.BZMeshQdc(bz, bz.ir_polyhedron.volume / 500, 3)
+        W._gamma_fill(hg, 12, 4, 17)
+        wl = W.Workload(which, hg, bz, 12, 4, W._uniform_q(-3, 3))
+    elif which == "C4":
+        wl = W.c4_p21c_nest(host, density=300)
+    else:
+        wl = W.c2_nacl(host, density=300) if which == "C2" else W.c3_p63mmc(host, density=300, seed=5)
     g = brille_b200.accelerate(wl.grid)
-    Q = wl.make_q(300000, 41)
+    Q = wl.make_q(60000 if which == "C4" else 300000, 41)
     Q[:10] = 0.0  # the zone centre sits on node corners: neighbour search, compact emission, general kernel
     out = {}
     for split in (0, 1):
