@@ -437,7 +437,7 @@ static void build_bins(b200_grid* g, const double* vertices, size_t n_vertices) 
   b.total = 1;
   for (int d = 0; d < 3; ++d) {
     const double ext = hi[d] - lo[d];
-    b.n[d] = ext > 0.0 ? 16 : 1;
+    b.n[d] = ext > 0.0 ? 64 : 1;
     b.lo[d] = lo[d];
     b.inv[d] = ext > 0.0 ? b.n[d] / ext : 0.0;
     b.total *= (uint32_t)b.n[d];
@@ -780,9 +780,15 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   }
   const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
   // two-kernel trellis location (points regrouped by node between the halves): pays off once the nodes hold a few points each
-  const uint32_t n_nodes = g->gd.kind == B200_GRID_TRELLIS ? g->gd.tr.n_nodes : g->gd.bins.total;  // (nest / mesh: spatial bins)
+  // (nest / mesh: spatial bins, coarsened to about 100 points of the call per bin; the work space is sized for the finest level)
+  const bool trellis = g->gd.kind == B200_GRID_TRELLIS;
+  int bin_shift = 0;
+  if (!trellis && g->gd.bins.total)
+    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 100 > n_call) ++bin_shift;
+  const uint32_t n_nodes_alloc = trellis ? g->gd.tr.n_nodes : g->gd.bins.total;
+  const uint32_t n_nodes = trellis ? g->gd.tr.n_nodes : (g->gd.bins.total ? bins_at_level(g->gd.bins, bin_shift) : 0u);
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
-  CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes : ws.n_nodes));
+  CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes_alloc : ws.n_nodes));
   if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, N_FAIL * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
   lo.x_ir = ws.x_ir;
@@ -799,9 +805,12 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     lo.parked = ws.parked;
     lo.lean = want_probe ? 0 : 1;
     lo.node_count = ws.node_count;
+    lo.bin_shift = bin_shift;
     CU(cudaMemsetAsync(ws.node_count, 0, ((size_t)n_nodes + 1) * sizeof(uint32_t), stream));
     CU(launch_locate(g->d_bz, g->gd, dQ, n, mode | MODE_SPLIT_A, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
-    CU(launch_bucket_sort(ws.nbk, ws.key, ws.rank, n, g->sm_count, stream));
+    BucketDev nbk = ws.nbk;  // (allocated for the finest level of bins; this call uses n_nodes of them + the "no node" bucket)
+    nbk.n_buckets = n_nodes + 1;
+    CU(launch_bucket_sort(nbk, ws.key, ws.rank, n, g->sm_count, stream));
     CU(launch_locate_in_node(g->d_bz, g->gd, n, mode, lo, ws.nbk.order, d_fail, g->sm_count, stream));
     g->launches += 6;
   } else {

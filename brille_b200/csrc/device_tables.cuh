@@ -97,10 +97,15 @@ struct CellsDev {
 // two-kernel location: the points are regrouped by bin between the kernels, so that the lanes of a warp descend the tree / the
 // layers next to each other (same branches, shared loads).  It only orders the work: the location itself is unchanged.
 struct BinDev {
-  double lo[3], inv[3];  // bin of x along d: floor((x[d] - lo[d]) * inv[d]), clamped
-  int n[3];
-  uint32_t total;        // 0: not available
+  double lo[3], inv[3];  // finest bin of x along d: floor((x[d] - lo[d]) * inv[d]), clamped to [0, n[d])
+  int n[3];              // finest level (64 per axis with an extent); a call uses every 2^shift-th bin (LocateOut::bin_shift)
+  uint32_t total;        // bins of the finest level; 0: not available
 };
+__host__ __device__ inline uint32_t bins_at_level(const BinDev& b, int shift) {
+  uint32_t t = 1;
+  for (int d = 0; d < 3; ++d) t *= (uint32_t)(((b.n[d] - 1) >> shift) + 1);
+  return t;
+}
 
 struct GridDev {
   int kind;  // b200_grid_kind
@@ -147,6 +152,7 @@ struct LocateOut {
   // split trellis location (MODE_SPLIT_A): parked points and their node buckets (key/rank double as node bucket/rank)
   ParkedPoint* parked;   // (n)
   int lean;              // second kernel: points of a cell bucket write only their record (no probe was asked for)
+  int bin_shift;         // nest / mesh: coarsening of the spatial bins for this call (about 100 points per bin)
   uint32_t* node_count;  // (n_nodes + 1), zeroed before the launch; bucket n_nodes = no node found
   uint32_t sub;          // sub-buckets per bucket = number of point group operations: the sort is by (cell, operation), so
                          //     that consecutive points of a cell share the rotation matrix

@@ -764,13 +764,14 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
         st |= trellis_find_node(bz, tr, knots, x, cell);
       } else {
         const BinDev& bn = gd.bins;
-        int ib[3];
+        int ib[3], nb[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const double f = (x[d] - bn.lo[d]) * bn.inv[d];
-          ib[d] = f > 0.0 ? (f < (double)bn.n[d] ? (int)f : bn.n[d] - 1) : 0;  // (NaN -> 0)
+          ib[d] = (f > 0.0 ? (f < (double)bn.n[d] ? (int)f : bn.n[d] - 1) : 0) >> out.bin_shift;  // (NaN -> 0)
+          nb[d] = ((bn.n[d] - 1) >> out.bin_shift) + 1;
         }
-        cell = (uint32_t)(ib[0] + bn.n[0] * (ib[1] + bn.n[1] * ib[2]));
+        cell = (uint32_t)(ib[0] + nb[0] * (ib[1] + nb[1] * ib[2]));
       }
       ParkedPoint pp;
       pp.x[0] = x[0]; pp.x[1] = x[1]; pp.x[2] = x[2];
@@ -780,7 +781,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       // third sector of the point's record (device_tables.cuh): q_ir, rotation indices, point index
       st32(out.weight + REC_DOUBLES * i + 8, q[0], q[1], q[2],
            __hiloint2double((int)(uint32_t)i, (int)((uint32_t)ridx | ((uint32_t)invridx << 16))));
-      const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? (KIND == B200_GRID_TRELLIS ? tr.n_nodes : gd.bins.total) : cell;
+      const uint32_t bucket = (st & B200_ST_NOT_FOUND) ? (KIND == B200_GRID_TRELLIS ? tr.n_nodes : bins_at_level(gd.bins, out.bin_shift)) : cell;
       out.key[i] = bucket;
       if (pending_at) *pending_at = pending_rank;
       pending_rank = atomicAdd(out.node_count + bucket, 1u);
