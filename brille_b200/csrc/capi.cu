@@ -784,7 +784,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   const bool trellis = g->gd.kind == B200_GRID_TRELLIS;
   int bin_shift = 0;
   if (!trellis && g->gd.bins.total)
-    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 100 > n_call) ++bin_shift;
+    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 30 > n_call) ++bin_shift;
   const uint32_t n_nodes_alloc = trellis ? g->gd.tr.n_nodes : g->gd.bins.total;
   const uint32_t n_nodes = trellis ? g->gd.tr.n_nodes : (g->gd.bins.total ? bins_at_level(g->gd.bins, bin_shift) : 0u);
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
