@@ -168,6 +168,7 @@ struct HostStage {  // device-side staging buffers of one pipeline slot of the h
   double* dsf = nullptr;  // structure factor rows of the chunk (b200_ir_structure_factor)
   double* dgs = nullptr;  // fused consumer: compact eigenvector rows of the points that take the general kernel
   uint32_t gcap = 0;
+  size_t vecs_capacity = 0;  // points dvecs has room for (the fused consumer runs larger chunks without it)
   Workspace ws;
   unsigned long long* d_fail = nullptr;  // N_FAIL counters
   unsigned long long* h_fail = nullptr;  // pinned mirror (keeps the D2H of the counters asynchronous)
@@ -973,11 +974,18 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       }
       h.capacity = 0;
       h.gcap = 0;
+      h.vecs_capacity = 0;
       CU(cudaMalloc(&h.dQ, n * 3 * sizeof(double)));
       h.capacity = n;
     }
     if (interp && !h.dvals) CU(cudaMalloc(&h.dvals, std::max<size_t>(h.capacity * g->vals_row_bytes, 8)));
-    if (interp && !fuse && !h.dvecs) CU(cudaMalloc(&h.dvecs, std::max<size_t>(h.capacity * g->vecs_row_bytes, 8)));
+    if (interp && !fuse && h.vecs_capacity < n) {  // sized for this call's chunks, not for the (possibly larger) chunks of a fused call
+      if (h.dvecs) cudaFree(h.dvecs);
+      h.dvecs = nullptr;
+      h.vecs_capacity = 0;
+      CU(cudaMalloc(&h.dvecs, std::max<size_t>(std::min(chunk, h.capacity) * g->vecs_row_bytes, 8)));
+      h.vecs_capacity = std::min(chunk, h.capacity);
+    }
     if (sf_out && !h.dsf) CU(cudaMalloc(&h.dsf, std::max<size_t>(h.capacity * sf_row, 8)));
     if (fuse && !h.dgs) {
       h.gcap = (uint32_t)std::max<size_t>(1024, h.capacity / 16);
