@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "brille_b200.h"
@@ -169,6 +170,11 @@ struct HostStage {  // device-side staging buffers of one pipeline slot of the h
   double* dgs = nullptr;  // fused consumer: compact eigenvector rows of the points that take the general kernel
   uint32_t gcap = 0;
   size_t vecs_capacity = 0;  // points dvecs has room for (the fused consumer runs larger chunks without it)
+  // pageable destinations: the chunk's results are copied D2H into page-locked bounce buffers and from there, by several host
+  // threads, into the caller's arrays
+  char* hb = nullptr;        // [vals | vecs or sf] of one chunk
+  size_t hb_bytes = 0;
+  size_t pend_lo = 0, pend_n = 0;  // rows of the chunk waiting in hb
   Workspace ws;
   unsigned long long* d_fail = nullptr;  // N_FAIL counters
   unsigned long long* h_fail = nullptr;  // pinned mirror (keeps the D2H of the counters asynchronous)
@@ -206,6 +212,7 @@ struct b200_grid {
   bool has_sf = false;
   void* sf_scratch = nullptr;
   size_t sf_scratch_bytes = 0;
+  int bounce = 1;               // host-buffer calls: pageable destinations through page-locked bounce buffers + host threads
   int replay_stores = 0;        // diagnostic: run k_store_replay after the pipelined cell kernel and time it ("replay")
   int sf_fused = 1;             // 1: reduce inside the pipelined cell kernel whenever possible (the eigenvectors never reach HBM)
   double* sf_gscratch = nullptr;  // device-buffer entry point: compact rows of the general-kernel points
@@ -629,6 +636,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
     if (h.dvecs) cudaFree(h.dvecs);
     if (h.dsf) cudaFree(h.dsf);
     if (h.dgs) cudaFree(h.dgs);
+    if (h.hb) cudaFreeHost(h.hb);
     if (h.d_fail) cudaFree(h.d_fail);
     if (h.h_fail) cudaFreeHost(h.h_fail);
     if (h.stream) cudaStreamDestroy(h.stream);
@@ -933,6 +941,36 @@ extern "C" int b200_ir_interpolate_at_device(b200_grid_t* g, const double* dQ, s
   return interpolate_device(g, dQ, nQ, flags, 1, dvals, dvecs, dprobe, static_cast<cudaStream_t>(stream), n_failed);
 }
 
+// copy with several host threads (a fresh numpy array is first touched here: the page faults are spread over the cores)
+static void parallel_copy(void* dst, const void* src, size_t bytes) {
+  const size_t min_slice = (size_t)4 << 20;
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(nt, 16u));
+  nt = (unsigned)std::min<size_t>(nt, std::max<size_t>(1, bytes / min_slice));
+  if (nt <= 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t slice = ((bytes + nt - 1) / nt + 4095) / 4096 * 4096;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t lo = (size_t)t * slice;
+    if (lo >= bytes) break;
+    const size_t n = std::min(slice, bytes - lo);
+    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, n); });
+  }
+  for (auto& x : th) x.join();
+}
+static bool is_pageable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
 // host-pointer pipeline: chunks alternate between two stages (stream + staging buffers) so that the H2D copy of
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 // sf_out != nullptr: the structure-factor consumer -- fused into the pipelined cell kernel when `fuse` (the eigenvectors then
@@ -954,8 +992,21 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
     const size_t nb = (size_t)g->gd.cells.n_cubes + g->gd.cells.n_tets + 1;
     chunk = std::min(chunk, std::max<size_t>(std::max<size_t>(32 * nb, (nQ + 7) / 8), 65536));
   }
+  // Pageable destinations (plain numpy arrays): a device-to-pageable copy runs at a fraction of the PCIe rate and first-touches the
+  // caller's fresh pages on one thread; instead the chunk goes to a page-locked bounce buffer at full rate and several host threads
+  // move it on while the GPU works on the next chunk.
+  const size_t second_row = sf_out ? sf_row : g->vecs_row_bytes;
+  char* const second_dst = sf_out ? reinterpret_cast<char*>(sf_out) : static_cast<char*>(vecs);
+  const bool bounce = interp && g->bounce && nQ * (g->vals_row_bytes + second_row) >= ((size_t)8 << 20) && (is_pageable(vals) || is_pageable(second_dst));
+  if (bounce) chunk = std::min(chunk, std::max<size_t>(((size_t)640 << 20) / (g->vals_row_bytes + second_row), 1024));
   if (g->host_chunk) chunk = std::min(chunk, g->host_chunk);
   if (chunk > nQ) chunk = std::max<size_t>(nQ, 1);
+  auto flush = [&](HostStage& h) {  // the finished chunk of this stage: bounce buffer -> caller's arrays
+    if (!bounce || !h.pend_n) return;
+    parallel_copy(static_cast<char*>(vals) + h.pend_lo * g->vals_row_bytes, h.hb, h.pend_n * g->vals_row_bytes);
+    parallel_copy(second_dst + h.pend_lo * second_row, h.hb + h.pend_n * g->vals_row_bytes, h.pend_n * second_row);
+    h.pend_n = 0;
+  };
   unsigned long long total[N_FAIL] = {0, 0, 0, 0};
   bool pending[2] = {false, false};
   size_t nchunks = (nQ + chunk - 1) / chunk;
@@ -965,6 +1016,7 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
       CU(cudaStreamSynchronize(h.stream));
       for (int k = 0; k < N_FAIL; ++k) total[k] += h.h_fail[k];
       pending[c & 1] = false;
+      flush(h);
     }
     const size_t lo = c * chunk, n = std::min(chunk, nQ - lo);
     if (h.capacity < n) {
@@ -1000,15 +1052,32 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
     }
     if (rc) return rc;
     if (interp) {
-      CU(cudaMemcpyAsync(static_cast<char*>(vals) + lo * g->vals_row_bytes, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+      char* vals_to = static_cast<char*>(vals) + lo * g->vals_row_bytes;
+      char* second_to = second_dst + lo * second_row;
+      if (bounce) {
+        const size_t need = n * (g->vals_row_bytes + second_row);
+        if (h.hb_bytes < need) {
+          if (h.hb) cudaFreeHost(h.hb);
+          h.hb = nullptr;
+          h.hb_bytes = 0;
+          const size_t want = std::min(chunk, nQ) * (g->vals_row_bytes + second_row);
+          CU(cudaHostAlloc(reinterpret_cast<void**>(&h.hb), want, cudaHostAllocDefault));
+          h.hb_bytes = want;
+        }
+        vals_to = h.hb;
+        second_to = h.hb + n * g->vals_row_bytes;
+        h.pend_lo = lo;
+        h.pend_n = n;
+      }
+      CU(cudaMemcpyAsync(vals_to, h.dvals, n * g->vals_row_bytes, cudaMemcpyDeviceToHost, h.stream));
       if (sf_out) {  // only `modes` doubles per Q go back
         if (!fuse) {  // the eigenvectors of the chunk are reduced where they are
           CU(launch_structure_factor(g->sf, h.dQ, h.dvecs, n, g->dd.vectors.branches, h.dsf, g->sm_count, h.stream));
           g->launches += 1;
         }
-        CU(cudaMemcpyAsync(reinterpret_cast<char*>(sf_out) + lo * sf_row, h.dsf, n * sf_row, cudaMemcpyDeviceToHost, h.stream));
+        CU(cudaMemcpyAsync(second_to, h.dsf, n * sf_row, cudaMemcpyDeviceToHost, h.stream));
       } else {
-        CU(cudaMemcpyAsync(static_cast<char*>(vecs) + lo * g->vecs_row_bytes, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
+        CU(cudaMemcpyAsync(second_to, h.dvecs, n * g->vecs_row_bytes, cudaMemcpyDeviceToHost, h.stream));
       }
     }
     if (probe) {
@@ -1031,6 +1100,7 @@ static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode
     if (pending[s]) {
       CU(cudaStreamSynchronize(g->stage[s].stream));
       for (int k = 0; k < N_FAIL; ++k) total[k] += g->stage[s].h_fail[k];
+      flush(g->stage[s]);
     }
   int rc = status_error(total, nQ);
   if (rc == B200_OK && fuse && total[3])  // more general-kernel points than compact rows in some chunk (a degenerate point set)
@@ -1270,6 +1340,8 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
   } else if (n == "chunk") {
     if (value < 32 || value > 256) return fail(B200_E_INVALID, "chunk must be in [32, 256]");
     g->chunk = ((uint32_t)value / 4u) * 4u;  // the weight tile is read with 16-byte loads
+  } else if (n == "bounce") {
+    g->bounce = value != 0;
   } else if (n == "replay_stores") {
     g->replay_stores = value != 0;
   } else if (n == "sf_fused") {

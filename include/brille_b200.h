@@ -285,7 +285,9 @@ int b200_ir_structure_factor_device(b200_grid_t* grid, const double* dQ, size_t 
                                     double* d_sf_out, void* d_vecs_scratch, void* stream, uint64_t* n_failed);
 
 /* Page-locked host memory for Q / output buffers: with pinned buffers the chunked copies of the host-buffer
- * entry points overlap the kernels (pageable memory works too but serialises the copies).                  */
+ * entry points run at the PCIe rate and overlap the kernels.  Pageable output buffers work too: the library lands
+ * every chunk in a page-locked bounce buffer of its own and moves it on with several host threads (about half the
+ * rate of pinned buffers; option "bounce" 0 restores plain device-to-pageable copies).                      */
 void* b200_alloc_pinned(size_t bytes);
 void b200_free_pinned(void* ptr);
 
