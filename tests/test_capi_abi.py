@@ -34,6 +34,9 @@ def test_struct_layout_matches_header_sizes():
     assert C.sizeof(T.Probe) == 11 * C.sizeof(C.c_void_p)
     assert T.BZTables.P6t.size == 36 and T.BZTables.to_xyz.size == 72
     assert T.InterpDesc.elements.size == 12
+    # b200_sf_config_t: uint32 + 3 pointers + 9 doubles + int32, natural alignment
+    assert C.sizeof(capi.SFConfig) == 112 and capi.SFConfig.q_transform.offset == 32 and capi.SFConfig.conjugate.offset == 104
+    assert C.sizeof(capi.SortConfig) == 56
 
 
 def test_no_cpu_fallback_without_device():
