@@ -310,7 +310,11 @@ double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
  * fill; auto uses it whenever the table fits in a quarter of the free device memory); "tile" points per register tile
  * of the pipelined kernel (4: 124 registers, 2 CTAs/SM, default; 2: 80 registers, 3 CTAs/SM - measured slower); "host_chunk" upper bound on
  * the points per chunk of the host-buffer pipeline (0 = sized from free device memory); "sf_fused" 1 (default) / 0: structure
- * factor reduced inside the pipelined cell kernel whenever possible / always through the eigenvector scratch           */
+ * factor reduced inside the pipelined cell kernel whenever possible / always through the eigenvector scratch; "bounce" 1
+ * (default) / 0: pageable host destinations through page-locked bounce buffers and host threads / plain device-to-pageable
+ * copies; "split_locate" 1 (default) / 0: two-kernel location with the points regrouped in between / single kernel;
+ * "replay_stores" 1: diagnostic, with timing enabled the output stores of the pipelined kernel are replayed on their own
+ * and timed as "replay" (b200_grid_kernel_ms)                                                                       */
 int b200_grid_set_option(b200_grid_t* grid, const char* name, double value);
 /* output row sizes in bytes for one Q (values, vectors) and algorithmic HBM bytes per Q of the path          */
 int b200_grid_row_bytes(const b200_grid_t* grid, size_t* vals_bytes, size_t* vecs_bytes);

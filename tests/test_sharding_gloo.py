@@ -44,9 +44,18 @@ def _worker(rank, world, port, q):
     assert rc == 0
     V = gather_rows(torch.from_numpy(v)).numpy()
     Wr = gather_rows(torch.from_numpy(np.ascontiguousarray(w.view(np.float64)))).numpy().view(np.complex128)
+    # the structure-factor consumer reduces every shard where it was computed; only (n, modes) rows are gathered
+    from oracle.consumer import structure_factor
+
+    coef = np.array([1.0 + 0.5j, -0.3 + 2.0j])
+    pos = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
+    sf = structure_factor(shard(Q, rank, world), w, coef, positions=pos)
+    SF = gather_rows(torch.from_numpy(sf)).numpy()
     if rank == 0:
         rc, v1, w1, _ = orc.interpolate_at(Q, probe=False)
-        q.put(bool(np.array_equal(V, v1) and np.array_equal(Wr, w1) and V.shape[0] == len(Q)))
+        ok = np.array_equal(V, v1) and np.array_equal(Wr, w1) and V.shape[0] == len(Q)
+        ok = ok and np.array_equal(SF, structure_factor(Q, w1, coef, positions=pos))
+        q.put(bool(ok))
     dist.barrier()
     dist.destroy_process_group()
 
