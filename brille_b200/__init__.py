@@ -13,6 +13,7 @@ from __future__ import annotations
 from . import tables  # noqa: F401
 from .capi import B200Error  # noqa: F401
 from .grid import B200Grid, PinnedArray, accelerate  # noqa: F401
+from .sharding import ShardedGrid  # noqa: F401
 
 __version__ = "0.1.0"
 
