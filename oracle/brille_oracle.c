@@ -180,6 +180,12 @@ static uint32_t moveinto_one(const b200_bz_tables_t* bz, const double* Q, double
 }
 
 /* _inside_wedge_outer (bz.hpp:757-763) with Array2::all (array2.tpp:664-672) */
+/* BrillouinZone::isinside (bz.hpp:631-640): the conventional-lattice plane test (the one moveinto re-checks its result with) */
+static int isinside_one(const b200_bz_tables_t* bz, const double* q) {
+  tol_t cfg = make_tol(bz->float_tolerance, bz->approx_tolerance);
+  return inside_all_planes(bz->o_recip_metric, bz->o_real_metric, bz->o_recip_volume, bz->n_faces, bz->ca, bz->cb, bz->cc, q, cfg);
+}
+
 static int inside_wedge(const b200_bz_tables_t* bz, const double* q) {
   const int K = bz->n_wedge;
   if (K == 0) return 1;
@@ -202,8 +208,17 @@ static int inside_wedge(const b200_bz_tables_t* bz, const double* q) {
 }
 
 /* ir_moveinto for one Q (bz_move.cpp:165-296) */
+static uint32_t wedge_search(const b200_bz_tables_t* bz, double* q, int* ridx, int* invridx, uint32_t st);
 static uint32_t ir_moveinto_one(const b200_bz_tables_t* bz, const double* Q, double* q, int32_t* tau, int* ridx, int* invridx) {
-  uint32_t st = moveinto_one(bz, Q, q, tau);
+  return wedge_search(bz, q, ridx, invridx, moveinto_one(bz, Q, q, tau));
+}
+/* ir_moveinto_wedge (bz_move.cpp:299-356): the same rotation search applied to Q itself */
+static uint32_t wedge_rotate_one(const b200_bz_tables_t* bz, const double* Q, double* q, int* ridx, int* invridx) {
+  for (int i = 0; i < 3; ++i) q[i] = Q[i];
+  return wedge_search(bz, q, ridx, invridx, 0u);
+}
+/* the wedge loop shared by both (bz_move.cpp:257-285, 330-347) */
+static uint32_t wedge_search(const b200_bz_tables_t* bz, double* q, int* ridx, int* invridx, uint32_t st) {
   if (inside_wedge(bz, q)) {
     *ridx = *invridx = bz->identity_index;
     return st;
@@ -913,13 +928,24 @@ static void probe_store(b200_probe_t* p, size_t i, const double* q, const double
   if (p->status) p->status[i] = st;
 }
 
+/* ir: 0 moveinto (bz_move.cpp:103-163), 1 ir_moveinto (:165-296), 2 ir_moveinto_wedge (:299-356: the wedge rotation of Q
+ * itself, no translation), 3 isinside (bz.hpp:631-640: status bit only, never an error) */
 int oracle_moveinto(const b200_bz_tables_t* bz, const double* Q, size_t nQ, int ir, b200_probe_t* probe) {
   int rc = 0;
   for (size_t i = 0; i < nQ; ++i) {
     double q[3], x[3];
-    int32_t tau[3];
+    int32_t tau[3] = {0, 0, 0};
     int r = bz->identity_index, ri = bz->identity_index;
-    uint32_t st = ir ? ir_moveinto_one(bz, Q + 3 * i, q, tau, &r, &ri) : moveinto_one(bz, Q + 3 * i, q, tau);
+    uint32_t st = 0;
+    if (ir == 3) {
+      memcpy(q, Q + 3 * i, sizeof(q));
+      st = isinside_one(bz, q) ? 0u : (uint32_t)B200_ST_OUTSIDE_BZ;
+      matvec_dd(x, bz->to_xyz, q);
+      probe_store(probe, i, q, x, tau, r, ri, NULL, st);
+      continue;
+    }
+    if (ir == 2) st = wedge_rotate_one(bz, Q + 3 * i, q, &r, &ri);
+    else st = ir ? ir_moveinto_one(bz, Q + 3 * i, q, tau, &r, &ri) : moveinto_one(bz, Q + 3 * i, q, tau);
     matvec_dd(x, bz->to_xyz, q);
     probe_store(probe, i, q, x, tau, r, ri, NULL, st);
     if ((st & B200_ST_OUTSIDE_BZ) && !rc) rc = B200_E_OUTSIDE_BZ;

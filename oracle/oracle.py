@@ -80,9 +80,10 @@ class Oracle:
         return rc, vals, vecs, pr
 
     def moveinto(self, Q, ir=True):
+        """``ir``: False / 0 moveinto, True / 1 ir_moveinto, 2 ir_moveinto_wedge, 3 isinside (status bit ST_OUTSIDE_BZ)."""
         Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, 3)
         pr = T.ProbeArrays(Q.shape[0], fields=("q_ir", "x_ir", "tau", "ridx", "invridx", "status"))
-        rc = lib().oracle_moveinto(C.byref(self.bz), Q.ctypes.data, Q.shape[0], 1 if ir else 0, pr.byref())
+        rc = lib().oracle_moveinto(C.byref(self.bz), Q.ctypes.data, Q.shape[0], int(ir), pr.byref())
         return rc, pr
 
 

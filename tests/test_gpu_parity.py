@@ -500,6 +500,14 @@ def test_bz_methods_against_reference(host, bridge, which):
     qw, rw = g.ir_moveinto_wedge(Q)
     rqw, rRw = bz.ir_moveinto_wedge(Q)
     assert np.array_equal(qw, rqw) and np.array_equal(rots[rw], rRw)
+    # ... and the oracle's restatement of the same methods (indices instead of matrices)
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rc, opr = orc.moveinto(Q, 3)
+    assert np.array_equal(inside, (opr.status & T.ST_OUTSIDE_BZ) == 0)
+    rc, opr = orc.moveinto(Q, 2)
+    assert np.array_equal(qw, opr.q_ir) and np.array_equal(rw, opr.ridx)
+    rc, opr = orc.moveinto(Q, 1)
+    assert np.array_equal(q, opr.q_ir) and np.array_equal(tau, opr.tau) and np.array_equal(ridx, opr.ridx) and np.array_equal(invridx, opr.invridx)
     g.close()
 
 

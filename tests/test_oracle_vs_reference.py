@@ -73,3 +73,24 @@ def test_lattice_zoo(host, probe, bridge, name, cls):
     base = wl.make_q
     wl.make_q = lambda n, seed: np.vstack([SPECIAL, base(n, seed)])
     _compare(host, probe, bridge, wl, 3000, 5)
+
+
+@pytest.mark.parametrize("which", ["C2", "C3", "F23", "P3_timereversal", "P-1"])
+def test_bz_methods(host, bridge, which):
+    """BrillouinZone.isinside / moveinto / ir_moveinto_wedge (wrap/_bz.cpp:378-520) restated by the oracle, bit for bit."""
+    from brille_b200 import tables as T
+
+    wl = W.BUILDERS[which](host, density=100) if which in W.BUILDERS else W.zoo_grid(host, which)
+    bz = wl.bz
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    rng = np.random.default_rng(8)
+    Q = np.vstack([rng.uniform(-1.5, 1.5, (6000, 3)), rng.integers(-4, 5, (1000, 3)) / 4.0, np.zeros((1, 3))])
+    rots = np.asarray(bridge.flatten_bz(bz)["rotations"]).reshape(-1, 3, 3)
+    rc, pr = orc.moveinto(Q, 3)
+    assert rc == 0 and np.array_equal((pr.status & T.ST_OUTSIDE_BZ) == 0, np.asarray(bz.isinside(Q), dtype=bool))
+    rc, pr = orc.moveinto(Q, 0)
+    rq, rtau = bz.moveinto(Q)
+    assert rc == 0 and np.array_equal(pr.tau, rtau) and np.array_equal(pr.q_ir, rq)
+    rc, pr = orc.moveinto(Q, 2)
+    rqw, rRw = bz.ir_moveinto_wedge(Q)
+    assert rc == 0 and np.array_equal(pr.q_ir, rqw) and np.array_equal(rots[pr.ridx], rRw) and not pr.tau.any()
