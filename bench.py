@@ -155,6 +155,114 @@ def profiled_traffic():
     return None
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the other BASELINE configurations (and the C3 lattice on the Nest / Mesh grid kinds), device resident, reported in the
+# `configs` block of the JSON line beside the C3 headline
+# ---------------------------------------------------------------------------------------------------------------------
+def _config_specs(world):
+    """(key, text, builder, points per GPU per step, points per call, Q maker or None)"""
+    from brille_b200 import workloads as W
+    from brille_b200 import _bridge
+    from oracle import ref
+
+    b = ref.host()
+
+    def powder(wl, n, seed):
+        return np.ascontiguousarray(W.powder_q(np.asarray(_bridge.flatten_bz(wl.bz)["to_xyz"]), n, seed))
+
+    specs = [
+        ("C5", "BASELINE configs[4]: powder-average sweep (|Q| in U(0.1,10) 1/angstrom, isotropic) on the C3 P6_3/mmc 12-mode trellis, 1e7 Q per GPU per step, Q sharded across the GPUs",
+         lambda: W.c3_p63mmc(b), 10_000_000, 10_000_000, powder),
+    ]
+    if world == 1:
+        specs += [
+            ("C1", "BASELINE configs[0]: Fd-3m a=4.96 BZTrellisQdc V_ir/2000, one scalar eigenvalue (general kernel), 1e5 Q per step (3.2 MB of traffic: L2 flushed between steps)",
+             lambda: W.c1_fd3m_scalar(b), 100_000, 100_000, None),
+            ("C2", "BASELINE configs[1]: NaCl-like primitive 2-atom cell BZTrellisQdc V_ir/1000, 6 modes eigvals+eigvecs (Gamma), 1e6 Q per step",
+             lambda: W.c2_nacl(b), 1_000_000, 1_000_000, None),
+            ("C4", "BASELINE configs[3]: P2_1/c 24-atom cell BZNestQdc V_ir/2000, 72 modes eigvals+eigvecs (Gamma), 1e7 Q per step in calls of 5e5 (41.8 GB of output per call)",
+             lambda: W.c4_p21c_nest(b), 10_000_000, 500_000, None),
+            ("C3-nest", "the C3 lattice and data on a BZNestQdc V_ir/2000 (tetrahedron tree), 1e7 Q per step",
+             lambda: W.c3_p63mmc(b, cls="BZNestQdc"), 10_000_000, 10_000_000, None),
+            ("C3-mesh", "the C3 lattice and data on a BZMeshQdc V_ir/2000 (layered tetrahedral meshes), 1e7 Q per step",
+             lambda: W.c3_p63mmc(b, cls="BZMeshQdc"), 10_000_000, 10_000_000, None),
+        ]
+    return specs
+
+
+def measure_config(torch, dist, brille_b200, spec, local, rank, world, steps, peak):
+    """Device-resident Q/s of one configuration: every step is timed with its own CUDA event pair on the launching stream, L2 is
+    flushed (256 MB written) between steps, the slowest rank counts."""
+    key, text, build, nq, per_call, qmaker = spec
+    dev = torch.device("cuda", local)
+    wl = build()
+    grid = brille_b200.accelerate(wl.grid, device=local)
+    Q = qmaker(wl, nq, Q_SEED + 1000 * rank) if qmaker else wl.make_q(nq, Q_SEED + 1000 * rank)
+    dQ = torch.from_numpy(np.ascontiguousarray(Q)).to(dev)
+    c = min(per_call, nq)
+    tv = torch.complex128 if grid._vals_dtype == np.complex128 else torch.float64
+    tw = torch.complex128 if grid._vecs_dtype == np.complex128 else torch.float64
+    vals = torch.empty((c,) + grid._vals_shape, dtype=tv, device=dev)
+    vecs = torch.empty((c,) + grid._vecs_shape, dtype=tw, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(check=False):
+        for lo in range(0, nq, c):
+            m = min(c, nq - lo)
+            grid.ir_interpolate_at_device(dQ[lo:lo + m], vals[:m], vecs[:m], check=check, stream=stream)
+
+    step(check=True)
+    l0 = grid.launch_count
+    step()
+    launches = grid.launch_count - l0
+    path = grid.last_path
+    times = []
+    for _ in range(max(steps, 1)):
+        flush.fill_(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    # per-kernel times (CUDA events inside the library, on the launching stream), summed over the calls of one step
+    grid.enable_timing(True)
+    k = {"locate": 0.0, "sort": 0.0, "interpolate": 0.0}
+    for lo in range(0, nq, c):
+        m = min(c, nq - lo)
+        grid.ir_interpolate_at_device(dQ[lo:lo + m], vals[:m], vecs[:m], check=False, stream=stream)
+        for name in k:
+            k[name] += max(grid.kernel_ms(name), 0.0)
+    grid.enable_timing(False)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    bpq = grid.bytes_per_q
+    achieved = bpq * nq / (k["interpolate"] * 1e-3) / 1e9 if k["interpolate"] > 0 else None
+    names = {4: "k_interp_cell_tma (pipelined cell kernel)", 2: "k_interp_cell (on-the-fly cell kernel)", 8: "k_interp (general kernel)"}
+    kernel = next((v for b_, v in names.items() if path & b_), "?")
+    traffic = (profiled_traffic() or {}).get("configs", {}).get(key)
+    out = {
+        "workload": text, "value": world * nq / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "q_per_gpu_per_step": nq, "q_per_call": c,
+        "modes": wl.modes, "atoms": wl.n_atoms, "vertices": int(wl.grid.rlu.shape[0]), "bytes_per_q": bpq, "gpu_launches_per_step": int(launches),
+        "two_kernel_location": bool(path & 1),
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "kernel_ms": k["interpolate"], "locate_kernel_ms": k["locate"], "bucket_sort_ms": k["sort"],
+                     "path_frac": bpq * nq / (ms * 1e-3) / 1e9 / peak, "traffic": traffic},
+    }
+    grid.close()
+    del dQ, vals, vecs, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_rate(wl, nq, threads, repeats=1):
     """The reference's own ir_interpolate_at (oracle/_ref, unmodified brille) on the host cores."""
     Q = make_q(wl, nq, Q_SEED + 100)
@@ -374,6 +482,19 @@ def run_ours(args):
                     "d2h_bytes_per_step": (8 * wl.modes + 8 * wl.modes) * nc, "checksum": float(hs2.array[:1000].sum())},
         }
 
+    # the other configurations (device resident; see measure_config)
+    configs = None
+    if not args.no_configs:
+        del vals, vecs, dQ
+        torch.cuda.empty_cache()
+        peak0, _ = measured_peak()
+        configs = {}
+        for spec in _config_specs(world):
+            try:
+                configs[spec[0]] = measure_config(torch, dist, brille_b200, spec, local, rank, world, min(args.steps, 5), peak0)
+            except Exception as e:  # noqa: BLE001 - a failing side configuration must not take the headline line with it
+                configs[spec[0]] = {"workload": spec[1], "error": f"{type(e).__name__}: {e}"}
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -400,6 +521,7 @@ def run_ours(args):
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},
             "cpu_baseline": cpu,
             "consumer": consumer,
+            "configs": configs,
         }
         print(json.dumps(line))
     if world > 1:
@@ -417,6 +539,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consumer", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration block (C1, C2, C4, C5, C3 on Nest / Mesh)")
     ap.add_argument("--workload", default="C3", choices=["C3", "C5"], help="C3 (default, the headline configuration) or the C5 powder-average Q on the same grid")
     args = ap.parse_args()
     global WORKLOAD

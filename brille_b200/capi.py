@@ -28,6 +28,7 @@ EXPORTS = (
     "b200_abi_version",
     "b200_device_count",
     "b200_grid_launch_count",
+    "b200_grid_last_path",
     "b200_grid_enable_timing",
     "b200_grid_kernel_ms",
     "b200_grid_row_bytes",
@@ -108,6 +109,8 @@ def lib():
     L.b200_device_count.restype = C.c_int
     L.b200_grid_launch_count.restype = C.c_uint64
     L.b200_grid_launch_count.argtypes = [vp]
+    L.b200_grid_last_path.restype = C.c_uint32
+    L.b200_grid_last_path.argtypes = [vp]
     L.b200_grid_enable_timing.restype = C.c_int
     L.b200_grid_enable_timing.argtypes = [vp, C.c_int]
     L.b200_grid_kernel_ms.restype = C.c_double

@@ -28,6 +28,17 @@ static int fail(int code, const std::string& msg) {
       return fail(B200_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);     \
   } while (0)
 
+// The device-buffer entry points run underneath a caller (torch) that has a current device of its own: it is restored on return.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // owning device buffer list
 struct DevPool {
   std::vector<void*> ptrs;
@@ -218,10 +229,35 @@ struct b200_grid {
   double* sf_gscratch = nullptr;  // device-buffer entry point: compact rows of the general-kernel points
   uint32_t sf_gcap = 0;
   uint64_t launches = 0;
+  uint32_t last_path = 0;  // B200_PATH_* of the last enqueue
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
 };
+
+// Device / bounce buffers of the host pipeline and the consumer scratches are sized in POINTS times the row sizes of the data that
+// was filled when they were allocated: they are dropped whenever the data (and with it the row sizes) changes.
+static void drop_row_sized_buffers(b200_grid* g) {
+  for (int s = 0; s < 2; ++s) {
+    HostStage& h = g->stage[s];
+    for (double** p : {&h.dQ, &h.dvals, &h.dvecs, &h.dsf, &h.dgs}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    if (h.hb) cudaFreeHost(h.hb);
+    h.hb = nullptr;
+    h.hb_bytes = 0;
+    h.capacity = h.vecs_capacity = 0;
+    h.gcap = 0;
+    h.pend_lo = h.pend_n = 0;
+  }
+  if (g->sf_gscratch) cudaFree(g->sf_gscratch);
+  g->sf_gscratch = nullptr;
+  g->sf_gcap = 0;
+  if (g->sf_scratch) cudaFree(g->sf_scratch);
+  g->sf_scratch = nullptr;
+  g->sf_scratch_bytes = 0;
+}
 
 static void drop_cell_table(b200_grid* g) {
   if (g->cell_table) cudaFree(g->cell_table);
@@ -652,6 +688,7 @@ extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
   CU(cudaDeviceSynchronize());
   g->data_pool.release();
   drop_cell_table(g);
+  drop_row_sized_buffers(g);
   g->has_data = false;
   if (t->n_vertices != g->n_vertices)
     return fail(B200_E_INVALID, "Provided " + std::to_string(t->n_vertices) + " arrays but " + std::to_string(g->n_vertices) + " were expected!");
@@ -686,6 +723,21 @@ extern "C" int b200_grid_set_data(b200_grid_t* g, const b200_data_tables_t* t) {
     if (!check(d.values) || !check(d.vectors)) return fail(B200_E_INVALID, "Attempting to access out of bounds mapping!");  // phonon.hpp:190-193
     for (size_t i = 0; i < (size_t)t->n_atoms * G; ++i)
       if (t->gamma_F0[i] >= t->n_atoms || t->gamma_vidx[i] >= t->n_gamma_vectors) return fail(B200_E_INVALID, "GammaTable index out of range");
+    // The reference scatters the rotated vector of atom k to slot F0(k, R) of a work array of no1 slots (and matrix (n, m) to
+    // slot (F0(n, R), F0(m, R^-1)) of Nmat x Nmat, interpolator_gamma.tpp:100-132): only defined when the atoms that carry
+    // data are mapped among themselves.
+    auto closed = [&](uint32_t count) {
+      for (uint32_t k = 0; k < count; ++k)
+        for (int r = 0; r < G; ++r)
+          if (t->gamma_F0[(size_t)k * G + r] >= count) return false;
+      return true;
+    };
+    for (const InterpDev* i : {&d.values, &d.vectors}) {
+      if (i->rot_kind < 3) continue;
+      const uint32_t Nmat = (uint32_t)(std::sqrt((double)i->no2)) / 3u;
+      if (!closed(i->no1) || !closed(Nmat))
+        return fail(B200_E_INVALID, "RotatesLike::Gamma data: the atoms that carry vectors / matrices are not mapped among themselves by the point group");
+    }
     CU(g->data_pool.upload(t->gamma_F0, (size_t)t->n_atoms * G, &d.gamma_F0));
     CU(g->data_pool.upload(t->gamma_vidx, (size_t)t->n_atoms * G, &d.gamma_vidx));
     CU(g->data_pool.upload(t->gamma_vectors, (size_t)t->n_gamma_vectors * 3, &d.gamma_vectors));
@@ -809,6 +861,8 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     lo.sub = nsub;
     CU(cudaMemsetAsync(ws.cell_count, 0, (size_t)nb * nsub * sizeof(uint32_t), stream));
   }
+  g->last_path = (split ? B200_PATH_SPLIT_LOCATE : 0u) | (interp && cell ? (tma ? B200_PATH_CELL_PIPELINED : B200_PATH_CELL_ONTHEFLY) : 0u) |
+                 (interp && !cell ? B200_PATH_GENERAL : 0u) | (fz ? B200_PATH_SF_FUSED : 0u);
   if (g->timing) cudaEventRecord(g->ev[0], stream);
   if (split) {
     lo.parked = ws.parked;
@@ -910,6 +964,7 @@ static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_
                               b200_probe_t* dprobe, cudaStream_t stream, uint64_t* n_failed) {
   int rc = check_ready(g, true, ir);
   if (rc) return rc;
+  DeviceGuard guard;
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
   uint32_t mode = (flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u;
@@ -975,8 +1030,27 @@ static bool is_pageable(const void* p) {
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 // sf_out != nullptr: the structure-factor consumer -- fused into the pipelined cell kernel when `fuse` (the eigenvectors then
 // exist nowhere; the staging buffer for them is not even allocated), otherwise reduced from the staging buffer by k_structure_factor.
+static int host_pipeline_body(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
+                              b200_probe_t* probe, double* sf_out, bool fuse);
+// Every exit of the pipeline passes through here: on an error nothing may be left in flight -- kernels of the other stage and
+// their asynchronous copies into the caller's arrays (or the bounce buffers) -- when the caller gets control back (and may free
+// those arrays), and no chunk may be left waiting in a bounce buffer for the next call.
 static int host_pipeline(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
                          b200_probe_t* probe, double* sf_out = nullptr, bool fuse = false) {
+  const int rc = host_pipeline_body(g, Q, nQ, mode, interp, ir, vals, vecs, probe, sf_out, fuse);
+  if (rc != B200_OK) {
+    const std::string msg = g_err;
+    for (int s = 0; s < 2; ++s) {
+      if (g->stage[s].stream) cudaStreamSynchronize(g->stage[s].stream);
+      g->stage[s].pend_n = 0;
+    }
+    (void)cudaGetLastError();
+    g_err = msg;
+  }
+  return rc;
+}
+static int host_pipeline_body(b200_grid* g, const double* Q, size_t nQ, uint32_t mode, bool interp, int ir, void* vals, void* vecs,
+                              b200_probe_t* probe, double* sf_out, bool fuse) {
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
   const size_t sf_row = (size_t)g->dd.vectors.branches * sizeof(double);
@@ -1194,6 +1268,7 @@ extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ,
   if (n_failed) *n_failed = 0;
   if (nQ == 0) return B200_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard;
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
   const uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
@@ -1293,6 +1368,7 @@ extern "C" int b200_device_count(void) {
   return n;
 }
 extern "C" uint64_t b200_grid_launch_count(const b200_grid_t* g) { return g ? g->launches : 0; }
+extern "C" uint32_t b200_grid_last_path(const b200_grid_t* g) { return g ? g->last_path : 0u; }
 extern "C" int b200_grid_sort_pairs(b200_grid_t* g, const uint32_t* pairs, size_t n_pairs, const b200_sort_config_t* cfg, int32_t* row_out,
                                     int32_t* col_out, double* cost_out) {
   if (!g || !cfg || (n_pairs && (!pairs || !row_out || !col_out))) return fail(B200_E_INVALID, "NULL argument");

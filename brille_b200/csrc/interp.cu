@@ -149,8 +149,22 @@ __device__ __forceinline__ void interp_unit(const InterpDev& id, const DataDev& 
   // 3x3 matrices
   if (id.no2) {
     const uint32_t Nmat = (uint32_t)(sqrt((double)id.no2)) / 3u;
+    // Gamma: the reference rotates only the first Nmat x Nmat of its 9 Nmat^2 matrices (interpolator_gamma.tpp:116-132) and copies
+    // the whole mode back from a work array it shares with the vector pass (:100-114,134): the elements behind the rotated matrices
+    // come out as what that array holds there -- element e of the rotated VECTORS of the mode while e < 3 no1, zero beyond.
+    if (rot.kind >= 3) __syncwarp(gmask);  // (the rotated vectors of this mode were written by the other lanes of the group)
     for (uint32_t mm = lane; mm < id.no2; mm += LANES) {
       const uint32_t off = id.no0 + 3 * id.no1 + 9 * mm;
+      if (rot.kind >= 3 && mm >= Nmat * Nmat) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const uint32_t e = 9 * mm + c;
+          double2 v = make_double2(0.0, 0.0);
+          if (e < 3 * id.no1) v = reinterpret_cast<const double2*>(out)[id.no0 + e];
+          reinterpret_cast<double2*>(out)[off + c] = v;
+        }
+        continue;
+      }
       cplx acc[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) acc[c] = {0.0, 0.0};

@@ -650,13 +650,16 @@ __device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const MeshDev& 
 
 // in-order scan with the reference arithmetic (bz_move.cpp:262-285); taken by points within tolerance of a wedge
 // plane and by Brillouin zones for which the sign-pattern lookup is not available
-__device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, int& invridx) {
+// (`qs`: the rounding bounds of the certified tests were derived for |q_i| <= 4 rlu, true inside any first Brillouin zone; the
+// wedge rotation of an untranslated point, ir_moveinto_wedge, scales them with the point)
+__device__ __noinline__ bool wedge_scan(const BZDev& bz, double* q, int& ridx, int& invridx, double qs) {
   for (int j = 0; j < bz.n_ops; ++j) {
     int verdict = 2;  // 0 outside, 1 inside, 2 ask the reference arithmetic
     if (bz.wedge_fast) {
       // (G* n_k).(R_j^T q) evaluated as (R_j G* n_k).q; certain unless within eps_wedge of the threshold
       verdict = 1;
-      const double lo = -bz.cfg_abs * (1.0 + 4.0 * bz.cfg_rel) - bz.eps_wedge, hi = -bz.cfg_abs + bz.eps_wedge;
+      const double ew = bz.eps_wedge * qs;
+      const double lo = -bz.cfg_abs * (1.0 + 4.0 * bz.cfg_rel) - ew, hi = -bz.cfg_abs + ew;
       for (int k = 0; k < bz.n_wedge; ++k) {
         const double d = (bz.wc[j][k][0] * q[0] + bz.wc[j][k][1] * q[1]) + bz.wc[j][k][2] * q[2];
         if (d < lo) { verdict = 0; break; }
@@ -706,7 +709,9 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
     if (mode & MODE_NO_MOVE) {
       q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
       // BrillouinZone::isinside (bz.hpp:631-640): the conventional-lattice plane test moveinto re-checks its result with
-      if ((mode & MODE_ISINSIDE) && !inside_planes(bz, false, q, eps_o)) st = B200_ST_OUTSIDE_BZ;
+      if ((mode & MODE_ISINSIDE) &&
+          !inside_planes(bz, false, q, eps_o * fmax(1.0, 0.25 * fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2]))))))
+        st = B200_ST_OUTSIDE_BZ;
     } else {
       if (mode & MODE_NO_TAU) {  // ir_moveinto_wedge (bz_move.cpp:299-356): the rotation search on Q itself
         q[0] = Qi[0]; q[1] = Qi[1]; q[2] = Qi[2];
@@ -717,12 +722,14 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
         // ---- wedge rotation: bz_move.cpp:257-285 ----
         // fast path: signs of q on the distinct wedge-bounding planes -> operation index through a lookup table
         int pick = -1;
+        const double qs = (mode & MODE_NO_TAU) ? fmax(1.0, 0.25 * fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2])))) : 1.0;
         if (bz.n_wplanes > 0) {
           unsigned mask = 0;
           bool ambiguous = false;
+          const double band = bz.wband * qs;
           for (int p = 0; p < bz.n_wplanes; ++p) {
             const double d = (bz.wplane[p][0] * q[0] + bz.wplane[p][1] * q[1]) + bz.wplane[p][2] * q[2];
-            ambiguous |= fabs(d) <= bz.wband;
+            ambiguous |= fabs(d) <= band;
             mask |= (d > 0.0 ? 1u : 0u) << p;
           }
           if (!ambiguous) {
@@ -740,7 +747,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
             ridx = bz.inverse_index[pick];
           }
         } else if (!inside_wedge(bz, q)) {
-          done = wedge_scan(bz, q, ridx, invridx);
+          done = wedge_scan(bz, q, ridx, invridx, qs);
         }
         if (!done) {
           st |= B200_ST_OUTSIDE_WEDGE;

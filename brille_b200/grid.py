@@ -134,8 +134,10 @@ class B200Grid:
         the device tables; brille's host object is left untouched (its own ``ir_interpolate_at`` keeps interpolating
         unsorted data).  ``device=False`` runs brille's host ``sort`` and re-uploads the tables, as do grids whose
         eigenvectors are real (not offloaded, see the header)."""
-        data = _bridge().flatten_data(self._host) if self._host is not None else None
-        if not device or data is None or not np.iscomplexobj(np.asarray(data["vectors_data"])):
+        if self._host is None:
+            raise RuntimeError("sort() needs the brille host grid (this grid was built from flat tables only)")
+        data = _bridge().flatten_data(self._host)
+        if not device or not np.iscomplexobj(np.asarray(data["vectors_data"])):
             out = self._host.sort(*args, **kwargs)
             self._sync_data()
             return out
@@ -168,9 +170,19 @@ class B200Grid:
             raise RuntimeError("Interpolation requires one or more 3-vectors")
         return np.ascontiguousarray(Q)
 
-    def _outputs(self, n, pinned):
+    def _check_filled(self):
         if self._vals_shape is None:
             raise RuntimeError("The interpolation data must be filled before interpolating.")
+
+    def _check_device_tensor(self, t, shape, dtype, name, like):
+        """caller-provided device outputs: a wrong tensor would mean out-of-bounds or strided device writes"""
+        if not t.is_cuda or t.device != like.device:
+            raise RuntimeError(f"{name} must be a CUDA tensor on {like.device}")
+        if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)}")
+
+    def _outputs(self, n, pinned):
+        self._check_filled()
         vs, ws = (n,) + self._vals_shape, (n,) + self._vecs_shape
         if pinned:
             pv, pw = PinnedArray(vs, self._vals_dtype), PinnedArray(ws, self._vecs_dtype)
@@ -180,6 +192,7 @@ class B200Grid:
     def _run(self, fn, Q, no_move, probe, pinned, out=None):
         Q = self._check_q(Q)
         n = Q.shape[0]
+        self._check_filled()
         if out is not None:  # caller-provided (e.g. pinned, reused) output buffers
             vals, vecs = out
             keep = None
@@ -252,10 +265,16 @@ class B200Grid:
             raise RuntimeError("The interpolation data must be filled before interpolating.")
         tv = torch.complex128 if self._vals_dtype == np.complex128 else torch.float64
         tw = torch.complex128 if self._vecs_dtype == np.complex128 else torch.float64
+        if dQ.device.index != self.device:
+            raise RuntimeError(f"dQ is on {dQ.device}, the grid on cuda:{self.device}")
         if vals_out is None:
             vals_out = torch.empty((n,) + self._vals_shape, dtype=tv, device=dQ.device)
+        else:
+            self._check_device_tensor(vals_out, (n,) + self._vals_shape, tv, "vals_out", dQ)
         if vecs_out is None:
             vecs_out = torch.empty((n,) + self._vecs_shape, dtype=tw, device=dQ.device)
+        else:
+            self._check_device_tensor(vecs_out, (n,) + self._vecs_shape, tw, "vecs_out", dQ)
         s = stream if stream is not None else torch.cuda.current_stream(dQ.device)
         nf = C.c_uint64(0)
         rc = capi.lib().b200_ir_interpolate_at_device(
@@ -300,6 +319,8 @@ class B200Grid:
             vals, sf = out
             if vals.shape != (n,) + self._vals_shape or sf.shape != (n, M) or sf.dtype != np.float64 or vals.dtype != self._vals_dtype:
                 raise RuntimeError("out buffers have the wrong shape or dtype")
+            if not (vals.flags.c_contiguous and sf.flags.c_contiguous):
+                raise RuntimeError("out buffers must be C-contiguous")
             keep = None
         elif pinned:
             pv, ps = PinnedArray((n,) + self._vals_shape, self._vals_dtype), PinnedArray((n, M), np.float64)
@@ -324,12 +345,19 @@ class B200Grid:
             raise RuntimeError("The interpolation data must be filled before interpolating.")
         M = int(self._data_tables.vectors.branches)
         tv = torch.complex128 if self._vals_dtype == np.complex128 else torch.float64
+        if dQ.device.index != self.device:
+            raise RuntimeError(f"dQ is on {dQ.device}, the grid on cuda:{self.device}")
         if vals_out is None:
             vals_out = torch.empty((n,) + self._vals_shape, dtype=tv, device=dQ.device)
+        else:
+            self._check_device_tensor(vals_out, (n,) + self._vals_shape, tv, "vals_out", dQ)
         if sf_out is None:
             sf_out = torch.empty((n, M), dtype=torch.float64, device=dQ.device)
-        if scratch is not None and scratch.numel() * scratch.element_size() < n * self.row_bytes[1]:
-            raise RuntimeError("scratch is too small for the eigenvectors of all points")
+        else:
+            self._check_device_tensor(sf_out, (n, M), torch.float64, "sf_out", dQ)
+        if scratch is not None and (not scratch.is_cuda or scratch.device != dQ.device or not scratch.is_contiguous()
+                                    or scratch.numel() * scratch.element_size() < n * self.row_bytes[1]):
+            raise RuntimeError("scratch must be a contiguous CUDA tensor on the grid's device with room for the eigenvectors of all points")
         s = stream if stream is not None else torch.cuda.current_stream(dQ.device)
         nf = C.c_uint64(0)
         capi.check(capi.lib().b200_ir_structure_factor_device(
@@ -341,6 +369,17 @@ class B200Grid:
     @property
     def launch_count(self):
         return int(capi.lib().b200_grid_launch_count(self._handle))
+
+    @property
+    def last_path(self):
+        """B200_PATH_* bits of the kernels the last interpolation call took (1 two-kernel location, 2 on-the-fly cell kernel,
+        4 pipelined cell kernel, 8 general kernel for all points, 16 fused structure factor, 32 cooperative second location kernel)."""
+        return int(capi.lib().b200_grid_last_path(self._handle))
+
+    @property
+    def hot_path_taken(self):
+        """True when the last call ran the kernels the bench runs: two-kernel location + pipelined cell kernel."""
+        return (self.last_path & 5) == 5
 
     def enable_timing(self, on=True):
         capi.check(capi.lib().b200_grid_enable_timing(self._handle, 1 if on else 0))

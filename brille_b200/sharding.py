@@ -51,8 +51,9 @@ class ShardedGrid:
         self.grids = [B200Grid(host_grid, device=d) for d in devices]
 
     def ir_interpolate_at(self, Q, useparallel=False, threads=-1, do_not_move_points=False):
-        Q = np.ascontiguousarray(Q, dtype=np.float64)
         g0 = self.grids[0]
+        Q = g0._check_q(Q)
+        g0._check_filled()
         vals = np.empty((len(Q),) + g0._vals_shape, g0._vals_dtype)
         vecs = np.empty((len(Q),) + g0._vecs_shape, g0._vecs_dtype)
         errors = []
@@ -79,8 +80,9 @@ class ShardedGrid:
 
     def ir_structure_factor(self, Q, do_not_move_points=False):
         """``(vals, sf)`` of :meth:`B200Grid.ir_structure_factor`, the shards reduced on their own devices."""
-        Q = np.ascontiguousarray(Q, dtype=np.float64)
         g0 = self.grids[0]
+        Q = g0._check_q(Q)
+        g0._check_filled()
         vals = np.empty((len(Q),) + g0._vals_shape, g0._vals_dtype)
         sf = np.empty((len(Q), int(g0._data_tables.vectors.branches)), np.float64)
         errors = []

@@ -124,6 +124,35 @@ def c4_p21c_nest(b, density=2000, seed=14):
     return Workload("C4 P2_1/c 24 atoms / 72 modes nest", g, bz, 72, 24, _uniform_q(-3, 3), args)
 
 
+def nacl_conventional_lattice(b, a=5.64):
+    """NaCl conventional cell (Fm-3m, 8 atoms): the point group leaves the Na at the origin in place."""
+    pos = [[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [.5, .5, .5], [.5, 0, 0], [0, .5, 0], [0, 0, .5]]
+    return b.Lattice((a, a, a), (90, 90, 90), "Fm-3m", b.Basis(pos, [0, 0, 0, 0, 1, 1, 1, 1]))
+
+
+def gamma_matrix_grid(b, which="prim", density=60, seed=21, modes=3, cartesian=False):
+    """Gamma-rotated 3-vectors AND 3x3 matrices in one mode (interpolator_gamma.tpp:100-134): complex values with `no1` vectors
+    and 9 matrices (Nmat = 1: the reference rotates matrix 0 and copies the rest of the mode back from its work array).
+    ``prim``: NaCl primitive cell, 2 vectors; ``conv``: conventional cell, 8 vectors -- 24 vector elements reach into the
+    matrix part of the work array."""
+    lat = nacl_primitive_lattice(b) if which == "prim" else nacl_conventional_lattice(b)
+    n_at = 2 if which == "prim" else 8
+    bz = b.BrillouinZone(lat)
+    g = b.BZTrellisQcc(bz, bz.ir_polyhedron.volume / density)
+    nv = g.rlu.shape[0]
+    rng = np.random.default_rng(seed)
+
+    def rnd(shape):
+        return rng.normal(size=shape) + 1j * rng.normal(size=shape)
+
+    lu = 1 if cartesian else 3
+    vals = rnd((nv, modes, 1 + 3 * n_at))               # scalar + Gamma vectors
+    vecs = rnd((nv, modes, 2 + 3 * n_at + 81))          # 2 scalars + Gamma vectors + 9 matrices
+    args = (vals, (1, 3 * n_at, 0, 2, lu), vecs, (2, 3 * n_at, 81, 2, lu))
+    g.fill(*args)
+    return Workload(f"Gamma vectors+matrices NaCl {which}", g, bz, modes, n_at, _uniform_q(-2, 2), args)
+
+
 def powder_q(lat_to_xyz, n, seed):
     """C5 Q generator: |Q| ~ U(0.1, 10) 1/angstrom, isotropic directions, converted to rlu with B^-1."""
     rng = np.random.default_rng(seed)

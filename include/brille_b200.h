@@ -297,6 +297,15 @@ int b200_abi_version(void);
 int b200_device_count(void);
 /* number of kernels this library has launched on the grid since creation (bench.py's gpu_launches claim)  */
 uint64_t b200_grid_launch_count(const b200_grid_t* grid);
+/* which kernels the last interpolation call enqueued (a diagnostic for tests / the smoke run: a call with few points takes the
+ * single-kernel location and the general interpolation kernel, the bench takes the two-kernel location and the pipelined kernel) */
+#define B200_PATH_SPLIT_LOCATE 1u   /* two-kernel location, points regrouped by node / spatial bin in between           */
+#define B200_PATH_CELL_ONTHEFLY 2u  /* cell-batched kernel that stages and aligns the vertex rows per work item          */
+#define B200_PATH_CELL_PIPELINED 4u /* persistent pipelined cell kernel fed from the per-cell record table               */
+#define B200_PATH_GENERAL 8u        /* the general per-(Q, mode) kernel handled ALL points (not only the leftovers)       */
+#define B200_PATH_SF_FUSED 16u      /* structure factor reduced inside the pipelined cell kernel                          */
+#define B200_PATH_COOP_LOCATE 32u   /* second location kernel in its warp-cooperative form (node records staged in shared memory) */
+uint32_t b200_grid_last_path(const b200_grid_t* grid);
 /* average device time in ms of the kernels launched by the last *_device call, measured with CUDA events
  * on the launching stream when timing was enabled with b200_grid_enable_timing(grid, 1).
  * names: "locate", "sort", "interpolate", "consumer" (k_structure_factor of the unfused device-buffer call); returns <0 if

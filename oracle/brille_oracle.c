@@ -862,7 +862,9 @@ static int rotate_one(const b200_interp_desc_t* d, const b200_data_tables_t* dat
     memcpy(iRd, data->rot_cart + 9 * invridx, sizeof(iRd));
   }
   size_t need = (size_t)(no1 * 3u > no2 * 9u ? no1 * 3u : no2 * 9u);
-  cx* tA = (cx*)malloc(sizeof(cx) * (need ? need : 1));
+  /* zero-initialised like the reference's std::vector work array (:74,101,117): the elements behind the Nmat x Nmat rotated
+   * matrices are copied back from it as they are -- leftovers of the vector pass, zero beyond */
+  cx* tA = (cx*)calloc(need ? need : 1, sizeof(cx));
   cx* xc = (cx*)x;
   for (uint32_t b = 0; b < B; ++b) {
     size_t o = (size_t)b * S + no0;

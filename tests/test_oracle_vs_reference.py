@@ -94,3 +94,11 @@ def test_bz_methods(host, bridge, which):
     rc, pr = orc.moveinto(Q, 2)
     rqw, rRw = bz.ir_moveinto_wedge(Q)
     assert rc == 0 and np.array_equal(pr.q_ir, rqw) and np.array_equal(rots[pr.ridx], rRw) and not pr.tau.any()
+
+
+@pytest.mark.parametrize("which,cartesian", [("prim", False), ("conv", False), ("conv", True)])
+def test_gamma_vectors_and_matrices(host, probe, bridge, which, cartesian):
+    """RotatesLike::Gamma data with 3x3 matrices (interpolator_gamma.tpp:116-134): the reference rotates the first Nmat x Nmat
+    matrices and copies the rest of the mode back from the work array it shares with the vector pass."""
+    wl = W.gamma_matrix_grid(host, which, cartesian=cartesian)
+    _compare(host, probe, bridge, wl, 4000, 23)
