@@ -34,6 +34,7 @@ EXPORTS = (
     "b200_grid_row_bytes",
     "b200_grid_set_option",
     "b200_grid_sort_pairs",
+    "b200_solve_assignments",
     "b200_grid_set_structure_factor",
     "b200_ir_structure_factor",
     "b200_ir_structure_factor_device",
@@ -119,6 +120,8 @@ def lib():
     L.b200_grid_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.b200_grid_sort_pairs.restype = C.c_int
     L.b200_grid_sort_pairs.argtypes = [vp, vp, C.c_size_t, C.POINTER(SortConfig), vp, vp, vp]
+    L.b200_solve_assignments.restype = C.c_int
+    L.b200_solve_assignments.argtypes = [vp, C.c_size_t, C.c_uint32, vp, vp, C.c_int]
     L.b200_grid_set_structure_factor.restype = C.c_int
     L.b200_grid_set_structure_factor.argtypes = [vp, C.POINTER(SFConfig)]
     L.b200_ir_structure_factor.restype = C.c_int
@@ -135,6 +138,20 @@ def check(rc):
     if rc != 0:
         msg = lib().b200_last_error()
         raise B200Error(rc, msg.decode() if msg else f"brille_b200 error {rc}")
+
+
+def solve_assignments(cost, device=0):
+    """(row, col) solutions of the assignment problems ``cost`` (n, modes, modes) on the device (``b200_solve_assignments``)."""
+    import numpy as np
+
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    n, B, B2 = cost.shape
+    if B != B2:
+        raise ValueError("cost matrices must be square")
+    row = np.zeros((n, B), dtype=np.int32)
+    col = np.zeros((n, B), dtype=np.int32)
+    check(lib().b200_solve_assignments(cost.ctypes.data, n, B, row.ctypes.data, col.ctypes.data, int(device)))
+    return row, col
 
 
 def device_count() -> int:

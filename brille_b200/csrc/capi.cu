@@ -211,6 +211,7 @@ struct b200_grid {
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
   int split_locate = 1;    // trellis: two-kernel location with the points regrouped by node in between
+  int coop_locate = 1;     // trellis: second location kernel in its warp-cooperative form (node records staged in shared memory)
   int tile = 4;            // points per register tile of the pipelined cell kernel (4: 2 CTAs/SM, 2: 3 CTAs/SM)
   int cell_kernel = 0;     // 0 auto (pipelined kernel when its cell table fits), 1 on-the-fly staging kernel, 2 pipelined only
   unsigned char* cell_table = nullptr;  // pre-aligned per-cell records (cellinterp_tma.cu), built lazily per fill
@@ -231,7 +232,7 @@ struct b200_grid {
   uint64_t launches = 0;
   uint32_t last_path = 0;  // B200_PATH_* of the last enqueue
   bool timing = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, std::pair<double, int>> kernel_ms;  // name -> (sum ms, count) of the last device call
 };
 
@@ -413,6 +414,9 @@ static int build_trellis(b200_grid* g, const b200_trellis_tables_t* t) {
     d.n_knots[i] = t->n_knots[i];
     d.knot_offset[i] = (int)knots.size();
     knots.insert(knots.end(), t->knots[i], t->knots[i] + t->n_knots[i]);
+    const double span = t->knots[i][t->n_knots[i] - 1] - t->knots[i][0];
+    d.knot0[i] = t->knots[i][0];
+    d.knot_inv[i] = span > 0.0 ? (t->n_knots[i] - 1) / span : 0.0;
   }
   if (knots.size() > (size_t)MAX_KNOTS * 3) return fail(B200_E_INVALID, "too many trellis knots");
   if ((size_t)(t->n_knots[0] - 1) * (t->n_knots[1] - 1) * (t->n_knots[2] - 1) != t->n_nodes)
@@ -641,7 +645,7 @@ extern "C" int b200_grid_create(int kind, const b200_bz_tables_t* bz, const void
         cudaHostAlloc(&g->stage[s].h_fail, N_FAIL * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
       rc = fail(B200_E_CUDA, "stream/counter creation failed");
   }
-  for (int i = 0; i < 6 && rc == B200_OK; ++i)
+  for (int i = 0; i < 8 && rc == B200_OK; ++i)
     if (cudaEventCreate(&g->ev[i]) != cudaSuccess) rc = fail(B200_E_CUDA, "event creation failed");
   if (rc != B200_OK) {
     b200_grid_destroy(g);
@@ -677,7 +681,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
     if (h.h_fail) cudaFreeHost(h.h_fail);
     if (h.stream) cudaStreamDestroy(h.stream);
   }
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
     if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;
 }
@@ -852,8 +856,10 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   CU(ws.ensure(n, nb, chunk, 0u, nsub, split ? n_nodes_alloc : ws.n_nodes));
   if (reset_fail) CU(cudaMemsetAsync(d_fail, 0, N_FAIL * sizeof(unsigned long long), stream));
   LocateOut lo = ws.lo;
-  lo.x_ir = ws.x_ir;
-  lo.tau = ws.tau;
+  if (want_probe) {  // x_ir and tau leave the kernel only for a caller who asked for them (36 bytes per point)
+    lo.x_ir = ws.x_ir;
+    lo.tau = ws.tau;
+  }
   if (cell) {
     lo.key = ws.key;
     lo.rank = ws.rank;
@@ -871,10 +877,13 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
     lo.bin_shift = bin_shift;
     CU(cudaMemsetAsync(ws.node_count, 0, ((size_t)n_nodes + 1) * sizeof(uint32_t), stream));
     CU(launch_locate(g->d_bz, g->gd, dQ, n, mode | MODE_SPLIT_A, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
+    if (g->timing) cudaEventRecord(g->ev[6], stream);
     BucketDev nbk = ws.nbk;  // (allocated for the finest level of bins; this call uses n_nodes of them + the "no node" bucket)
     nbk.n_buckets = n_nodes + 1;
     CU(launch_bucket_sort(nbk, ws.key, ws.rank, n, g->sm_count, stream));
-    CU(launch_locate_in_node(g->d_bz, g->gd, n, mode, lo, ws.nbk.order, d_fail, g->sm_count, stream));
+    if (g->timing) cudaEventRecord(g->ev[7], stream);
+    CU(launch_locate_in_node(g->d_bz, g->gd, n, mode, lo, ws.nbk.order, d_fail, g->sm_count, stream, g->coop_locate != 0));
+    if (g->coop_locate && trellis) g->last_path |= B200_PATH_COOP_LOCATE;
     g->launches += 6;
   } else {
     CU(launch_locate(g->d_bz, g->gd, dQ, n, mode, g->eps_w, g->eps_o, lo, d_fail, g->sm_count, stream));
@@ -934,6 +943,11 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   if (g->timing) {
     cudaEventSynchronize(interp ? g->ev[3] : g->ev[1]);
     note_time(g, "locate", g->ev[0], g->ev[1]);
+    if (split) {  // the parts of the two-kernel location
+      note_time(g, "locate_a", g->ev[0], g->ev[6]);
+      note_time(g, "locate_sort", g->ev[6], g->ev[7]);
+      note_time(g, "locate_b", g->ev[7], g->ev[1]);
+    }
     if (interp) {
       note_time(g, "sort", g->ev[1], g->ev[2]);
       note_time(g, "interpolate", g->ev[2], g->ev[3]);
@@ -1387,6 +1401,20 @@ extern "C" int b200_grid_sort_pairs(b200_grid_t* g, const uint32_t* pairs, size_
   return B200_OK;
 }
 
+extern "C" int b200_solve_assignments(const double* cost, size_t n, uint32_t modes, int32_t* row_out, int32_t* col_out, int device) {
+  if (n && (!cost || !row_out || !col_out)) return fail(B200_E_INVALID, "NULL argument");
+  if (modes == 0) return fail(B200_E_INVALID, "modes must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_E_CUDA, "no CUDA device available; brille_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(B200_E_INVALID, "device index out of range");
+  DeviceGuard guard;
+  CU(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  CU(run_match_only(cost, n, modes, row_out, col_out, sms));
+  return B200_OK;
+}
+
 extern "C" int b200_grid_enable_timing(b200_grid_t* g, int on) {
   if (!g) return fail(B200_E_INVALID, "NULL grid");
   g->timing = on != 0;
@@ -1407,6 +1435,8 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
     g->interp_path = (int)value;
   } else if (n == "split_locate") {
     g->split_locate = value != 0;
+  } else if (n == "coop_locate") {
+    g->coop_locate = value != 0;
   } else if (n == "tile") {
     if (value != 2 && value != 4) return fail(B200_E_INVALID, "tile must be 2 or 4");
     g->tile = (int)value;

@@ -52,6 +52,7 @@ struct TrellisDev {
   int n_knots[3];
   int knot_offset[3];
   const double* knots;  // concatenated knot vectors
+  double knot0[3], knot_inv[3];  // first knot and bins per unit length of every axis: the guess of find_bin
   uint32_t n_nodes;
   const uint8_t* node_type;
   const uint32_t* node_index;
@@ -280,7 +281,7 @@ cudaError_t launch_locate(const BZDev* bzg, const GridDev& gd, const double* Q, 
                           double eps_o, const LocateOut& out, unsigned long long* fail_count, int sm_count,
                           cudaStream_t stream);
 cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n, uint32_t mode, const LocateOut& out, const uint32_t* order,
-                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream);
+                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream, bool coop = true);
 cudaError_t launch_interp(const DataDev& dd, const LocateIn& in, size_t n, int ir, double* vals, double* vecs, int sm_count,
                           cudaStream_t stream, const uint32_t* order, const uint32_t* segment, uint32_t compact_cap = 0,
                           unsigned long long* overflow = nullptr);
@@ -305,15 +306,14 @@ struct SortWorkspace {
   uint32_t branches = 0;
   uint32_t* pairs = nullptr;
   double* cost = nullptr;
-  double* fwork = nullptr;
   int* row = nullptr;
   int* col = nullptr;
-  int* iwork = nullptr;
   cudaError_t ensure(size_t n_pairs, uint32_t branches);
   void release();
 };
 cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun, const double w_mult[3], int w_vfun, const uint32_t* h_pairs,
                            size_t n_pairs, int32_t* h_row, int32_t* h_col, double* h_cost, int sm_count, size_t max_ws_bytes,
                            SortWorkspace& ws, uint64_t* launches);
+cudaError_t run_match_only(const double* h_cost, size_t n, uint32_t B, int32_t* h_row, int32_t* h_col, int sm_count);
 
 }  // namespace b200

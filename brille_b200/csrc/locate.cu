@@ -16,6 +16,7 @@
 namespace b200 {
 
 #define TWO_PI 6.283185307179586476925286766559005768394338798750211641949889
+constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ bool approx_eq(double a, double b, double rel, double abs_) {
   double x = fabs(a - b);  // approx_float.hpp:171-188
@@ -127,6 +128,7 @@ __device__ __forceinline__ uint32_t moveinto_one(const BZDev& bz, double eps_w, 
       // N = round(d/|tau_j|) (bz_move.cpp:30): multiply by the reciprocal, and divide exactly only when the quotient is
       // within 1e-9 of a rounding boundary (half-integers) where the last bit could matter
       double quo = d * bz.inv_tau_lens[j];
+      if (quo < 0.499999) continue;  // N = round(d/|tau_j|) <= 0 for certain: the face plays no part (bz_move.cpp:31-34)
       const double fr = quo - floor(quo);
       if (fabs(fr - 0.5) < 1e-9) quo = d / bz.tau_lens[j];
       int N = (int)round(quo);
@@ -174,14 +176,16 @@ __device__ __forceinline__ uint32_t moveinto_one(const BZDev& bz, double eps_w, 
 // ---------------------------------------------------------------------------------------------------
 // trellis
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_bin(const double* k, int n, double x) {
-  // trellis_poly.hpp:67-73: index of the first knot > x (knots ascend => binary search is the same scan)
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (k[mid] > x) hi = mid; else lo = mid + 1;
-  }
-  int d = lo;
+__device__ __forceinline__ int find_bin(const double* k, int n, double x, double k0, double inv) {
+  // trellis_poly.hpp:67-73: index d of the first knot > x (the reference scans; the knots ascend).  The knots of a trellis are
+  // (nearly) uniform (trellis_poly.hpp:635-641): d - 1 is guessed from the spacing and corrected by comparing with the knots
+  // themselves, so the result is the scan's for any ascending knot vector; usually two loads instead of a binary search.
+  int g = (int)((x - k0) * inv);
+  g = max(-1, min(g, n - 1));
+  if (x != x) g = n - 1;  // (no knot compares greater than NaN: the scan ends at n)
+  while (g + 1 < n && k[g + 1] <= x) ++g;
+  while (g >= 0 && k[g] > x) --g;
+  int d = g + 1;
   if (d > n - 1 && x < k[0]) d = 0;
   return d > 0 ? d - 1 : d;
 }
@@ -265,7 +269,7 @@ __device__ __forceinline__ uint32_t trellis_find_node(const BZDev& bz, const Tre
   uint32_t st = 0;
   cell = 0xffffffffu;
   int sub[3];
-  for (int d = 0; d < 3; ++d) sub[d] = find_bin(knots + t.knot_offset[d], t.n_knots[d], x[d]);
+  for (int d = 0; d < 3; ++d) sub[d] = find_bin(knots + t.knot_offset[d], t.n_knots[d], x[d], t.knot0[d], t.knot_inv[d]);
   bool bad = !sub_ok(t, sub);
   if (bad) {  // trellis_poly.hpp:391-424
     int close[3], num_close = 0, ns[3] = {sub[0], sub[1], sub[2]};
@@ -702,6 +706,10 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
   uint32_t* pending_at = nullptr;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double Qi[3] = {Q[3 * i], Q[3 * i + 1], Q[3 * i + 2]};
+    {  // the point of the next trip on its way into L2 (the warps of a CTA are too few to hide a DRAM round trip)
+      const size_t i_next = i + (size_t)gridDim.x * blockDim.x;
+      if (i_next < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Q + 3 * i_next));
+    }
     double q[3];
     int tau[3] = {0, 0, 0};
     int ridx = bz.identity_index, invridx = bz.identity_index;
@@ -752,6 +760,9 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
         if (!done) {
           st |= B200_ST_OUTSIDE_WEDGE;
           ridx = invridx = 0;
+          // ir_moveinto_wedge: the reference leaves the zero-initialised output row of such a point and does not fail
+          // (bz_move.cpp:348-354 re-tests the OUTPUT row, and the origin is inside every wedge)
+          if (mode & MODE_NO_TAU) q[0] = q[1] = q[2] = 0.0;
         }
       }
     }
@@ -831,7 +842,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       out.rank[i] = atomicAdd(out.cell_count + key, 1u);
     }
     f_bz += (st & B200_ST_OUTSIDE_BZ) != 0 && !(mode & MODE_ISINSIDE);  // (isinside reports, it does not fail)
-    f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
+    f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0 && !(mode & MODE_NO_TAU);
     f_find += (st & B200_ST_NOT_FOUND) != 0;
   }
   if (pending_at) *pending_at = pending_rank;
@@ -938,9 +949,264 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
   if (f_find) atomicAdd(fail_count + 2, f_find);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second kernel of the split TRELLIS location, warp-cooperative form (the default).
+//
+// The points arrive sorted by node, so the 32 points of a warp sit in one node (a node holds thousands of points; one warp in
+// a hundred straddles two).  k_locate_in_node lets every lane walk the node's records on its own: each step is a dependent load
+// from L2 (long-scoreboard stalls were 5.5 per issued instruction).  Here the warp copies the records of the node -- the cube's
+// 8 corners, or the tetrahedra of a triangulated node in blocks of TET_BLOCK -- into its slice of shared memory once, coalesced,
+// and the lanes scan them from there.  Same arithmetic in the same order as trellis_in_node: identical bits.
+// The parked point of the warp's next tile is fetched a tile ahead (its sort order two tiles ahead).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TET_BLOCK = 32;                            // tetrahedra staged per round
+constexpr int COOP_WARPS = 4;                            // warps per CTA
+constexpr int COOP_SLICE = TET_BLOCK * TET_PACK;         // doubles per warp (4608 bytes; a cube record needs 28)
+
+__global__ void __launch_bounds__(COOP_WARPS * 32, 4)
+k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, LocateOut out, const uint32_t* __restrict__ order,
+                       unsigned long long* __restrict__ fail_count) {
+  __shared__ __align__(16) double s_rec[COOP_WARPS][COOP_SLICE];
+  const TrellisDev& tr = gd.tr;
+  const double rel = bzg->def_rel, abs_ = bzg->def_abs;
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  double* const rec = s_rec[wib];
+  unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
+  const size_t n_tiles = (n + 31) / 32, tile_stride = (size_t)gridDim.x * COOP_WARPS;
+  size_t tile = (size_t)blockIdx.x * COOP_WARPS + wib;
+  if (tile >= n_tiles) return;
+  // pipeline registers: the point of this tile, and the sort order of the next
+  auto order_at = [&](size_t t) { const size_t p = t * 32 + lane; return t < n_tiles && p < n ? order[p] : 0xffffffffu; };
+  auto parked_at = [&](uint32_t i, double2& a, double2& b) {
+    if (i != 0xffffffffu) {
+      const double2* src = reinterpret_cast<const double2*>(out.parked + i);
+      a = src[0];
+      b = src[1];
+    }
+  };
+  uint32_t i_cur = order_at(tile), i_nxt = order_at(tile + tile_stride);
+  double2 pa = make_double2(0.0, 0.0), pb = pa, na = pa, nb = pa;
+  parked_at(i_cur, pa, pb);
+  for (; tile < n_tiles; tile += tile_stride) {
+    const uint32_t i_nn = order_at(tile + 2 * tile_stride);
+    parked_at(i_nxt, na, nb);  // (in flight while this tile is worked on)
+    const size_t p = tile * 32 + lane;
+    const bool valid = i_cur != 0xffffffffu;
+    const size_t i = valid ? i_cur : 0;
+    const double x[3] = {pa.x, pa.y, pb.x};
+    const uint32_t rot_st = (uint32_t)__double2loint(pb.y);
+    const uint32_t cell = (uint32_t)__double2hiint(pb.y);
+    uint32_t st = rot_st >> 16;
+    const int invridx = (int)((rot_st >> 8) & 0xffu);
+    int tet = -1, n_emit = 0;
+    uint64_t slots = 0;
+    double w[8];
+    bool generic = false;   // every corner of the cell carries weight: the weights go out with two vector stores
+    bool keep[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w[j] = 0.0; keep[j] = false; }
+    bool is_cube = false;
+    // ---- node by node (normally one) ----------------------------------------------------------------------------------
+    unsigned todo = __ballot_sync(FULL_MASK, valid && !(st & B200_ST_NOT_FOUND));
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const uint32_t node = __shfl_sync(FULL_MASK, cell, leader);
+      const bool mine = valid && !(st & B200_ST_NOT_FOUND) && cell == node;
+      todo &= ~__ballot_sync(FULL_MASK, mine);
+      const uint32_t payload = tr.node_index[node];
+      if (tr.node_type[node] == B200_NODE_CUBE) {
+        // corners (24 doubles) through shared memory; CubeNode::indices_weights (trellis_node.hpp:130-149)
+        if (lane < 12) reinterpret_cast<double2*>(rec)[lane] = reinterpret_cast<const double2*>(tr.cube_pack + 24 * (size_t)payload)[lane];
+        __syncwarp();
+        if (mine) {
+          is_cube = true;
+          const double vol = (fabs(rec[0] - rec[21]) * fabs(rec[1] - rec[22])) * fabs(rec[2] - rec[23]);
+          bool all = true;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            w[c] = ((fabs(x[0] - rec[3 * c]) * fabs(x[1] - rec[3 * c + 1])) * fabs(x[2] - rec[3 * c + 2])) / vol;
+            keep[c] = !approx_eq(w[c], 0.0, rel, abs_) && w[c] > 0.0;  // w.is(gt, 0.)
+            all &= keep[c];
+          }
+          generic = all;
+          n_emit = 8;
+          slots = 0x0001020304050607ull;
+        }
+        __syncwarp();
+      } else {
+        // PolyNode::indices_weights (trellis_node.hpp:273-308): first tetrahedron, in storage order, that contains the point
+        const uint32_t t0 = tr.poly_offsets[payload], t1 = tr.poly_offsets[payload + 1];
+        double best = 0.0;
+        uint32_t best_at = t0;
+        bool have_best = false;
+        int found = -1;
+        for (uint32_t base = t0; base < t1; base += TET_BLOCK) {
+          if (!__ballot_sync(FULL_MASK, mine && found < 0)) break;
+          const uint32_t nblk = min((uint32_t)TET_BLOCK, t1 - base);
+          {
+            const double2* src = reinterpret_cast<const double2*>(tr.tet_pack + (size_t)TET_PACK * base);
+            for (uint32_t c = lane; c < nblk * (TET_PACK / 2); c += 32) reinterpret_cast<double2*>(rec)[c] = src[c];
+          }
+          __syncwarp();
+          if (mine && found < 0) {
+            // circumsphere test of every tetrahedron of the block (tetrahedra_might_contain :349-364), then the weights of the
+            // candidates in storage order (first accepted wins, :284-290); `best` keeps max_element's first-maximum rule
+            unsigned cand = 0u;
+            for (uint32_t k = 0; k < nblk; ++k) {
+              const double* tp = rec + TET_PACK * k;
+              const double v0 = tp[0] - x[0], v1 = tp[1] - x[1], v2 = tp[2] - x[2];
+              const double d2 = ((0.0 + v0 * v0) + v1 * v1) + v2 * v2;
+              if (d2 < tp[3] || approx_eq(d2, tp[3], rel, abs_)) {
+                cand |= 1u << k;
+              } else {
+                const double mn = -d2;
+                if (!have_best || mn > best || (mn == best && base + k < best_at)) {
+                  best = mn;
+                  best_at = base + k;
+                  have_best = true;
+                }
+              }
+            }
+            while (cand && found < 0) {
+              const uint32_t kk = (uint32_t)(__ffs((int)cand) - 1);
+              cand &= cand - 1u;
+              const double mn = tet_weights(rec + TET_PACK * kk, x, w, rel, abs_);
+              if (mn >= 0.0) {
+                found = (int)(base + kk);
+              } else if (!have_best || mn > best || (mn == best && base + kk < best_at)) {
+                best = mn;
+                best_at = base + kk;
+                have_best = true;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (mine) {
+          if (found < 0) {
+            if (t1 == t0) {
+              st |= B200_ST_NOT_FOUND;
+            } else {
+              st |= B200_ST_FALLBACK_TET;  // trellis_node.hpp:295-306
+              found = (int)best_at;
+              tet_weights(tr.tet_pack + (size_t)TET_PACK * best_at, x, w, rel, abs_);
+            }
+          }
+          if (found >= 0) {
+            tet = found;
+            bool all = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              keep[j] = !approx_eq(w[j], 0.0, rel, abs_);
+              all &= keep[j];
+            }
+            generic = all;
+            n_emit = 4;
+            slots = 0x03020100ull;
+#pragma unroll
+            for (int j = 4; j < 8; ++j) w[j] = 0.0;
+          }
+        }
+      }
+    }
+    // ---- outputs (as k_locate_in_node) -----------------------------------------------------------------------------------
+    if (valid) {
+      double* const wrow = out.weight + REC_DOUBLES * i;
+      __align__(16) uint32_t vtmp[8];
+      bool wrote_vertices = false;
+      if (generic) {
+        st32(wrow, w[0], w[1], w[2], w[3]);
+        st32(wrow + 4, w[4], w[5], w[6], w[7]);
+      } else {
+        // a point on a face / edge / vertex of its cell, or one that was not found: compact emission (rare)
+        EmitOut e;
+        e.v = vtmp;
+        e.w = wrow;
+        e.n = 0;
+        e.slots = 0;
+        if (n_emit) {
+          uint32_t vi[8];
+          if (is_cube) {
+            const uint4* vip = reinterpret_cast<const uint4*>(tr.cube_vertices + 8 * (size_t)tr.node_index[cell]);
+            const uint4 va = vip[0], vb = vip[1];
+            vi[0] = va.x; vi[1] = va.y; vi[2] = va.z; vi[3] = va.w; vi[4] = vb.x; vi[5] = vb.y; vi[6] = vb.z; vi[7] = vb.w;
+          } else {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(tr.tet_vertices + 4 * (size_t)tet);
+            vi[0] = v4.x; vi[1] = v4.y; vi[2] = v4.z; vi[3] = v4.w;
+          }
+          double wc[8];  // (copies: the arrays handed to the out-of-line routine live in local memory, w and keep must not)
+          bool kc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { wc[j] = w[j]; kc[j] = keep[j]; }
+          emit_compact(e, vi, wc, kc, is_cube ? 8 : 4, is_cube);
+        }
+        if (e.n == 0) {
+          for (int j = 0; j < 8; ++j) { vtmp[j] = 0xffffffffu; wrow[j] = 0.0; }
+          if (n_emit) st |= B200_ST_NOT_FOUND;
+        }
+        n_emit = e.n;
+        slots = e.slots;
+        wrote_vertices = true;
+      }
+      const uint32_t general = gd.cells.n_cubes + gd.cells.n_tets;
+      uint32_t key = general;
+      if (generic && !(st & (B200_ST_OUTSIDE_BZ | B200_ST_OUTSIDE_WEDGE | B200_ST_NOT_FOUND)))
+        key = tet >= 0 ? gd.cells.n_cubes + (uint32_t)tet : gd.cells.node_index[cell];
+      const bool in_cell_bucket = key != general;
+      key = key * out.sub + (uint32_t)invridx;
+      {
+        const unsigned active = __activemask();
+        const unsigned same = __match_any_sync(active, key);
+        const int lead = __ffs(same) - 1;
+        uint32_t first = 0;
+        if ((int)lane == lead) first = atomicAdd(out.cell_count + key, (uint32_t)__popc(same));
+        first = __shfl_sync(same, first, lead);
+        out.key[p] = key;
+        out.rank[p] = first + (uint32_t)__popc(same & ((1u << lane) - 1u));
+      }
+      if (!(out.lean && in_cell_bucket)) {  // per-point arrays only the probe and the general kernel read
+        if (!wrote_vertices) {
+          if (is_cube) {
+            const uint4* vip = reinterpret_cast<const uint4*>(tr.cube_vertices + 8 * (size_t)tr.node_index[cell]);
+            const uint4 va = vip[0], vb = vip[1];
+            vtmp[0] = vb.w; vtmp[1] = vb.z; vtmp[2] = vb.y; vtmp[3] = vb.x; vtmp[4] = va.w; vtmp[5] = va.z; vtmp[6] = va.y; vtmp[7] = va.x;
+          } else {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(tr.tet_vertices + 4 * (size_t)tet);
+            vtmp[0] = v4.x; vtmp[1] = v4.y; vtmp[2] = v4.z; vtmp[3] = v4.w;
+            vtmp[4] = vtmp[5] = vtmp[6] = vtmp[7] = 0xffffffffu;
+          }
+        }
+        uint4* vo = reinterpret_cast<uint4*>(out.vertex + 8 * i);
+        vo[0] = make_uint4(vtmp[0], vtmp[1], vtmp[2], vtmp[3]);
+        vo[1] = make_uint4(vtmp[4], vtmp[5], vtmp[6], vtmp[7]);
+        out.cell[i] = cell;
+        out.tet[i] = tet;
+        out.n_vert[i] = n_emit;
+        out.slots[i] = slots;
+        out.status[i] = st;
+      }
+      f_bz += (st & B200_ST_OUTSIDE_BZ) != 0;
+      f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
+      f_find += (st & B200_ST_NOT_FOUND) != 0;
+    }
+    i_cur = i_nxt;
+    i_nxt = i_nn;
+    pa = na;
+    pb = nb;
+  }
+  if (f_bz) atomicAdd(fail_count + 0, f_bz);
+  if (f_wedge) atomicAdd(fail_count + 1, f_wedge);
+  if (f_find) atomicAdd(fail_count + 2, f_find);
+}
+
 cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n, uint32_t mode, const LocateOut& out, const uint32_t* order,
-                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream) {
+                                  unsigned long long* fail_count, int sm_count, cudaStream_t stream, bool coop) {
   if (n == 0) return cudaSuccess;
+  if (coop && gd.kind == B200_GRID_TRELLIS) {
+    const size_t tiles = (n + 31) / 32, want_c = (tiles + COOP_WARPS - 1) / COOP_WARPS, cap_c = (size_t)sm_count * 16;
+    k_trellis_in_node_coop<<<(unsigned)(want_c < cap_c ? want_c : cap_c), COOP_WARPS * 32, 0, stream>>>(bzg, gd, n, out, order, fail_count);
+    return cudaGetLastError();
+  }
   const size_t want = (n + 127) / 128, cap = (size_t)sm_count * 32;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   switch (gd.kind) {

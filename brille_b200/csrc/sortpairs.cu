@@ -9,7 +9,8 @@
 //   k_pair_costs   one thread per cost-matrix entry (pair, mode i, mode j): the anti-phase e^{-i arg<a|b>}, then the scalar,
 //                  vector and matrix costs of the two rows, in the reference's operation order (compiled without FMA
 //                  contraction; the transcendental functions are CUDA's, not glibc's: costs agree to ~1 ulp)
-//   k_pair_assign  one thread per pair: the Jonker-Volgenant solver, same control flow as the reference (idx = int)
+//   k_pair_match   one warp per pair: the assignment problem with the reference's decisions (ties included), every scan over
+//                  the columns lane-parallel, work arrays in shared memory (see match_pair)
 //
 // Permutations are integers: the tests demand equality with the reference's for every pair (ties of the cost are the only
 // place where the 1-ulp difference of the transcendental functions could show; none occurs in the test grids).
@@ -222,184 +223,342 @@ __global__ void __launch_bounds__(256) k_pair_costs(InterpDev values, InterpDev 
   }
 }
 
-// lapjv (lapjv.hpp:281-538) for one pair; work arrays of `dim` entries each live in global memory
-__device__ void lapjv_one(int dim, const double* assign_cost, int* rowsol, int* colsol, double* v, double* d, int* freerows,
-                          int* collist, int* matches, int* pred) {
-  if (1 == dim) {
-    rowsol[0] = colsol[0] = 0;
-    return;
-  }
-  for (int i = 0; i < dim; i++) matches[i] = 0;
-  double total_cost = 0;
-  for (int tc = 0; tc < dim * dim; ++tc) total_cost += assign_cost[tc];
-  const double cost_epsilon = total_cost / (double)(10000 * dim);
-  // COLUMN REDUCTION
-  for (int j = dim; j-- > 0;) {
-    double mn = assign_cost[j];
-    int imin = 0;
-    for (int i = 1; i < dim; i++) {
-      const double c = assign_cost[i * dim + j];
-      if (c < mn) {
-        mn = c;
-        imin = i;
-      }
-    }
-    v[j] = mn;
-    if (++matches[imin] == 1) {
-      rowsol[imin] = j;
-      colsol[j] = imin;
-    } else {
-      colsol[j] = -1;
-    }
-  }
-  // REDUCTION TRANSFER
-  int numfree = 0;
-  for (int i = 0; i < dim; i++) {
-    const double* local_cost = assign_cost + i * dim;
-    if (matches[i] == 0) {
-      freerows[numfree++] = i;
-    } else if (matches[i] == 1) {
-      const int j1 = rowsol[i];
-      double mn = DBL_MAX;
-      for (int j = 0; j < dim; j++)
-        if (j != j1)
-          if (local_cost[j] - v[j] < mn + cost_epsilon) mn = local_cost[j] - v[j];
-      v[j1] = v[j1] - mn;
-    }
-  }
-  // AUGMENTING ROW REDUCTION
-  for (int loopcnt = 0; loopcnt < 2; loopcnt++) {
-    int k = 0;
-    const int prevnumfree = numfree;
-    numfree = 0;
-    while (k < prevnumfree) {
-      const int i = freerows[k++];
-      const double* local_cost = assign_cost + i * dim;  // find_umins_plain (lapjv.hpp:74-99)
-      double umin = local_cost[0] - v[0];
-      int j1 = 0, j2 = -1;
-      double usubmin = DBL_MAX;
-      for (int j = 1; j < dim; j++) {
-        const double h = local_cost[j] - v[j];
-        if (h < usubmin) {
-          if (h >= umin) {
-            usubmin = h;
-            j2 = j;
-          } else {
-            usubmin = umin;
-            umin = h;
-            j2 = j1;
-            j1 = j;
-          }
-        }
-      }
-      int i0 = colsol[j1];
-      const double vj1_new = v[j1] - (usubmin + cost_epsilon - umin);
-      const bool vj1_lowers = vj1_new < v[j1];
-      if (vj1_lowers) {
-        v[j1] = vj1_new;
-      } else if (i0 != -1) {
-        j1 = j2;
-        i0 = colsol[j2];
-      }
-      rowsol[i] = j1;
-      colsol[j1] = i;
-      if (i0 != -1) {
-        if (vj1_lowers) freerows[--k] = i0;
-        else freerows[numfree++] = i0;
-      }
-    }
-  }
-  // AUGMENT SOLUTION for each free row
-  for (int f = 0; f < numfree; f++) {
-    int endofpath = 0;
-    const int freerow = freerows[f];
-    for (int j = 0; j < dim; j++) {
-      d[j] = assign_cost[freerow * dim + j] - v[j];
-      pred[j] = freerow;
-      collist[j] = j;
-    }
-    int low = 0, up = 0;
-    bool unassigned_found = false;
-    int last = 0;
-    double mn = 0;
-    do {
-      if (up == low) {
-        last = low - 1;
-        mn = d[collist[up++]];
-        for (int k = up; k < dim; k++) {
-          const int j = collist[k];
-          const double h = d[j];
-          if (h <= mn) {
-            if (h < mn) {
-              up = low;
-              mn = h;
-            }
-            collist[k] = collist[up];
-            collist[up++] = j;
-          }
-        }
-        for (int k = low; k < up; k++)
-          if (colsol[collist[k]] == -1) {
-            endofpath = collist[k];
-            unassigned_found = true;
-            break;
-          }
-      }
-      if (!unassigned_found) {
-        const int j1 = collist[low];
-        low++;
-        const int i = colsol[j1];
-        const double* local_cost = assign_cost + i * dim;
-        const double h = local_cost[j1] - v[j1] - mn;
-        for (int k = up; k < dim; k++) {
-          const int j = collist[k];
-          const double v2 = local_cost[j] - v[j] - h;
-          if (v2 < d[j]) {
-            pred[j] = i;
-            if (v2 == mn) {
-              if (colsol[j] == -1) {
-                endofpath = j;
-                unassigned_found = true;
-                break;
-              } else {
-                collist[k] = collist[up];
-                collist[up++] = j;
-              }
-            }
-            d[j] = v2;
-          }
-        }
-      }
-    } while (!unassigned_found);
-    for (int k = 0; k <= last; k++) {
-      const int j1 = collist[k];
-      v[j1] = v[j1] + d[j1] - mn;
-    }
-    int i;
-    do {
-      i = pred[endofpath];
-      colsol[endofpath] = i;
-      const int j1 = endofpath;
-      endofpath = rowsol[i];
-      rowsol[i] = j1;
-    } while (i != freerow);
+// ---------------------------------------------------------------------------------------------------------------------
+// Assignment solver: one WARP per vertex pair, work arrays in shared memory.
+//
+// The reference solves every pair with a sequential Jonker-Volgenant routine (lapjv.hpp:281-538).  Its result depends on the
+// order in which ties are met, so a different algorithm (or a different scan order) would give other -- equally cheap --
+// permutations.  Here every scan over the columns is replaced by a lane-parallel formulation that provably takes the same
+// decisions (oracle/lap_model.py states them in numpy and is checked against the sequential restatement on tie-heavy
+// matrices; tests/test_sort_oracle.py):
+//
+//   column minima   per-column arg-min, lowest row among equals; a row keeps the LARGEST column that chose it (the reference
+//                   walks the columns downwards, first claim wins)                                     lapjv.hpp:311-335
+//   dual transfer   the reference's tolerant running minimum `if (h < mn + eps) mn = h` is a recurrence, not a minimum: 32
+//                   columns at a time, ballot the columns below mn + eps, the first one sets mn, re-ballot behind it
+//                                                                                                     lapjv.hpp:340-358
+//   row bidding     (umin, j1) = lexicographic minimum of (h_j, j); (usubmin, j2) the same without j1 -- what the scan of
+//                   find_umins_plain (lapjv.hpp:74-99) ends with                                       lapjv.hpp:365-410
+//   augmenting path a scan moves the prefix-minimum records of d over the to-do list (new minimum, or tie with the running
+//                   minimum) to the ready list: found with a warp prefix-min, applied in list order; a relaxation step
+//                   flags (improved, ties the minimum, unassigned) per column: the first unassigned tie ends the path, the
+//                   ties before it join the ready list in list order                                   lapjv.hpp:416-520
+//
+// The tolerance eps = sum(cost) / (10000 dim) is summed in storage order with one accumulator, as the reference does
+// (lapjv.hpp:305-307): it enters comparisons.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PairWork {  // per-warp arrays of `dim` entries each, carved from dynamic shared memory
+  double* v;       // column duals
+  double* d;       // path distances (scratch h_j during the bidding)
+  int* rowsol;
+  int* colsol;
+  int* pred;       // row before a column on the alternating path (row chosen per column during the column minima)
+  int* todo;       // column to-do list of a path: [0, low) scanned, [low, up) ready, [up, dim) to do
+  int* freerow;    // unassigned rows
+  int* claims;     // how many columns chose a row
+};
+__host__ __device__ inline size_t pair_work_bytes(uint32_t dim) { return (size_t)dim * (2 * sizeof(double) + 6 * sizeof(int)); }
+
+constexpr unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ void lexmin_reduce(double& val, int& idx) {  // minimum value, lowest index among equals, in every lane
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(FULL, val, o);
+    const int oi = __shfl_xor_sync(FULL, idx, o);
+    if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
   }
 }
 
-__global__ void __launch_bounds__(128) k_pair_assign(uint32_t B, size_t n_pairs, const double* __restrict__ cost, int* __restrict__ row,
-                                                     int* __restrict__ col, double* __restrict__ fwork, int* __restrict__ iwork) {
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (size_t)gridDim.x * blockDim.x) {
-    double* fw = fwork + p * 2 * B;  // v, d
-    int* iw = iwork + p * 4 * B;     // free rows, column list, matches, predecessors
-    lapjv_one((int)B, cost + p * B * B, row + p * B, col + p * B, fw, fw + B, iw, iw + B, iw + 2 * B, iw + 3 * B);
+__device__ void match_pair(const int dim, const double* __restrict__ C, const PairWork& w, const int lane) {
+  if (dim == 1) {
+    if (lane == 0) w.rowsol[0] = w.colsol[0] = 0;
+    return;
   }
+  // ---- tolerance: the entries summed in storage order (every lane runs the same chain on coalesced loads) ---------------
+  double total = 0.0;
+  for (int base = 0; base < dim * dim; base += 32) {
+    const double x = base + lane < dim * dim ? C[base + lane] : 0.0;
+    const int cnt = min(32, dim * dim - base);
+    for (int k = 0; k < cnt; ++k) total += __shfl_sync(FULL, x, k);
+  }
+  const double eps = total / (double)(10000 * dim);
+  // ---- column minima ------------------------------------------------------------------------------------------------
+  for (int j = lane; j < dim; j += 32) { w.claims[j] = 0; w.rowsol[j] = -1; }
+  __syncwarp();
+  for (int j = lane; j < dim; j += 32) {
+    double mn = C[j];
+    int at = 0;
+    for (int i = 1; i < dim; ++i) {
+      const double c = C[(size_t)i * dim + j];
+      if (c < mn) { mn = c; at = i; }
+    }
+    w.v[j] = mn;
+    w.pred[j] = at;
+    atomicAdd(w.claims + at, 1);
+    atomicMax(w.rowsol + at, j);
+  }
+  __syncwarp();
+  for (int j = lane; j < dim; j += 32) {
+    const int at = w.pred[j];
+    w.colsol[j] = w.rowsol[at] == j ? at : -1;
+  }
+  __syncwarp();
+  // ---- dual transfer (rows in order: later rows see the duals lowered by earlier ones) ----------------------------------
+  int nfree = 0;
+  for (int i = 0; i < dim; ++i) {
+    const int c = w.claims[i];
+    if (c == 0) {
+      if (lane == 0) w.freerow[nfree] = i;
+      ++nfree;
+    } else if (c == 1) {
+      const int j1 = w.rowsol[i];
+      double mn = DBL_MAX;
+      for (int base = 0; base < dim; base += 32) {
+        const int j = base + lane;
+        const bool in = j < dim && j != j1;
+        const double h = in ? C[(size_t)i * dim + j] - w.v[j] : 0.0;
+        int start = 0;
+        for (;;) {
+          const unsigned below = __ballot_sync(FULL, in && lane >= start && h < mn + eps);
+          if (!below) break;
+          const int first = __ffs(below) - 1;
+          mn = __shfl_sync(FULL, h, first);
+          start = first + 1;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) w.v[j1] = w.v[j1] - mn;
+      __syncwarp();
+    }
+  }
+  // ---- row bidding: two sweeps over the unassigned rows (the list is consumed and refilled in place) ----------------------
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    int k = 0;
+    const int n_todo = nfree;
+    nfree = 0;
+    __syncwarp();
+    while (k < n_todo) {
+      const int i = w.freerow[k++];
+      double umin = DBL_MAX;
+      int j1 = dim;
+      for (int j = lane; j < dim; j += 32) {  // (ascending per lane: the first of equal values stays)
+        const double h = C[(size_t)i * dim + j] - w.v[j];
+        w.d[j] = h;
+        if (h < umin) { umin = h; j1 = j; }
+      }
+      lexmin_reduce(umin, j1);
+      double usub = DBL_MAX;
+      int j2 = dim;
+      for (int j = lane; j < dim; j += 32) {
+        const double h = w.d[j];  // (written by this lane)
+        if (j != j1 && h < usub) { usub = h; j2 = j; }
+      }
+      lexmin_reduce(usub, j2);
+      int i0 = w.colsol[j1];
+      const double vj = w.v[j1];
+      const double lowered = vj - (usub + eps - umin);
+      const bool lowers = lowered < vj;
+      __syncwarp();
+      if (!lowers && i0 != -1) {  // the dual cannot move and the column is taken: bid for the second best instead
+        j1 = j2;
+        i0 = w.colsol[j2];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (lowers) w.v[j1] = lowered;
+        w.rowsol[i] = j1;
+        w.colsol[j1] = i;
+        if (i0 != -1) {
+          if (lowers) w.freerow[k - 1] = i0;  // the displaced row bids next
+          else w.freerow[nfree] = i0;
+        }
+      }
+      if (i0 != -1) {
+        if (lowers) --k; else ++nfree;
+      }
+      __syncwarp();
+    }
+  }
+  // ---- one shortest augmenting path per row that is still unassigned --------------------------------------------------
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  for (int f = 0; f < nfree; ++f) {
+    const int start_row = w.freerow[f];
+    for (int j = lane; j < dim; j += 32) {
+      w.d[j] = C[(size_t)start_row * dim + j] - w.v[j];
+      w.pred[j] = start_row;
+      w.todo[j] = j;
+    }
+    __syncwarp();
+    int low = 0, up = 0, last = 0, end = -1;
+    double mn = 0.0;
+    while (end < 0) {
+      if (up == low) {
+        // scan: the columns of the to-do list whose distance is a new minimum, or ties the running minimum, in list order
+        last = low - 1;
+        double run = INF;
+        for (int base = low; base < dim; base += 32) {
+          const int k = base + lane;
+          const bool in = k < dim;
+          const int j = in ? w.todo[k] : 0;
+          const double h = in ? w.d[j] : INF;
+          double pm = h;  // inclusive prefix minimum over the lanes
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(FULL, pm, o);
+            if (lane >= o) pm = fmin(pm, t);
+          }
+          double before = __shfl_up_sync(FULL, pm, 1);
+          if (lane == 0) before = INF;
+          before = fmin(before, run);
+          unsigned record = __ballot_sync(FULL, in && h <= before);
+          const unsigned fresh = __ballot_sync(FULL, in && h < before);
+          while (record) {
+            const int p = __ffs(record) - 1;
+            record &= record - 1u;
+            const int jj = __shfl_sync(FULL, j, p);
+            if ((fresh >> p) & 1u) {
+              up = low;
+              mn = __shfl_sync(FULL, h, p);
+            }
+            if (lane == 0) {
+              w.todo[base + p] = w.todo[up];
+              w.todo[up] = jj;
+            }
+            ++up;
+          }
+          run = fmin(run, __shfl_sync(FULL, pm, 31));
+        }
+        __syncwarp();
+        for (int base = low; base < up && end < 0; base += 32) {  // an unassigned column among the ready ones ends the path
+          const int k = base + lane;
+          const int j = k < up ? w.todo[k] : 0;
+          const unsigned open = __ballot_sync(FULL, k < up && w.colsol[j] == -1);
+          if (open) end = __shfl_sync(FULL, j, __ffs(open) - 1);
+        }
+        if (end >= 0) break;
+      }
+      // relax through the row of the next ready column
+      const int j1 = w.todo[low++];
+      const int i = w.colsol[j1];
+      const double h1 = C[(size_t)i * dim + j1] - w.v[j1] - mn;
+      const int first = up;
+      for (int base = first; base < dim && end < 0; base += 32) {
+        const int k = base + lane;
+        const bool in = k < dim;
+        const int j = in ? w.todo[k] : 0;
+        const double v2 = in ? C[(size_t)i * dim + j] - w.v[j] - h1 : 0.0;
+        const bool better = in && v2 < w.d[j];
+        const bool tie = better && v2 == mn;
+        const unsigned closing = __ballot_sync(FULL, tie && w.colsol[j] == -1);
+        const int stop = closing ? __ffs(closing) - 1 : 32;
+        if (better && lane <= stop) w.pred[j] = i;
+        if (better && lane < stop) w.d[j] = v2;
+        unsigned joins = __ballot_sync(FULL, tie) & (stop >= 32 ? FULL : ((1u << stop) - 1u));
+        while (joins) {
+          const int p = __ffs(joins) - 1;
+          joins &= joins - 1u;
+          const int jj = __shfl_sync(FULL, j, p);
+          if (lane == 0) {
+            w.todo[base + p] = w.todo[up];
+            w.todo[up] = jj;
+          }
+          ++up;
+        }
+        if (closing) end = __shfl_sync(FULL, j, stop);
+      }
+      __syncwarp();
+    }
+    // duals of the scanned columns, then flip the assignments along the path back to the starting row
+    for (int k = lane; k <= last; k += 32) {
+      const int j = w.todo[k];
+      w.v[j] = w.v[j] + w.d[j] - mn;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int at = end, i;
+      do {
+        i = w.pred[at];
+        w.colsol[at] = i;
+        const int was = w.rowsol[i];
+        w.rowsol[i] = at;
+        at = was;
+      } while (i != start_row);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pair_match(uint32_t B, size_t n_pairs, const double* __restrict__ cost, int* __restrict__ row,
+                                                    int* __restrict__ col) {
+  extern __shared__ __align__(16) unsigned char pm_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  unsigned char* base = pm_smem + (size_t)wid * ((pair_work_bytes(B) + 15) / 16 * 16);
+  PairWork w;
+  w.v = reinterpret_cast<double*>(base);
+  w.d = w.v + B;
+  w.rowsol = reinterpret_cast<int*>(w.d + B);
+  w.colsol = w.rowsol + B;
+  w.pred = w.colsol + B;
+  w.todo = w.pred + B;
+  w.freerow = w.todo + B;
+  w.claims = w.freerow + B;
+  for (size_t p = (size_t)blockIdx.x * wpc + wid; p < n_pairs; p += (size_t)gridDim.x * wpc) {
+    match_pair((int)B, cost + p * B * B, w, lane);
+    __syncwarp();
+    for (uint32_t j = lane; j < B; j += 32) {
+      row[p * B + j] = w.rowsol[j];
+      col[p * B + j] = w.colsol[j];
+    }
+    __syncwarp();
+  }
+}
+
+// warps per CTA and dynamic shared memory of k_pair_match for `B` modes (0: too many modes for one warp's work arrays)
+static int pair_match_config(uint32_t B, size_t* smem) {
+  const size_t per_warp = (pair_work_bytes(B) + 15) / 16 * 16;
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  if (per_warp * warps > 200 * 1024) return 0;
+  *smem = per_warp * warps;
+  return warps;
+}
+static cudaError_t launch_pair_match(uint32_t B, size_t n, const double* cost, int* row, int* col, int sm_count) {
+  size_t smem = 0;
+  const int warps = pair_match_config(B, &smem);
+  if (!warps) return cudaErrorInvalidConfiguration;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_pair_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const size_t want = (n + warps - 1) / warps, cap = (size_t)sm_count * 16;
+  k_pair_match<<<(unsigned)(want < cap ? want : cap), warps * 32, smem>>>(B, n, cost, row, col);
+  return cudaGetLastError();
+}
+
+// the solver on its own: cost matrices from the host, permutations back (diagnostic entry point b200_solve_assignments)
+cudaError_t run_match_only(const double* h_cost, size_t n, uint32_t B, int32_t* h_row, int32_t* h_col, int sm_count) {
+  if (n == 0 || B == 0) return cudaSuccess;
+  double* dc = nullptr;
+  int *dr = nullptr, *dl = nullptr;
+  cudaError_t e = cudaMalloc(&dc, n * B * B * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dr, n * B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&dl, n * B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(dc, h_cost, n * B * B * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_pair_match(B, n, dc, dr, dl, sm_count);
+  if (e == cudaSuccess) e = cudaMemcpy(h_row, dr, n * B * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(h_col, dl, n * B * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dc); cudaFree(dr); cudaFree(dl);
+  return e;
 }
 
 // host side: pairs are processed in batches so that the cost matrices stay within `max_ws_bytes`; the work space is kept
 // by the caller between calls (cudaMalloc / cudaFree cost more than the kernels)
 void SortWorkspace::release() {
-  cudaFree(pairs); cudaFree(cost); cudaFree(fwork); cudaFree(row); cudaFree(col); cudaFree(iwork);
-  pairs = nullptr; cost = fwork = nullptr; row = col = iwork = nullptr;
+  cudaFree(pairs); cudaFree(cost); cudaFree(row); cudaFree(col);
+  pairs = nullptr; cost = nullptr; row = col = nullptr;
   batch = 0; branches = 0;
 }
 cudaError_t SortWorkspace::ensure(size_t n, uint32_t B) {
@@ -408,8 +567,6 @@ cudaError_t SortWorkspace::ensure(size_t n, uint32_t B) {
   cudaError_t e;
   if ((e = cudaMalloc(&pairs, n * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&cost, n * B * B * sizeof(double))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&fwork, n * 2 * B * sizeof(double))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&iwork, n * 4 * B * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&row, n * B * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&col, n * B * sizeof(int))) != cudaSuccess) return e;
   batch = n;
@@ -426,7 +583,7 @@ cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun
   for (int i = 0; i < 3; ++i) { cfg.v_mult[i] = v_mult[i]; cfg.w_mult[i] = w_mult[i]; }
   cfg.v_vfun = v_vfun;
   cfg.w_vfun = w_vfun;
-  const size_t per_pair = (size_t)B * B * 8 + (size_t)B * (2 * 4 + 2 * 8 + 4 * 4) + 8;
+  const size_t per_pair = (size_t)B * B * 8 + (size_t)B * (2 * 4) + 8;
   size_t batch = max_ws_bytes / per_pair;
   if (batch < 1) batch = 1;
   if (batch > n_pairs) batch = n_pairs;
@@ -438,10 +595,9 @@ cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun
     if ((e = cudaMemcpy(ws.pairs, h_pairs + 2 * lo, n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     const size_t entries = n * B * B, want = (entries + 255) / 256, cap = (size_t)sm_count * 32;
     k_pair_costs<<<(unsigned)(want < cap ? want : cap), 256>>>(dd.values, dd.vectors, cfg, ws.pairs, n, ws.cost);
-    const size_t want2 = (n + 127) / 128;
-    k_pair_assign<<<(unsigned)(want2 < cap ? want2 : cap), 128>>>(B, n, ws.cost, ws.row, ws.col, ws.fwork, ws.iwork);
-    if (launches) *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_pair_match(B, n, ws.cost, ws.row, ws.col, sm_count)) != cudaSuccess) return e;
+    if (launches) *launches += 2;
     if ((e = cudaMemcpy(h_row + lo * B, ws.row, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     if ((e = cudaMemcpy(h_col + lo * B, ws.col, n * B * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     if (h_cost && (e = cudaMemcpy(h_cost + lo * B * B, ws.cost, n * B * B * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;

@@ -223,7 +223,8 @@ int b200_interpolate_at(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t 
 /* BrillouinZone.ir_moveinto (wrap/_bz.cpp:434-463) / moveinto (:378-405) on the device; host buffers;
  * fills probe->q_ir, tau, ridx, invridx, status (x_ir if requested).  ir = 1 ir_moveinto, 0 moveinto,
  * 2 ir_moveinto_wedge (wrap/_bz.cpp:498-520, bz_move.cpp:299-356: the wedge rotation of Q itself, no translation; ridx is
- * the operation with Q = R q_ir), 3 isinside (wrap/_bz.cpp:378-384, bz.hpp:631-640: probe->status gets B200_ST_OUTSIDE_BZ
+ * the operation with Q = R q_ir; like the reference it does not fail: a point no operation places comes back as q_ir = 0 with
+ * operation 0 and B200_ST_OUTSIDE_WEDGE in probe->status), 3 isinside (wrap/_bz.cpp:378-384, bz.hpp:631-640: probe->status gets B200_ST_OUTSIDE_BZ
  * for the points outside the first Brillouin zone; never fails).                                             */
 int b200_moveinto(b200_grid_t* grid, const double* Q, size_t nQ, int ir, b200_probe_t* probe);
 
@@ -246,6 +247,11 @@ typedef struct b200_sort_config {
 } b200_sort_config_t;
 int b200_grid_sort_pairs(b200_grid_t* grid, const uint32_t* pairs, size_t n_pairs, const b200_sort_config_t* config,
                          int32_t* row_out, int32_t* col_out, double* cost_out);
+
+/* The assignment solver of sort() on its own: `n` cost matrices (n x modes x modes, host) in, the row and column solutions the
+ * reference's lapjv (lapjv.hpp:281-538) returns for each of them out -- ties included.  Used by the tests to drive the solver
+ * with matrices full of ties, which grids do not produce.  Runs on `device`; synchronous.                              */
+int b200_solve_assignments(const double* cost, size_t n, uint32_t modes, int32_t* row_out, int32_t* col_out, int device);
 
 /* ---- device-resident consumer: one-phonon structure factor ----------------------------------
  * What brille's callers do with the output of ir_interpolate_at straight away (Euphonic's BrilleInterpolator /
@@ -308,7 +314,8 @@ uint64_t b200_grid_launch_count(const b200_grid_t* grid);
 uint32_t b200_grid_last_path(const b200_grid_t* grid);
 /* average device time in ms of the kernels launched by the last *_device call, measured with CUDA events
  * on the launching stream when timing was enabled with b200_grid_enable_timing(grid, 1).
- * names: "locate", "sort", "interpolate", "consumer" (k_structure_factor of the unfused device-buffer call); returns <0 if
+ * names: "locate" (and its parts "locate_a", "locate_sort", "locate_b" when the two-kernel location ran), "sort", "interpolate",
+ * "consumer" (k_structure_factor of the unfused device-buffer call); returns <0 if
  * unknown / not timed.                                                                                              */
 int b200_grid_enable_timing(b200_grid_t* grid, int on);
 double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
@@ -322,6 +329,7 @@ double b200_grid_kernel_ms(const b200_grid_t* grid, const char* name);
  * factor reduced inside the pipelined cell kernel whenever possible / always through the eigenvector scratch; "bounce" 1
  * (default) / 0: pageable host destinations through page-locked bounce buffers and host threads / plain device-to-pageable
  * copies; "split_locate" 1 (default) / 0: two-kernel location with the points regrouped in between / single kernel;
+ * "coop_locate" 1 (default) / 0: trellis, second location kernel warp-cooperative (node records staged in shared memory) / per lane;
  * "replay_stores" 1: diagnostic, with timing enabled the output stores of the pipelined kernel are replayed on their own
  * and timed as "replay" (b200_grid_kernel_ms)                                                                       */
 int b200_grid_set_option(b200_grid_t* grid, const char* name, double value);

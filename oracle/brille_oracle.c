@@ -946,12 +946,18 @@ int oracle_moveinto(const b200_bz_tables_t* bz, const double* Q, size_t nQ, int 
       probe_store(probe, i, q, x, tau, r, ri, NULL, st);
       continue;
     }
-    if (ir == 2) st = wedge_rotate_one(bz, Q + 3 * i, q, &r, &ri);
-    else st = ir ? ir_moveinto_one(bz, Q + 3 * i, q, tau, &r, &ri) : moveinto_one(bz, Q + 3 * i, q, tau);
+    if (ir == 2) {
+      st = wedge_rotate_one(bz, Q + 3 * i, q, &r, &ri);
+      /* a point no operation places: the reference counts it but then only re-tests the OUTPUT row, which still holds its
+       * zero initialisation and passes (bz_move.cpp:348-354) -- q = 0, operation 0, no error */
+      if (st & B200_ST_OUTSIDE_WEDGE) q[0] = q[1] = q[2] = 0.0;
+    } else {
+      st = ir ? ir_moveinto_one(bz, Q + 3 * i, q, tau, &r, &ri) : moveinto_one(bz, Q + 3 * i, q, tau);
+    }
     matvec_dd(x, bz->to_xyz, q);
     probe_store(probe, i, q, x, tau, r, ri, NULL, st);
     if ((st & B200_ST_OUTSIDE_BZ) && !rc) rc = B200_E_OUTSIDE_BZ;
-    if ((st & B200_ST_OUTSIDE_WEDGE) && !rc) rc = B200_E_OUTSIDE_WEDGE;
+    if ((st & B200_ST_OUTSIDE_WEDGE) && ir != 2 && !rc) rc = B200_E_OUTSIDE_WEDGE;
   }
   return rc;
 }

@@ -184,16 +184,15 @@ def test_points_shared_by_many_cells(host, bridge, cls, args):
 @pytest.mark.parametrize("which", ["C3", "C2", "F23", "P3_timereversal", "Im-3m"])
 def test_wedge_rotation_of_far_points(host, bridge, which):
     """ir_moveinto_wedge does not translate (bz_move.cpp:299-356): |Q| up to 1e3 rlu reaches the sign-pattern lookup and the
-    certified wedge test, whose rounding bounds must scale with |Q|.  Bit for bit against the reference's own method and the oracle;
+    certified wedge test, whose rounding bounds must scale with |Q|.  Bit for bit against the reference's own method and the oracle
+    (including the far points on wedge planes that no operation places: the reference returns q = 0, operation 0, no error);
     isinside for the same points."""
     wl = W.BUILDERS[which](host) if which in W.BUILDERS else W.zoo_grid(host, which)
     g = brille_b200.accelerate(wl.grid)
     bz = wl.bz
-    rng = np.random.default_rng(11)
-    base = rng.uniform(-1, 1, (40000, 3))
-    scale = 10.0 ** rng.uniform(-3, 3, (40000, 1))
-    special = rng.integers(-4, 5, (4000, 3)).astype(float)  # on the wedge planes, scaled exactly by powers of two
-    Q = np.vstack([base * scale, special * 2.0 ** rng.integers(-3, 9, (4000, 1)), np.zeros((1, 3))])
+    from test_oracle_vs_reference import far_points
+
+    Q = far_points()
     rots = np.asarray(bridge.flatten_bz(bz)["rotations"]).reshape(-1, 3, 3)
     qw, rw = g.ir_moveinto_wedge(Q)
     rqw, rRw = bz.ir_moveinto_wedge(Q)

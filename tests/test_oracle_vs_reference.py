@@ -96,6 +96,32 @@ def test_bz_methods(host, bridge, which):
     assert rc == 0 and np.array_equal(pr.q_ir, rqw) and np.array_equal(rots[pr.ridx], rRw) and not pr.tau.any()
 
 
+def far_points(seed=11, n=40000):
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(-1, 1, (n, 3))
+    scale = 10.0 ** rng.uniform(-3, 3, (n, 1))
+    special = rng.integers(-4, 5, (n // 10, 3)).astype(float)  # on the wedge planes, scaled exactly by powers of two
+    return np.vstack([base * scale, special * 2.0 ** rng.integers(-3, 9, (n // 10, 1)), np.zeros((1, 3))])
+
+
+@pytest.mark.parametrize("which", ["C3", "C2", "F23", "P3_timereversal", "Im-3m"])
+def test_wedge_rotation_of_far_points(host, bridge, which):
+    """ir_moveinto_wedge does not translate: |Q| up to 1e3 rlu.  Far points ON a wedge plane can fail every operation's tolerance
+    test; the reference then returns the zero-initialised row (q = 0, operation 0) without an error (bz_move.cpp:348-354)."""
+    from brille_b200 import tables as T
+
+    wl = W.BUILDERS[which](host, density=100) if which in W.BUILDERS else W.zoo_grid(host, which)
+    bz = wl.bz
+    orc = Oracle(bridge.flatten(wl.grid), bridge.flatten_data(wl.grid))
+    Q = far_points()
+    rots = np.asarray(bridge.flatten_bz(bz)["rotations"]).reshape(-1, 3, 3)
+    rc, pr = orc.moveinto(Q, 2)
+    rqw, rRw = bz.ir_moveinto_wedge(Q)
+    assert rc == 0 and np.array_equal(pr.q_ir, rqw) and np.array_equal(rots[pr.ridx], rRw)
+    rc, pr = orc.moveinto(Q, 3)
+    assert np.array_equal((pr.status & T.ST_OUTSIDE_BZ) == 0, np.asarray(bz.isinside(Q), dtype=bool))
+
+
 @pytest.mark.parametrize("which,cartesian", [("prim", False), ("conv", False), ("conv", True)])
 def test_gamma_vectors_and_matrices(host, probe, bridge, which, cartesian):
     """RotatesLike::Gamma data with 3x3 matrices (interpolator_gamma.tpp:116-134): the reference rotates the first Nmat x Nmat

@@ -54,3 +54,49 @@ def test_sort_oracle_vector_cost_functions(host, bridge):
         rc, row, col = orc.sort_pairs(data, plan)
         assert rc == 0
         assert np.array_equal(row.astype(np.uint32), ref[:, 0, :]) and np.array_equal(col.astype(np.uint32), ref[:, 1, :]), vcf
+
+
+def tie_heavy_matrices(seed=0):
+    """cost matrices full of ties (small integers, rounded decimals, constant rows / columns) next to generic ones"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for B, n, kind in [(1, 3, "int"), (2, 100, "int"), (3, 200, "int"), (6, 200, "int"), (12, 200, "int"), (12, 200, "float"), (33, 40, "int"),
+                       (72, 12, "float"), (72, 12, "int"), (40, 40, "bin"), (12, 200, "dec"), (65, 10, "bin"), (12, 50, "neg")]:
+        if kind == "int":
+            c = rng.integers(0, 4, (n, B, B)).astype(float)
+        elif kind == "bin":
+            c = rng.integers(0, 2, (n, B, B)).astype(float)
+        elif kind == "dec":
+            c = np.round(rng.uniform(0, 2, (n, B, B)), 1)
+        elif kind == "neg":
+            c = rng.integers(-3, 3, (n, B, B)).astype(float)
+        else:
+            c = rng.uniform(0, 1, (n, B, B))
+        out.append(c)
+    return out
+
+
+def test_lane_parallel_formulation_equals_sequential_solver():
+    """The device solver (brille_b200/csrc/sortpairs.cu: match_pair) replaces the sequential scans of lapjv.hpp by lane-parallel
+    formulations; oracle/lap_model.py states them in numpy.  They must take the decisions of the sequential restatement
+    (oracle/sort_oracle.c, pinned on the reference above) on every matrix, ties included."""
+    from oracle import lap_model
+
+    for c in tie_heavy_matrices():
+        r, cc = orc.lapjv_batch(c)
+        r2, c2 = lap_model.solve_batch(c)
+        assert np.array_equal(r, r2) and np.array_equal(cc, c2), c.shape
+
+
+@pytest.mark.gpu
+def test_device_solver_on_tie_heavy_matrices():
+    from brille_b200 import capi
+
+    for c in tie_heavy_matrices():
+        r, cc = orc.lapjv_batch(c)
+        r2, c2 = capi.solve_assignments(c)
+        assert np.array_equal(r, r2) and np.array_equal(cc, c2), c.shape
+    big = np.random.default_rng(3).integers(0, 5, (3, 200, 200)).astype(float)  # more modes than a grid ever has
+    r, cc = orc.lapjv_batch(big)
+    r2, c2 = capi.solve_assignments(big)
+    assert np.array_equal(r, r2) and np.array_equal(cc, c2)
