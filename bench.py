@@ -12,7 +12,8 @@ replicated, no collective on the data path).  One step = one pass of the whole p
 The printed JSON line follows the driver's contract.  `value` is timed with CUDA events with Q and the outputs
 resident in HBM; `e2e` goes through the host-buffer C-ABI call (pinned host buffers, H2D of Q and D2H of both
 results inside the timed region); `roofline` is the dominant (interpolation) kernel against the measured HBM copy
-bandwidth; `cpu_baseline` is the reference's own OpenMP implementation (oracle/_ref) on the host cores.
+bandwidth; `cpu_baseline` is the reference's own OpenMP implementation (the unmodified build, third_party/brille_host) on
+the host cores.
 """
 from __future__ import annotations
 
@@ -39,11 +40,11 @@ Q_SEED = 3
 
 
 def build_workload():
-    """Host-side construction with brille's own C++ (oracle/_ref is the unmodified reference build)."""
-    from oracle import ref
+    """Host-side construction with brille's own C++ (brille_b200.host: an installed brille, or third_party/brille_host)."""
+    from brille_b200 import host
     from brille_b200 import workloads as W
 
-    return W.c3_p63mmc(ref.host())
+    return W.c3_p63mmc(host.get())
 
 
 WORKLOAD_TEXT = {
@@ -163,9 +164,9 @@ def _config_specs(world):
     """(key, text, builder, points per GPU per step, points per call, Q maker or None)"""
     from brille_b200 import workloads as W
     from brille_b200 import _bridge
-    from oracle import ref
+    from brille_b200 import host
 
-    b = ref.host()
+    b = host.get()
 
     def powder(wl, n, seed):
         return np.ascontiguousarray(W.powder_q(np.asarray(_bridge.flatten_bz(wl.bz)["to_xyz"]), n, seed))
@@ -264,7 +265,7 @@ def measure_config(torch, dist, brille_b200, spec, local, rank, world, steps, pe
 
 
 def cpu_reference_rate(wl, nq, threads, repeats=1):
-    """The reference's own ir_interpolate_at (oracle/_ref, unmodified brille) on the host cores."""
+    """The reference's own ir_interpolate_at (unmodified brille, third_party/brille_host) on the host cores."""
     Q = make_q(wl, nq, Q_SEED + 100)
     best = None
     for _ in range(repeats):
@@ -297,7 +298,7 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(wl, {"reference_sample_q_per_step": nq}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{nq} Q per step of the same workload, brille ir_interpolate_at(Q, True, {cores}) from oracle/_ref"},
+                         "sample": f"{nq} Q per step of the same workload, brille ir_interpolate_at(Q, True, {cores}), unmodified reference build (third_party/brille_host)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -505,7 +506,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             rate, secs = cpu_reference_rate(wl, CPU_SAMPLE_NQ, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"{CPU_SAMPLE_NQ} Q of the same workload in one call of the unmodified reference (oracle/_ref) ir_interpolate_at(Q, True, {cores}): {secs:.1f} s"}
+                   "sample": f"{CPU_SAMPLE_NQ} Q of the same workload in one call of the unmodified reference (third_party/brille_host) ir_interpolate_at(Q, True, {cores}): {secs:.1f} s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "per_rank_ms_per_step": per_rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -357,7 +357,7 @@ class B200Grid:
             self._check_device_tensor(sf_out, (n, M), torch.float64, "sf_out", dQ)
         if scratch is not None and (not scratch.is_cuda or scratch.device != dQ.device or not scratch.is_contiguous()
                                     or scratch.numel() * scratch.element_size() < n * self.row_bytes[1]):
-            raise RuntimeError("scratch must be a contiguous CUDA tensor on the grid's device with room for the eigenvectors of all points")
+            raise RuntimeError("scratch is too small for the eigenvectors of all points (or not a contiguous CUDA tensor on the grid's device)")
         s = stream if stream is not None else torch.cuda.current_stream(dQ.device)
         nf = C.c_uint64(0)
         capi.check(capi.lib().b200_ir_structure_factor_device(

@@ -14,9 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import brille_b200  # noqa: E402
 from brille_b200 import workloads as W  # noqa: E402
-from oracle import ref  # noqa: E402
+from brille_b200 import host as _hostmod  # noqa: E402
 
-b = ref.host()
+b = _hostmod.get()
 name = sys.argv[1]
 variants, nq, steps = [], None, 5
 for a in sys.argv[2:]:

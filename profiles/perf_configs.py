@@ -10,9 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import brille_b200  # noqa: E402
 from brille_b200 import workloads as W  # noqa: E402
-from oracle import ref  # noqa: E402
+from brille_b200 import host as _hostmod  # noqa: E402
 
-b = ref.host()
+b = _hostmod.get()
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C1", "C2", "C3", "C3nest", "C3mesh", "C4"]
 
 
