@@ -14,6 +14,7 @@
 //
 // Permutations are integers: the tests demand equality with the reference's for every pair (ties of the cost are the only
 // place where the 1-ulp difference of the transcendental functions could show; none occurs in the test grids).
+#include <algorithm>
 #include <cfloat>
 
 #include "device_tables.cuh"
@@ -155,16 +156,16 @@ __device__ double vectorfun_c(int vfun, uint32_t n, const double2* a, const Phas
   }
 }
 
-// Interpolator::add_cost for one entry (mode i of vertex i0, mode j of vertex i1)
-__device__ double entry_cost(const InterpDev& t, const double* mult, int vfun, uint32_t i0, uint32_t i1, uint32_t i, uint32_t j,
-                             bool arbitrary_phase) {
-  const uint32_t e0 = t.no0, e1 = 3u * t.no1, e2 = 9u * t.no2, s_ = t.span, B = t.branches, mo_ = e0 + e1;
+// Interpolator::add_cost for one entry: `row_i` is mode i of the first vertex, `row_j` mode j of the second (span elements each,
+// in global or shared memory)
+__device__ double entry_cost(const InterpDev& t, const double* mult, int vfun, const void* row_i, const void* row_j, bool arbitrary_phase) {
+  const uint32_t e0 = t.no0, e1 = 3u * t.no1, e2 = 9u * t.no2, s_ = t.span, mo_ = e0 + e1;
   if (s_ == 0) return 0.0;
   double s_cost = 0, v_cost = 0, m_cost = 0;
   if (t.is_complex) {
-    const double2* x0i = reinterpret_cast<const double2*>(t.data) + ((size_t)i0 * B + i) * s_;
+    const double2* x0i = static_cast<const double2*>(row_i);
     PhasedRow rhs;
-    rhs.b = reinterpret_cast<const double2*>(t.data) + ((size_t)i1 * B + j) * s_;
+    rhs.b = static_cast<const double2*>(row_j);
     rhs.phased = arbitrary_phase;
     rhs.f = make_double2(1.0, 0.0);
     if (arbitrary_phase) {  // antiphase (utilities.tpp:567-579): polar(1, -atan2(Im <a|b>, Re <a|b>))
@@ -190,8 +191,8 @@ __device__ double entry_cost(const InterpDev& t, const double* mult, int vfun, u
     if (e2)
       for (uint32_t m = 0; m < e2 / 9; ++m) m_cost += vector_distance_c(9, x0i + mo_ + 9u * m, rhs, mo_ + 9u * m);
   } else {
-    const double* x0i = t.data + ((size_t)i0 * B + i) * s_;
-    const double* x1j = t.data + ((size_t)i1 * B + j) * s_;
+    const double* x0i = static_cast<const double*>(row_i);
+    const double* x1j = static_cast<const double*>(row_j);
     if (e0) {
       double s = 0;
       for (uint32_t z = 0; z < e0; ++z) s += fabs(x0i[z] - x1j[z]);
@@ -216,10 +217,74 @@ __global__ void __launch_bounds__(256) k_pair_costs(InterpDev values, InterpDev 
     if (i0 == i1) {
       c = i == j ? -1.0 : 0.0;
     } else {
-      c += entry_cost(values, cfg.v_mult, cfg.v_vfun, i0, i1, i, j, false);
-      c += entry_cost(vectors, cfg.w_mult, cfg.w_vfun, i0, i1, i, j, true);
+      const size_t ev = values.is_complex ? 16 : 8, ew = vectors.is_complex ? 16 : 8;
+      const char* vd = reinterpret_cast<const char*>(values.data);
+      const char* wd = reinterpret_cast<const char*>(vectors.data);
+      c += entry_cost(values, cfg.v_mult, cfg.v_vfun, vd + ((size_t)i0 * B + i) * values.span * ev, vd + ((size_t)i1 * B + j) * values.span * ev, false);
+      c += entry_cost(vectors, cfg.w_mult, cfg.w_vfun, wd + ((size_t)i0 * B + i) * vectors.span * ew, wd + ((size_t)i1 * B + j) * vectors.span * ew, true);
     }
     cost[g] = c;
+  }
+}
+
+// The same costs with the rows of the two vertices of a pair staged in shared memory: one CTA per pair copies the 2 x modes rows
+// of both interpolators once (coalesced), every thread then walks "its" (i, j) entries over rows that sit in shared memory -- in
+// k_pair_costs every entry re-reads two rows from global memory several times, and the threads of a warp (consecutive j) read
+// them a whole row apart.  Row strides are padded to an odd number of 16-byte units, so that the rows j, j+1, ... that the lanes
+// of a warp read fall into different banks.  Same arithmetic, same order: identical costs.
+struct StagePlan {
+  uint32_t v_stride, w_stride;  // bytes between rows
+  uint32_t v0, v1, w0, w1;      // byte offsets of the four row blocks
+  uint32_t total;
+};
+__host__ __device__ inline StagePlan stage_plan(const InterpDev& values, const InterpDev& vectors) {
+  auto stride = [](const InterpDev& t) {
+    const uint32_t bytes = t.span * (t.is_complex ? 16u : 8u), units = (bytes + 15u) / 16u;
+    return (units | 1u) * 16u;
+  };
+  StagePlan p;
+  p.v_stride = stride(values);
+  p.w_stride = stride(vectors);
+  const uint32_t B = vectors.branches;
+  p.v0 = 0;
+  p.v1 = p.v0 + B * p.v_stride;
+  p.w0 = p.v1 + B * p.v_stride;
+  p.w1 = p.w0 + B * p.w_stride;
+  p.total = p.w1 + B * p.w_stride;
+  return p;
+}
+__global__ void __launch_bounds__(256) k_pair_costs_staged(InterpDev values, InterpDev vectors, CostCfg cfg, const uint32_t* __restrict__ pairs,
+                                                           size_t n_pairs, double* __restrict__ cost, StagePlan pl) {
+  extern __shared__ __align__(16) unsigned char pc_smem[];
+  const uint32_t B = vectors.branches;
+  auto stage = [&](const InterpDev& t, uint32_t vertex, uint32_t at, uint32_t stride) {
+    // rows of `vertex` are contiguous in global memory: 8-byte words, coalesced; padded rows in shared memory
+    const uint32_t words_per_row = t.span * (t.is_complex ? 2u : 1u);
+    const double* src = t.data + (size_t)vertex * B * words_per_row;
+    for (uint32_t k = threadIdx.x; k < B * words_per_row; k += blockDim.x) {
+      const uint32_t row = k / words_per_row, e = k - row * words_per_row;
+      *reinterpret_cast<double*>(pc_smem + at + row * stride + e * 8u) = src[k];
+    }
+  };
+  for (size_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+    const uint32_t i0 = pairs[2 * p], i1 = pairs[2 * p + 1];
+    double* out = cost + p * B * B;
+    if (i0 == i1) {
+      for (uint32_t r = threadIdx.x; r < B * B; r += blockDim.x) out[r] = (r / B == r % B) ? -1.0 : 0.0;
+      continue;
+    }
+    __syncthreads();  // (the previous pair's readers are done)
+    stage(values, i0, pl.v0, pl.v_stride);
+    stage(values, i1, pl.v1, pl.v_stride);
+    stage(vectors, i0, pl.w0, pl.w_stride);
+    stage(vectors, i1, pl.w1, pl.w_stride);
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < B * B; r += blockDim.x) {
+      const uint32_t i = r / B, j = r - i * B;
+      double c = entry_cost(values, cfg.v_mult, cfg.v_vfun, pc_smem + pl.v0 + i * pl.v_stride, pc_smem + pl.v1 + j * pl.v_stride, false);
+      c += entry_cost(vectors, cfg.w_mult, cfg.w_vfun, pc_smem + pl.w0 + i * pl.w_stride, pc_smem + pl.w1 + j * pl.w_stride, true);
+      out[r] = c;
+    }
   }
 }
 
@@ -488,11 +553,19 @@ __device__ void match_pair(const int dim, const double* __restrict__ C, const Pa
   }
 }
 
+// bytes of one warp's slice of shared memory: work arrays, then (small problems) the cost matrix itself
+__host__ __device__ inline size_t pair_slice_bytes(uint32_t dim, bool stage_cost) {
+  return (pair_work_bytes(dim) + 15) / 16 * 16 + (stage_cost ? (size_t)dim * dim * sizeof(double) : 0);
+}
+constexpr uint32_t STAGE_COST_MAX_DIM = 40;  // cost matrices up to 40 x 40 (12.8 KB) are copied into shared memory first
+
 __global__ void __launch_bounds__(256) k_pair_match(uint32_t B, size_t n_pairs, const double* __restrict__ cost, int* __restrict__ row,
                                                     int* __restrict__ col) {
   extern __shared__ __align__(16) unsigned char pm_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  unsigned char* base = pm_smem + (size_t)wid * ((pair_work_bytes(B) + 15) / 16 * 16);
+  const bool stage_cost = B <= STAGE_COST_MAX_DIM;
+  unsigned char* base = pm_smem + (size_t)wid * pair_slice_bytes(B, stage_cost);
+  double* const staged = reinterpret_cast<double*>(base + (pair_work_bytes(B) + 15) / 16 * 16);
   PairWork w;
   w.v = reinterpret_cast<double*>(base);
   w.d = w.v + B;
@@ -503,7 +576,13 @@ __global__ void __launch_bounds__(256) k_pair_match(uint32_t B, size_t n_pairs, 
   w.freerow = w.todo + B;
   w.claims = w.freerow + B;
   for (size_t p = (size_t)blockIdx.x * wpc + wid; p < n_pairs; p += (size_t)gridDim.x * wpc) {
-    match_pair((int)B, cost + p * B * B, w, lane);
+    const double* C = cost + p * B * B;
+    if (stage_cost) {  // the solver reads the matrix many times, a row or a column at a time
+      for (uint32_t k = lane; k < B * B; k += 32) staged[k] = C[k];
+      __syncwarp();
+      C = staged;
+    }
+    match_pair((int)B, C, w, lane);
     __syncwarp();
     for (uint32_t j = lane; j < B; j += 32) {
       row[p * B + j] = w.rowsol[j];
@@ -515,7 +594,7 @@ __global__ void __launch_bounds__(256) k_pair_match(uint32_t B, size_t n_pairs, 
 
 // warps per CTA and dynamic shared memory of k_pair_match for `B` modes (0: too many modes for one warp's work arrays)
 static int pair_match_config(uint32_t B, size_t* smem) {
-  const size_t per_warp = (pair_work_bytes(B) + 15) / 16 * 16;
+  const size_t per_warp = pair_slice_bytes(B, B <= STAGE_COST_MAX_DIM);
   int warps = 8;
   while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
   if (per_warp * warps > 200 * 1024) return 0;
@@ -594,7 +673,20 @@ cudaError_t run_sort_pairs(const DataDev& dd, const double v_mult[3], int v_vfun
     const size_t n = n_pairs - lo < batch ? n_pairs - lo : batch;
     if ((e = cudaMemcpy(ws.pairs, h_pairs + 2 * lo, n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     const size_t entries = n * B * B, want = (entries + 255) / 256, cap = (size_t)sm_count * 32;
-    k_pair_costs<<<(unsigned)(want < cap ? want : cap), 256>>>(dd.values, dd.vectors, cfg, ws.pairs, n, ws.cost);
+    const StagePlan pl = stage_plan(dd.values, dd.vectors);
+    if (pl.total <= 200u * 1024u) {  // rows of both vertices fit in shared memory: one CTA per pair
+      static size_t configured_dev[MAX_DEVICES] = {};
+      size_t& configured = configured_dev[current_device_slot()];
+      if (pl.total > 48u * 1024u && pl.total > configured) {
+        if ((e = cudaFuncSetAttribute(k_pair_costs_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total)) != cudaSuccess) return e;
+        configured = pl.total;
+      }
+      const unsigned threads = (unsigned)std::min<size_t>(256, ((size_t)B * B + 31) / 32 * 32);
+      const size_t cap_c = (size_t)sm_count * 8;
+      k_pair_costs_staged<<<(unsigned)(n < cap_c ? n : cap_c), threads, pl.total>>>(dd.values, dd.vectors, cfg, ws.pairs, n, ws.cost, pl);
+    } else {
+      k_pair_costs<<<(unsigned)(want < cap ? want : cap), 256>>>(dd.values, dd.vectors, cfg, ws.pairs, n, ws.cost);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = launch_pair_match(B, n, ws.cost, ws.row, ws.col, sm_count)) != cudaSuccess) return e;
     if (launches) *launches += 2;

@@ -62,5 +62,9 @@ for v in variants or [{}]:
         ref_out = cur
     else:
         same = " bit-identical to the first variant: %s" % (bool(torch.equal(cur[0], ref_out[0]) and torch.equal(cur[1], ref_out[1])))
+    import hashlib
+    k = max(1, nq // 2000)
+    digest = hashlib.sha1(vals[::k].cpu().numpy().tobytes() + vecs[::k].cpu().numpy().tobytes()).hexdigest()[:12]
+    same += f" sha1 {digest}"
     print(f"{name} {v}: {ms:.3f} ms/step = {nq / ms / 1e3:.4g} Q/s path {grid.last_path} | " +
           " ".join(f"{k} {np.mean(x):.3f}" for k, x in t.items()) + same, flush=True)
