@@ -511,8 +511,43 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         c_fused_ms, c_unfused_ms, c_e2e_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        # powder average: points generated on the device (200 |Q| bins x NQ/200 directions per GPU per step), structure factor fused
+        # into the cell kernel, histogram accumulated on the device; per step only the histogram (200 x 400 doubles) leaves the GPU and
+        # the ranks' partial histograms meet in one small all-reduce
+        from brille_b200 import _bridge as _br
+
+        grid.set_structure_factor(rng.normal(size=wl.n_atoms) + 1j * rng.normal(size=wl.n_atoms), positions=rng.uniform(0, 1, (wl.n_atoms, 3)),
+                                  q_transform=np.asarray(_br.flatten_bz(wl.bz)["to_xyz"]).reshape(3, 3))
+        nqb, nwb = 200, 400
+        n_dir = world * (NQ // nqb)
+        lo_d, hi_d = rank * (NQ // nqb), (rank + 1) * (NQ // nqb)
+
+        def p_step():
+            h, c_ = grid.ir_powder_sweep((0.1, 10.0), nqb, (0.0, 55.0), nwb, n_dir, seed=7, weight=1, dir_range=(lo_d, hi_d))
+            if world > 1:
+                th = torch.from_numpy(h).to(dev)
+                dist.all_reduce(th)
+                h = th.cpu().numpy()
+            return h, c_
+
+        p_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ph, pc_ = p_step()
+        torch.cuda.synchronize(dev)
+        p_s = (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([p_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        p_s = float(t.item())
+        powder = {"value": world * NQ / p_s, "unit": UNIT, "ms_per_step": 1e3 * p_s, "q_per_gpu_per_step": NQ, "h2d_bytes_per_step": 0,
+                  "d2h_bytes_per_step": 8 * (nqb * nwb + nqb), "bins": [nqb, nwb], "checksum": float(ph.sum()), "points_per_q_bin": float(pc_[0]),
+                  "note": "ir_powder_sweep: Q generated on the device, |F|^2/omega binned on (|Q|, omega) with FP64 atomics; end to end "
+                          "through the host call, histogram on the host (all-reduce of the partial histograms for N > 1)"}
         consumer = {
             "what": "ir_structure_factor: the path + |sum_k c_k e^{2 pi i Q.r_k} (TQ . eps_k^*)|^2 per (Q, mode) on the device",
+            "powder_average": powder,
             "device_resident": {"value": world * NQ / (c_fused_ms * 1e-3), "unit": UNIT, "ms_per_step": c_fused_ms,
                                 "fused_cell_kernel_ms": c_fused_kernel_ms,
                                 "note": "reduction fused into the finish of the pipelined cell kernel (k_interp_cell_tma<4,true>): the eigenvectors are never written",

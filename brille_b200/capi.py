@@ -38,6 +38,9 @@ EXPORTS = (
     "b200_grid_set_structure_factor",
     "b200_ir_structure_factor",
     "b200_ir_structure_factor_device",
+    "b200_ir_powder_bin",
+    "b200_ir_powder_sweep",
+    "b200_powder_points",
 )
 
 
@@ -62,6 +65,20 @@ class SFConfig(C.Structure):
         ("debye_waller", C.c_void_p),
         ("q_transform", C.c_double * 9),
         ("conjugate", C.c_int32),
+    ]
+
+
+class PowderConfig(C.Structure):
+    """``b200_powder_config_t``"""
+
+    _fields_ = [
+        ("n_qbins", C.c_uint32),
+        ("n_wbins", C.c_uint32),
+        ("q_lo", C.c_double),
+        ("q_hi", C.c_double),
+        ("w_lo", C.c_double),
+        ("w_hi", C.c_double),
+        ("weight", C.c_int32),
     ]
 
 
@@ -128,6 +145,12 @@ def lib():
     L.b200_ir_structure_factor.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp]
     L.b200_ir_structure_factor_device.restype = C.c_int
     L.b200_ir_structure_factor_device.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+    L.b200_ir_powder_bin.restype = C.c_int
+    L.b200_ir_powder_bin.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.POINTER(PowderConfig), vp, vp]
+    L.b200_ir_powder_sweep.restype = C.c_int
+    L.b200_ir_powder_sweep.argtypes = [vp, C.POINTER(PowderConfig), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
+    L.b200_powder_points.restype = C.c_int
+    L.b200_powder_points.argtypes = [vp, C.POINTER(PowderConfig), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp]
     L.b200_grid_row_bytes.restype = C.c_int
     L.b200_grid_row_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L

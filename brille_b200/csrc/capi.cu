@@ -192,6 +192,27 @@ struct HostStage {  // device-side staging buffers of one pipeline slot of the h
   cudaStream_t stream = nullptr;
 };
 
+struct PowderWS {  // device buffers of the powder-average entry points (sized in points of the current data: dropped with it)
+  size_t cap = 0;    // points per chunk
+  double* dQ = nullptr;
+  double* dvals = nullptr;
+  double* dsf = nullptr;
+  double* dvecs = nullptr;  // only when the reduction cannot be fused
+  double* dgs = nullptr;    // fused: compact rows of the general-kernel points
+  uint32_t gcap = 0;
+  double* dhist = nullptr;  // n_qbins * n_wbins + n_qbins
+  size_t hist_elems = 0;
+  void release() {
+    for (double** p : {&dQ, &dvals, &dsf, &dvecs, &dgs, &dhist}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    cap = 0;
+    gcap = 0;
+    hist_elems = 0;
+  }
+};
+
 struct b200_grid {
   int device = 0, sm_count = 148, kind = 0;
   BZDev h_bz;
@@ -229,6 +250,7 @@ struct b200_grid {
   int sf_fused = 1;             // 1: reduce inside the pipelined cell kernel whenever possible (the eigenvectors never reach HBM)
   double* sf_gscratch = nullptr;  // device-buffer entry point: compact rows of the general-kernel points
   uint32_t sf_gcap = 0;
+  PowderWS pw;
   uint64_t launches = 0;
   uint32_t last_path = 0;  // B200_PATH_* of the last enqueue
   bool timing = false;
@@ -258,6 +280,7 @@ static void drop_row_sized_buffers(b200_grid* g) {
   if (g->sf_scratch) cudaFree(g->sf_scratch);
   g->sf_scratch = nullptr;
   g->sf_scratch_bytes = 0;
+  g->pw.release();
 }
 
 static void drop_cell_table(b200_grid* g) {
@@ -667,6 +690,7 @@ extern "C" void b200_grid_destroy(b200_grid_t* g) {
   g->sf_pool.release();
   if (g->sf_scratch) cudaFree(g->sf_scratch);
   if (g->sf_gscratch) cudaFree(g->sf_gscratch);
+  g->pw.release();
   if (g->d_fail) cudaFree(g->d_fail);
   for (int s = 0; s < 2; ++s) {
     HostStage& h = g->stage[s];
@@ -1357,6 +1381,170 @@ extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ,
     return status_error(c, nQ);
   }
   return B200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// device-resident consumer: powder average (consumer.cu)
+// ----------------------------------------------------------------------------------------------------
+static int powder_config(b200_grid* g, const b200_powder_config_t* c, PowderDev* d) {
+  if (!c) return fail(B200_E_INVALID, "NULL powder configuration");
+  if (!c->n_qbins || !c->n_wbins || !(c->q_hi > c->q_lo) || !(c->w_hi > c->w_lo) || !(c->q_lo >= 0.0))
+    return fail(B200_E_INVALID, "powder average: need n_qbins, n_wbins > 0, 0 <= q_lo < q_hi and w_lo < w_hi");
+  if (c->weight != 0 && c->weight != 1) return fail(B200_E_INVALID, "powder average: weight must be 0 (|F|^2) or 1 (|F|^2 / omega)");
+  if (g->dd.values.is_complex || g->dd.values.span < 1)
+    return fail(B200_E_UNSUPPORTED, "powder average: the eigenvalue data must be real with at least one element per mode (the energy)");
+  d->n_qbins = c->n_qbins;
+  d->n_wbins = c->n_wbins;
+  d->q_lo = c->q_lo;
+  d->dq = (c->q_hi - c->q_lo) / c->n_qbins;
+  d->inv_dq = c->n_qbins / (c->q_hi - c->q_lo);
+  d->w_lo = c->w_lo;
+  d->inv_dw = c->n_wbins / (c->w_hi - c->w_lo);
+  d->weight = c->weight;
+  const double* B = g->h_bz.to_xyz;
+  for (int i = 0; i < 9; ++i) d->B[i] = B[i];
+  const double det = B[0] * (B[4] * B[8] - B[5] * B[7]) - B[1] * (B[3] * B[8] - B[5] * B[6]) + B[2] * (B[3] * B[7] - B[4] * B[6]);
+  if (det == 0.0) return fail(B200_E_INVALID, "singular reciprocal basis");
+  const double inv[9] = {B[4] * B[8] - B[5] * B[7], B[2] * B[7] - B[1] * B[8], B[1] * B[5] - B[2] * B[4],
+                         B[5] * B[6] - B[3] * B[8], B[0] * B[8] - B[2] * B[6], B[2] * B[3] - B[0] * B[5],
+                         B[3] * B[7] - B[4] * B[6], B[1] * B[6] - B[0] * B[7], B[0] * B[4] - B[1] * B[3]};
+  for (int i = 0; i < 9; ++i) d->Binv[i] = inv[i] / det;
+  return B200_OK;
+}
+
+// the points of a call in chunks: generated on the device (Q == NULL) or copied from the host; the path with the structure factor
+// fused into the pipelined cell kernel when possible (else through an eigenvector scratch); k_powder_bin; the histogram back
+static int powder_run(b200_grid* g, const double* Q, size_t n_total, uint32_t flags, const PowderDev& pc, uint64_t n_dir_local, uint64_t dir_lo,
+                      uint64_t n_dir, uint64_t seed, double* hist_out, double* counts_out, double* Q_out) {
+  DeviceGuard guard;
+  CU(cudaSetDevice(g->device));
+  if (g->timing) g->kernel_ms.clear();
+  cudaStream_t stream = g->stage[0].stream;
+  PowderWS& w = g->pw;
+  const size_t M = g->dd.vectors.branches, hist_elems = (size_t)pc.n_qbins * pc.n_wbins + pc.n_qbins;
+  const bool points_only = Q_out != nullptr;
+  bool fuse = !points_only && g->sf_fused && cell_sf_fusable(g->dd, g->sf);
+  const size_t want_cap = std::min<size_t>(n_total, (size_t)1 << 22);
+  if (w.cap < want_cap) {
+    w.release();
+    CU(cudaMalloc(&w.dQ, want_cap * 3 * sizeof(double)));
+    if (!points_only) {
+      CU(cudaMalloc(&w.dvals, std::max<size_t>(want_cap * g->vals_row_bytes, 8)));
+      CU(cudaMalloc(&w.dsf, std::max<size_t>(want_cap * M * sizeof(double), 8)));
+    }
+    w.cap = want_cap;
+  }
+  if (!points_only && !w.dvals) {
+    CU(cudaMalloc(&w.dvals, std::max<size_t>(w.cap * g->vals_row_bytes, 8)));
+    CU(cudaMalloc(&w.dsf, std::max<size_t>(w.cap * M * sizeof(double), 8)));
+  }
+  if (!points_only && w.hist_elems < hist_elems) {
+    if (w.dhist) cudaFree(w.dhist);
+    w.dhist = nullptr;
+    w.hist_elems = 0;
+    CU(cudaMalloc(&w.dhist, hist_elems * sizeof(double)));
+    w.hist_elems = hist_elems;
+  }
+  if (!points_only) CU(cudaMemsetAsync(w.dhist, 0, hist_elems * sizeof(double), stream));
+  const uint32_t mode = MODE_IR | ((flags & B200_FLAG_NO_MOVE) ? MODE_NO_MOVE : 0u);
+  unsigned long long total[3] = {0, 0, 0};
+  for (size_t lo = 0; lo < n_total; lo += w.cap) {
+    const size_t n = std::min(w.cap, n_total - lo);
+    if (Q) CU(cudaMemcpyAsync(w.dQ, Q + 3 * lo, n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    else CU(launch_powder_q(w.dQ, lo, n, n_dir_local, dir_lo, n_dir, seed, pc, g->sm_count, stream));
+    g->launches += Q ? 0 : 1;
+    if (points_only) {
+      CU(cudaMemcpyAsync(Q_out + 3 * lo, w.dQ, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      continue;
+    }
+    bool done = false;
+    if (fuse) {
+      if (!w.dgs) {
+        w.gcap = (uint32_t)std::max<size_t>(1024, w.cap / 16);
+        CU(cudaMalloc(&w.dgs, (size_t)w.gcap * g->vecs_row_bytes));
+      }
+      const SfFuse fz{w.dsf, w.dgs, w.gcap};
+      int rc = enqueue(g, g->ws, g->d_fail, w.dQ, n, mode, true, 1, w.dvals, nullptr, stream, n_total, false, true, &fz);
+      if (rc == RC_NOT_FUSABLE) {
+        fuse = false;
+      } else {
+        if (rc) return rc;
+        unsigned long long c[N_FAIL];
+        CU(cudaMemcpyAsync(c, g->d_fail, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        if (c[3] == 0) {
+          for (int k = 0; k < 3; ++k) total[k] += c[k];
+          done = true;
+        }  // else: more general-kernel points than compact rows in this chunk (a degenerate point set): once more, unfused
+      }
+    }
+    if (!done) {
+      if (!w.dvecs) CU(cudaMalloc(&w.dvecs, std::max<size_t>(w.cap * g->vecs_row_bytes, 8)));
+      int rc = enqueue(g, g->ws, g->d_fail, w.dQ, n, mode, true, 1, w.dvals, w.dvecs, stream, n_total, false, true);
+      if (rc) return rc;
+      CU(launch_structure_factor(g->sf, w.dQ, w.dvecs, n, (uint32_t)M, w.dsf, g->sm_count, stream));
+      g->launches += 1;
+      unsigned long long c[3];
+      CU(cudaMemcpyAsync(c, g->d_fail, sizeof(c), cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      for (int k = 0; k < 3; ++k) total[k] += c[k];
+    }
+    if (total[0] || total[1] || total[2]) return status_error(total, n_total);  // all-or-nothing, like ir_interpolate_at
+    CU(launch_powder_bin(w.dQ, w.dvals, w.dsf, n, (uint32_t)M, g->dd.values.span, pc, w.dhist, w.dhist + (size_t)pc.n_qbins * pc.n_wbins, g->sm_count, stream));
+    g->launches += 1;
+  }
+  if (!points_only) {
+    std::vector<double> h(hist_elems);
+    CU(cudaMemcpyAsync(h.data(), w.dhist, hist_elems * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const size_t nh = (size_t)pc.n_qbins * pc.n_wbins;
+    for (size_t i = 0; i < nh; ++i) hist_out[i] += h[i];
+    for (size_t i = 0; i < pc.n_qbins; ++i) counts_out[i] += h[nh + i];
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_ir_powder_bin(b200_grid_t* g, const double* Q, size_t nQ, uint32_t flags, const b200_powder_config_t* config, double* hist_out,
+                                  double* counts_out) {
+  int rc = check_sf_ready(g);
+  if (rc) return rc;
+  PowderDev pc;
+  if ((rc = powder_config(g, config, &pc))) return rc;
+  if (!hist_out || !counts_out || (nQ && !Q)) return fail(B200_E_INVALID, "NULL buffer");
+  if (nQ == 0) return B200_OK;
+  return powder_run(g, Q, nQ, flags, pc, 0, 0, 0, 0, hist_out, counts_out, nullptr);
+}
+
+static int sweep_args(const b200_powder_config_t* config, uint64_t n_dir, uint64_t dir_lo, uint64_t dir_hi, size_t* n_total) {
+  if (!config) return fail(B200_E_INVALID, "NULL powder configuration");
+  if (dir_lo > dir_hi || dir_hi > n_dir) return fail(B200_E_INVALID, "powder sweep: need dir_lo <= dir_hi <= n_dir");
+  *n_total = (size_t)config->n_qbins * (size_t)(dir_hi - dir_lo);
+  return B200_OK;
+}
+extern "C" int b200_ir_powder_sweep(b200_grid_t* g, const b200_powder_config_t* config, uint64_t n_dir, uint64_t seed, uint64_t dir_lo, uint64_t dir_hi,
+                                    double* hist_out, double* counts_out) {
+  int rc = check_sf_ready(g);
+  if (rc) return rc;
+  PowderDev pc;
+  if ((rc = powder_config(g, config, &pc))) return rc;
+  size_t n_total = 0;
+  if ((rc = sweep_args(config, n_dir, dir_lo, dir_hi, &n_total))) return rc;
+  if (!hist_out || !counts_out) return fail(B200_E_INVALID, "NULL buffer");
+  if (n_total == 0) return B200_OK;
+  return powder_run(g, nullptr, n_total, 0u, pc, dir_hi - dir_lo, dir_lo, n_dir, seed, hist_out, counts_out, nullptr);
+}
+extern "C" int b200_powder_points(b200_grid_t* g, const b200_powder_config_t* config, uint64_t n_dir, uint64_t seed, uint64_t dir_lo, uint64_t dir_hi,
+                                  double* Q_out) {
+  int rc = check_ready(g, true, 1);
+  if (rc) return rc;
+  PowderDev pc;
+  if ((rc = powder_config(g, config, &pc))) return rc;
+  size_t n_total = 0;
+  if ((rc = sweep_args(config, n_dir, dir_lo, dir_hi, &n_total))) return rc;
+  if (n_total && !Q_out) return fail(B200_E_INVALID, "NULL buffer");
+  if (n_total == 0) return B200_OK;
+  return powder_run(g, nullptr, n_total, 0u, pc, dir_hi - dir_lo, dir_lo, n_dir, seed, nullptr, nullptr, Q_out);
 }
 
 // ----------------------------------------------------------------------------------------------------

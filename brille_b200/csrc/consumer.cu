@@ -141,4 +141,115 @@ cudaError_t launch_structure_factor(const SFDev& c, const double* dQ, const doub
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Powder average ("powder binning of |F(Q)|^2 per mode"; the loop validation/profiling.md:30-67 times):
+// the sphere of directions is sampled at every |Q| and the one-phonon intensity |F(Q, nu)|^2 is binned on (|Q|, omega_nu(Q)).
+// With the points generated and the histogram accumulated on the device NOTHING per Q crosses PCIe: a sweep returns
+// n_qbins x n_wbins doubles.
+//
+// k_powder_q     point g of the sweep = (|Q| bin i, direction j): |Q| at the centre of bin i, direction from a counter-based
+//                generator (splitmix64 of seed and g: reproducible on the host, independent of the launch shape), Q = B^-1 (|Q| d)
+// k_powder_bin   one thread per (point, mode): |B Q| -> |Q| bin, eigenvalue -> energy bin, atomicAdd of the weighted intensity
+//                (FP64 reductions at L2; the histogram is L2 resident), one count per point for the normalisation
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_powder_q(double* __restrict__ Q, size_t first, size_t n, uint64_t n_dir_local, uint64_t dir_lo,
+                                                  uint64_t n_dir, uint64_t seed, PowderDev c) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = first + t;
+    const uint64_t i = g / n_dir_local, j = dir_lo + (g - i * n_dir_local);
+    const uint64_t z1 = splitmix64(seed ^ splitmix64(i * n_dir + j)), z2 = splitmix64(z1);
+    const double u1 = (double)(z1 >> 11) * 0x1.0p-53, u2 = (double)(z2 >> 11) * 0x1.0p-53;
+    const double ct = 1.0 - 2.0 * u1, st = sqrt(fmax(0.0, 1.0 - ct * ct));
+    double sp, cp;
+    sincospi(2.0 * u2, &sp, &cp);
+    const double qn = c.q_lo + ((double)i + 0.5) * c.dq;
+    const double x = qn * st * cp, y = qn * st * sp, zc = qn * ct;
+    Q[3 * t] = c.Binv[0] * x + c.Binv[1] * y + c.Binv[2] * zc;
+    Q[3 * t + 1] = c.Binv[3] * x + c.Binv[4] * y + c.Binv[5] * zc;
+    Q[3 * t + 2] = c.Binv[6] * x + c.Binv[7] * y + c.Binv[8] * zc;
+  }
+}
+
+// A CTA takes 256 consecutive points.  In a sweep they sit in one |Q| bin (the points are |Q|-bin major): the row of that bin is
+// accumulated in shared memory and flushed with one global reduction per non-empty energy bin; points of other |Q| bins (any
+// order of caller-provided points works) go to the global histogram directly.  The per-bin point counts are aggregated per warp.
+__global__ void __launch_bounds__(256) k_powder_bin(const double* __restrict__ Q, const double* __restrict__ vals, const double* __restrict__ sf,
+                                                    size_t n, uint32_t M, uint32_t vspan, PowderDev c, double* __restrict__ hist,
+                                                    double* __restrict__ counts, uint32_t row_bins) {
+  extern __shared__ __align__(16) unsigned char pb_smem[];
+  double* const row = reinterpret_cast<double*>(pb_smem);  // [row_bins] (0: no private row)
+  __shared__ int s_iq[256];
+  __shared__ int s_row;
+  const int tid = threadIdx.x;
+  for (size_t p0 = (size_t)blockIdx.x * 256; p0 < n; p0 += (size_t)gridDim.x * 256) {
+    const uint32_t np = (uint32_t)min((size_t)256, n - p0);
+    // ---- per point: |B Q| -> |Q| bin; counts, one reduction per distinct bin of a warp ------------------------------------
+    int iq = -1;
+    if ((uint32_t)tid < np) {
+      const double* q = Q + 3 * (p0 + tid);
+      const double q0 = q[0], q1 = q[1], q2 = q[2];
+      const double x = c.B[0] * q0 + c.B[1] * q1 + c.B[2] * q2, y = c.B[3] * q0 + c.B[4] * q1 + c.B[5] * q2, z = c.B[6] * q0 + c.B[7] * q1 + c.B[8] * q2;
+      const double fq = (sqrt(x * x + y * y + z * z) - c.q_lo) * c.inv_dq;
+      if (fq >= 0.0 && fq < (double)c.n_qbins) iq = (int)fq;
+    }
+    s_iq[tid] = iq;
+    {
+      const unsigned same = __match_any_sync(0xffffffffu, iq);
+      if (iq >= 0 && (int)(tid & 31) == __ffs(same) - 1) atomicAdd(counts + iq, (double)__popc(same));
+    }
+    if (tid == 0) s_row = iq;  // the block's private row: the |Q| bin of its first point
+    for (uint32_t k = tid; k < row_bins; k += 256) row[k] = 0.0;
+    __syncthreads();
+    const int my_row = row_bins ? s_row : -1;
+    // ---- per (point, mode): energy bin, weighted intensity ---------------------------------------------------------------
+    for (uint32_t g = tid; g < np * M; g += 256) {
+      const uint32_t t = g / M;
+      const int jq = s_iq[t];
+      if (jq < 0) continue;
+      const size_t pm = (p0 + t) * M + (g - t * M);
+      const double w = vals[pm * vspan];
+      const double fw = (w - c.w_lo) * c.inv_dw;
+      if (!(fw >= 0.0) || fw >= (double)c.n_wbins) continue;
+      double v = sf[pm];
+      if (c.weight == 1) {
+        if (!(w > 0.0)) continue;
+        v /= w;
+      }
+      if (jq == my_row) atomicAdd(row + (uint32_t)fw, v);
+      else atomicAdd(hist + (size_t)jq * c.n_wbins + (uint32_t)fw, v);
+    }
+    __syncthreads();
+    if (my_row >= 0)
+      for (uint32_t k = tid; k < row_bins; k += 256) {
+        const double v = row[k];
+        if (v != 0.0) atomicAdd(hist + (size_t)my_row * c.n_wbins + k, v);
+      }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_powder_q(double* dQ, size_t first, size_t n, uint64_t n_dir_local, uint64_t dir_lo, uint64_t n_dir, uint64_t seed,
+                            const PowderDev& c, int sm_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 16;
+  k_powder_q<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(dQ, first, n, n_dir_local, dir_lo, n_dir, seed, c);
+  return cudaGetLastError();
+}
+cudaError_t launch_powder_bin(const double* dQ, const double* dvals, const double* dsf, size_t n, uint32_t M, uint32_t vspan, const PowderDev& c,
+                              double* hist, double* counts, int sm_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+  const uint32_t row_bins = c.n_wbins <= 4096u ? c.n_wbins : 0u;  // (a private row of up to 32 KB)
+  k_powder_bin<<<(unsigned)(want < cap ? want : cap), 256, (size_t)row_bins * sizeof(double), stream>>>(dQ, dvals, dsf, n, M, vspan, c, hist, counts,
+                                                                                                          row_bins);
+  return cudaGetLastError();
+}
+
 }  // namespace b200

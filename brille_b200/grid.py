@@ -365,6 +365,51 @@ class B200Grid:
             scratch.data_ptr() if scratch is not None else None, s.cuda_stream, C.byref(nf) if check else None))
         return vals_out, sf_out
 
+    # ------------------------------------------------------------------ device-resident consumer: powder average
+    @staticmethod
+    def _powder_cfg(q_range, n_qbins, w_range, n_wbins, weight):
+        cfg = capi.PowderConfig()
+        cfg.n_qbins, cfg.n_wbins = int(n_qbins), int(n_wbins)
+        cfg.q_lo, cfg.q_hi = float(q_range[0]), float(q_range[1])
+        cfg.w_lo, cfg.w_hi = float(w_range[0]), float(w_range[1])
+        cfg.weight = int(weight)
+        return cfg
+
+    def ir_powder_bin(self, Q, q_range, n_qbins, w_range, n_wbins, weight=0, do_not_move_points=False, out=None):
+        """``(hist, counts)``: the structure factor |F(Q, mode)|^2 of every point binned on (|B Q|, eigenvalue) on the device
+        (``b200_ir_powder_bin``; ``set_structure_factor`` first).  ``hist`` (n_qbins, n_wbins), ``counts`` (n_qbins,) points per
+        |Q| bin; ``out=(hist, counts)`` accumulates into existing arrays.  Only the histogram leaves the GPU."""
+        Q = self._check_q(Q)
+        self._check_filled()
+        cfg = self._powder_cfg(q_range, n_qbins, w_range, n_wbins, weight)
+        hist, counts = out if out is not None else (np.zeros((cfg.n_qbins, cfg.n_wbins)), np.zeros(cfg.n_qbins))
+        if hist.shape != (cfg.n_qbins, cfg.n_wbins) or counts.shape != (cfg.n_qbins,) or hist.dtype != np.float64 or counts.dtype != np.float64 \
+                or not (hist.flags.c_contiguous and counts.flags.c_contiguous):
+            raise RuntimeError("out must be C-contiguous float64 arrays of shapes (n_qbins, n_wbins) and (n_qbins,)")
+        capi.check(capi.lib().b200_ir_powder_bin(self._handle, Q.ctypes.data, Q.shape[0], T.FLAG_NO_MOVE if do_not_move_points else 0, C.byref(cfg),
+                                                 hist.ctypes.data, counts.ctypes.data))
+        return hist, counts
+
+    def ir_powder_sweep(self, q_range, n_qbins, w_range, n_wbins, n_dir, seed=0, weight=0, dir_range=None, out=None):
+        """The powder sweep with the points generated on the device: ``n_dir`` isotropic directions at the centre of every |Q| bin
+        (``dir_range=(lo, hi)``: only that slice of the direction sequence -- ranks / GPUs take disjoint slices and add their
+        histograms).  Returns ``(hist, counts)``; nothing per Q crosses PCIe."""
+        self._check_filled()
+        cfg = self._powder_cfg(q_range, n_qbins, w_range, n_wbins, weight)
+        lo, hi = (0, int(n_dir)) if dir_range is None else (int(dir_range[0]), int(dir_range[1]))
+        hist, counts = out if out is not None else (np.zeros((cfg.n_qbins, cfg.n_wbins)), np.zeros(cfg.n_qbins))
+        capi.check(capi.lib().b200_ir_powder_sweep(self._handle, C.byref(cfg), int(n_dir), int(seed), lo, hi, hist.ctypes.data, counts.ctypes.data))
+        return hist, counts
+
+    def powder_points(self, q_range, n_qbins, n_dir, seed=0, dir_range=None):
+        """The points (rlu) of the sweep, |Q|-bin major: (n_qbins * (hi - lo), 3)."""
+        self._check_filled()
+        cfg = self._powder_cfg(q_range, n_qbins, (0.0, 1.0), 1, 0)
+        lo, hi = (0, int(n_dir)) if dir_range is None else (int(dir_range[0]), int(dir_range[1]))
+        Q = np.zeros((cfg.n_qbins * (hi - lo), 3))
+        capi.check(capi.lib().b200_powder_points(self._handle, C.byref(cfg), int(n_dir), int(seed), lo, hi, Q.ctypes.data))
+        return Q
+
     # ------------------------------------------------------------------ introspection
     @property
     def launch_count(self):

@@ -103,6 +103,28 @@ class ShardedGrid:
             raise errors[0]
         return vals, sf
 
+    def ir_powder_sweep(self, q_range, n_qbins, w_range, n_wbins, n_dir, seed=0, weight=0):
+        """:meth:`B200Grid.ir_powder_sweep` with the direction sequence cut into one contiguous slice per device; the partial
+        histograms (a few hundred KB each) are added on the host -- the only exchange of the path."""
+        parts = [None] * len(self.grids)
+        errors = []
+
+        def work(rank, grid):
+            lo, hi = shard_bounds(int(n_dir), rank, len(self.grids))
+            try:
+                parts[rank] = grid.ir_powder_sweep(q_range, n_qbins, w_range, n_wbins, n_dir, seed=seed, weight=weight, dir_range=(lo, hi))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        ts = [threading.Thread(target=work, args=(r, g)) for r, g in enumerate(self.grids)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errors:
+            raise errors[0]
+        return sum(p[0] for p in parts), sum(p[1] for p in parts)
+
     def close(self):
         for g in self.grids:
             g.close()

@@ -290,6 +290,31 @@ int b200_ir_structure_factor(b200_grid_t* grid, const double* Q, size_t nQ, uint
 int b200_ir_structure_factor_device(b200_grid_t* grid, const double* dQ, size_t nQ, uint32_t flags, void* d_vals_out,
                                     double* d_sf_out, void* d_vecs_scratch, void* stream, uint64_t* n_failed);
 
+/* ---- device-resident consumer: powder average ("powder binning of |F(Q)|^2 per mode") ---------------------
+ * What a powder (orientationally averaged) calculation does with ir_interpolate_at (Euphonic / brilleu; the loop
+ * validation/profiling.md:30-67 times): the sphere of directions is sampled at every |Q|, and the one-phonon intensity
+ * |F(Q, nu)|^2 of every mode is binned on (|Q|, omega_nu(Q)).  Here the structure factor is reduced on the device
+ * (b200_grid_set_structure_factor must have been called) and accumulated into the histogram on the device: nothing per Q
+ * crosses PCIe.  hist[iq * n_wbins + iw] += weight(|F|^2) for |B Q| in |Q| bin iq and the FIRST scalar of mode nu's eigenvalue
+ * in energy bin iw; counts[iq] = number of points in |Q| bin iq (the normalisation of the average).                         */
+typedef struct b200_powder_config {
+  uint32_t n_qbins, n_wbins;
+  double q_lo, q_hi;   /* |Q| axis, 1/angstrom                                                                          */
+  double w_lo, w_hi;   /* energy axis, units of the eigenvalues                                                         */
+  int32_t weight;      /* 0: |F|^2; 1: |F|^2 / omega for omega > 0 (the 1/omega of the one-phonon cross section)         */
+} b200_powder_config_t;
+/* caller-provided points (host, rlu), accumulated INTO hist_out (n_qbins x n_wbins) / counts_out (n_qbins): host doubles    */
+int b200_ir_powder_bin(b200_grid_t* grid, const double* Q, size_t nQ, uint32_t flags, const b200_powder_config_t* config,
+                       double* hist_out, double* counts_out);
+/* the sweep with the points generated on the device: for every |Q| bin (|Q| at its centre) the directions j in [dir_lo, dir_hi)
+ * of a reproducible sequence of n_dir isotropic directions (counter-based: splitmix64 of seed, bin and j), Q = B^-1 (|Q| d).
+ * Ranks / GPUs take disjoint direction ranges and add their histograms.  b200_powder_points returns the points of the same
+ * sequence on the host (for checks against the reference).                                                              */
+int b200_ir_powder_sweep(b200_grid_t* grid, const b200_powder_config_t* config, uint64_t n_dir, uint64_t seed, uint64_t dir_lo,
+                         uint64_t dir_hi, double* hist_out, double* counts_out);
+int b200_powder_points(b200_grid_t* grid, const b200_powder_config_t* config, uint64_t n_dir, uint64_t seed, uint64_t dir_lo,
+                       uint64_t dir_hi, double* Q_out);
+
 /* Page-locked host memory for Q / output buffers: with pinned buffers the chunked copies of the host-buffer
  * entry points run at the PCIe rate and overlap the kernels.  Pageable output buffers work too: the library lands
  * every chunk in a page-locked bounce buffer of its own and moves it on with several host threads (about half the

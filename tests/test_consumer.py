@@ -235,3 +235,98 @@ def test_structure_factor_sharded(host):
     with pytest.raises(RuntimeError):
         sg.ir_structure_factor(np.full((4, 3), 7.3), do_not_move_points=True)
     sg.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# powder average (b200_ir_powder_bin / b200_ir_powder_sweep)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_oracle_powder_histogram_against_literal_loop():
+    from oracle.consumer import powder_histogram, powder_points
+
+    rng = np.random.default_rng(2)
+    B = rng.normal(size=(3, 3)) + 2 * np.eye(3)
+    Q = powder_points(B, (0.5, 4.5), 8, 50, seed=7)
+    assert Q.shape == (400, 3)
+    qn = np.linalg.norm(Q @ B.T, axis=1)
+    assert np.allclose(qn.reshape(8, 50), (0.5 + (np.arange(8) + 0.5) * 0.5)[:, None], rtol=1e-12)  # bin centres, |Q|-bin major
+    d = (Q @ B.T) / qn[:, None]
+    assert abs(d.mean(axis=0)).max() < 0.15  # isotropic directions
+    assert np.array_equal(powder_points(B, (0.5, 4.5), 8, 50, seed=7, dir_range=(10, 30)), Q.reshape(8, 50, 3)[:, 10:30].reshape(-1, 3))
+    vals = rng.uniform(-1, 12, (400, 5, 1))
+    sf = rng.uniform(0, 3, (400, 5))
+    for weight in (0, 1):
+        hist, counts = powder_histogram(Q, B, vals, sf, (0.5, 4.5), 8, (0.0, 10.0), 20, weight)
+        want = np.zeros((8, 20))
+        for i in range(400):
+            iq = int((qn[i] - 0.5) / 0.5)
+            for m in range(5):
+                w = vals[i, m, 0]
+                if 0 <= w < 10 and (weight == 0 or w > 0):
+                    want[iq, int(w / 0.5)] += sf[i, m] / (w if weight else 1.0)
+        assert np.allclose(hist, want, rtol=1e-13) and np.array_equal(counts, np.full(8, 50.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["C3", "C3nest", "C2"])
+def test_powder_average_on_reference_eigenvectors(host, bridge, which):
+    """The histogram of the device (structure factor fused into the cell kernel, binned with atomics) against the numpy histogram
+    of the numpy structure factor of the REFERENCE's ir_interpolate_at output on the same points; the sweep with points generated
+    on the device against the same points binned from the host; direction slices add up to the whole."""
+    import brille_b200
+    from brille_b200 import workloads as W
+    from brille_b200.sharding import ShardedGrid
+    from oracle.consumer import powder_histogram, powder_points
+
+    if which == "C2":
+        wl = W.c2_nacl(host, density=300)
+    else:
+        wl = W.c3_p63mmc(host, density=300, seed=5, cls="BZNestQdc" if which == "C3nest" else "BZTrellisQdc")
+    g = brille_b200.accelerate(wl.grid)
+    B = np.asarray(bridge.flatten_bz(wl.bz)["to_xyz"]).reshape(3, 3)
+    cfg = sf_config(wl.n_atoms, 11, cartesian=False, dw=False)
+    cfg["q_transform"] = B  # Cartesian Q, as Euphonic uses it
+    g.set_structure_factor(**cfg)
+    qr, nqb, wr, nwb, n_dir = (0.2, 6.2), 24, (0.0, 52.0), 40, 4000
+    Q = g.powder_points(qr, nqb, n_dir, seed=3)
+    Qo = powder_points(B, qr, nqb, n_dir, seed=3)
+    assert Q.shape == (nqb * n_dir, 3) and np.abs(Q - Qo).max() <= 1e-13 * np.abs(Qo).max()
+    for weight in (0, 1):
+        hist, counts = g.ir_powder_bin(Q, qr, nqb, wr, nwb, weight)
+        assert g.last_path & 16, "the structure factor was not fused into the cell kernel"
+        assert np.array_equal(counts, np.full(nqb, float(n_dir)))
+        # reference eigenvectors -> numpy structure factor -> numpy histogram
+        m = 30000
+        sel = np.random.default_rng(1).choice(len(Q), m, replace=False)
+        rv, rw = wl.grid.ir_interpolate_at(Q[sel], True, 8)
+        want_sf = structure_factor(Q[sel], rw, **cfg)
+        h_ref, c_ref = powder_histogram(Q[sel], B, rv, want_sf, qr, nqb, wr, nwb, weight)
+        h_dev, c_dev = g.ir_powder_bin(Q[sel], qr, nqb, wr, nwb, weight)
+        assert np.array_equal(c_dev, c_ref)
+        # (an eigenvalue within rounding of a bin edge may fall on either side: compare bin-wise with a tolerance scaled to the
+        # largest bin, and the totals tightly)
+        assert np.abs(h_dev - h_ref).max() <= 1e-9 * h_ref.max()
+        assert abs(h_dev.sum() - h_ref.sum()) <= 1e-10 * h_ref.sum()
+        # against the device's own (vals, sf) through numpy: only the order of the additions differs
+        dv, dsf = g.ir_structure_factor(Q)
+        h_np, _ = powder_histogram(Q, B, dv, dsf, qr, nqb, wr, nwb, weight)
+        assert np.abs(hist - h_np).max() <= 1e-12 * h_np.max()
+        # the sweep (points generated on the device) == the same points binned from the host
+        hs, cs = g.ir_powder_sweep(qr, nqb, wr, nwb, n_dir, seed=3, weight=weight)
+        assert np.array_equal(cs, counts) and np.abs(hs - hist).max() <= 1e-12 * hist.max()
+        # direction slices add up
+        ha, ca = g.ir_powder_sweep(qr, nqb, wr, nwb, n_dir, seed=3, weight=weight, dir_range=(0, 1500))
+        hb, cb = g.ir_powder_sweep(qr, nqb, wr, nwb, n_dir, seed=3, weight=weight, dir_range=(1500, n_dir))
+        assert np.array_equal(ca + cb, counts) and np.abs(ha + hb - hist).max() <= 1e-12 * hist.max()
+    # unfused reduction: the same histogram to rounding
+    g.set_option("sf_fused", 0)
+    hu, cu = g.ir_powder_sweep(qr, nqb, wr, nwb, n_dir, seed=3, weight=1)
+    assert not (g.last_path & 16) and np.abs(hu - hist).max() <= 1e-11 * hist.max()
+    g.set_option("sf_fused", 1)
+    sg = ShardedGrid(wl.grid, [0, 0])
+    sg.set_structure_factor(**cfg)
+    hsg, csg = sg.ir_powder_sweep(qr, nqb, wr, nwb, n_dir, seed=3, weight=1)
+    assert np.array_equal(csg, counts) and np.abs(hsg - hist).max() <= 1e-12 * hist.max()
+    sg.close()
+    with pytest.raises(RuntimeError, match="q_lo"):
+        g.ir_powder_sweep((2.0, 1.0), 4, wr, nwb, 10)
+    g.close()
