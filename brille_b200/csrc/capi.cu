@@ -515,6 +515,60 @@ static void build_bins(b200_grid* g, const double* vertices, size_t n_vertices) 
   }
 }
 
+// Candidate lists of the Nest / Mesh fast path: for every finest bin the tetrahedra `ids` (rows of `pack`, ascending) whose
+// bounding box, widened by 1e-6 of the grid's extent, meets the bin.
+static int build_bin_candidates(b200_grid* g, const std::vector<double>& pack, const std::vector<uint32_t>& ids, uint32_t id_base) {
+  BinDev& b = g->gd.bins;
+  b.cand_offset = nullptr;
+  b.cand_index = nullptr;
+  if (!b.total || ids.empty()) return B200_OK;
+  std::vector<uint32_t> count((size_t)b.total + 1, 0u);
+  auto range = [&](uint32_t id, int lo[3], int hi[3]) {
+    const double* p = &pack[(size_t)id * TET_PACK];
+    for (int d = 0; d < 3; ++d) {
+      double mn = p[4 + d], mx = p[4 + d];
+      for (int j = 1; j < 4; ++j) {
+        mn = std::min(mn, p[4 + 3 * j + d]);
+        mx = std::max(mx, p[4 + 3 * j + d]);
+      }
+      const double pad = b.inv[d] > 0.0 ? 1e-6 * b.n[d] / b.inv[d] : 0.0;
+      const double flo = (mn - pad - b.lo[d]) * b.inv[d], fhi = (mx + pad - b.lo[d]) * b.inv[d];
+      lo[d] = std::max(0, std::min(b.n[d] - 1, (int)std::floor(flo)));
+      hi[d] = std::max(0, std::min(b.n[d] - 1, (int)std::floor(fhi)));
+    }
+  };
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<uint32_t> fill;
+    std::vector<uint32_t> index;
+    if (pass == 1) {
+      uint32_t run = 0;  // counts -> offsets
+      for (size_t i = 0; i <= b.total; ++i) {
+        const uint32_t c = count[i];
+        count[i] = run;
+        run += c;
+      }
+      fill.assign(count.begin(), count.end() - 1);
+      index.resize(count[b.total]);
+    }
+    for (uint32_t id : ids) {
+      int lo[3], hi[3];
+      range(id, lo, hi);
+      for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i) {
+            const size_t bin = (size_t)i + (size_t)b.n[0] * ((size_t)j + (size_t)b.n[1] * k);
+            if (pass == 0) ++count[bin];
+            else index[fill[bin]++] = id - id_base;
+          }
+    }
+    if (pass == 1) {
+      CU(g->structure_pool.upload(count.data(), count.size(), &b.cand_offset));
+      CU(g->structure_pool.upload(index.data(), index.size(), &b.cand_index));
+    }
+  }
+  return B200_OK;
+}
+
 static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
   NestDev& d = g->gd.ne;
   DevPool& pool = g->structure_pool;
@@ -529,6 +583,17 @@ static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
   }
   for (size_t n = 0; n < t->n_nodes; ++n)
     if (t->child_begin[n] > t->child_end[n] || t->child_end[n] > t->n_nodes) return fail(B200_E_INVALID, "nest child range out of bounds");
+  {  // depth of the tree: the slow path of the location walks it with an explicit stack
+    std::vector<uint32_t> depth(t->n_nodes, 0u);
+    uint32_t deepest = 0;
+    for (size_t n = 0; n < t->n_nodes; ++n)
+      for (uint32_t c = t->child_begin[n]; c < t->child_end[n]; ++c) {
+        if (c <= n) return fail(B200_E_INVALID, "nest nodes are not in breadth-first order");
+        depth[c] = depth[n] + 1;
+        deepest = std::max(deepest, depth[c]);
+      }
+    if (deepest >= (uint32_t)NEST_MAX_DEPTH) return fail(B200_E_UNSUPPORTED, "nest deeper than " + std::to_string(NEST_MAX_DEPTH) + " levels");
+  }
   d.n_nodes = t->n_nodes;
   d.n_vertices = t->n_vertices;
   tol_pair(t->tolerance, t->digit, &d.rel, &d.abs_);
@@ -540,6 +605,13 @@ static int build_nest(b200_grid* g, const b200_nest_tables_t* t) {
   g->n_vertices = t->n_vertices;
   g->gd.cells.n_cubes = 0;
   build_bins(g, t->vertices, t->n_vertices);
+  {
+    std::vector<uint32_t> leaves;
+    for (uint32_t n = 1; n < t->n_nodes; ++n)
+      if (t->node_is_leaf[n]) leaves.push_back(n);
+    int rc = build_bin_candidates(g, pack, leaves, 0u);
+    if (rc) return rc;
+  }
   g->gd.cells.n_tets = t->n_nodes;  // bucket key = node index (only leaves ever receive points)
   g->gd.cells.tet_vertices = d.node_vertices;
   return B200_OK;
@@ -574,6 +646,12 @@ static int build_mesh(b200_grid* g, const b200_mesh_tables_t* t) {
   CU(pool.upload(t->conn_offset, (size_t)nconn + (L > 1 ? 1 : 0), &d.conn_offset));
   CU(pool.upload(t->conn_index, L > 1 ? (size_t)t->conn_offset[nconn] : 0, &d.conn_index));
   build_bins(g, t->vertices + 3 * (size_t)t->vert_offset[L - 1], t->vert_offset[L] - t->vert_offset[L - 1]);
+  {  // candidates: the tetrahedra of the finest layer, as layer-local ids
+    std::vector<uint32_t> fine;
+    for (uint32_t k = t->tet_offset[L - 1]; k < t->tet_offset[L]; ++k) fine.push_back(k);
+    int rc = build_bin_candidates(g, pack, fine, t->tet_offset[L - 1]);
+    if (rc) return rc;
+  }
   g->n_vertices = t->vert_offset[L] - t->vert_offset[L - 1];  // data live on the finest layer's vertices
   g->gd.cells.n_cubes = 0;
   g->gd.cells.n_tets = d.n_tets_last;
@@ -869,11 +947,12 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   }
   const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
   // two-kernel trellis location (points regrouped by node between the halves): pays off once the nodes hold a few points each
-  // (nest / mesh: spatial bins, coarsened to about 100 points of the call per bin; the work space is sized for the finest level)
+  // (nest / mesh: spatial bins, coarsened to about 1000 points of the call per bin -- the regrouping only has to make the lanes of a
+  // warp neighbours, and the scan over the buckets is serial; the work space is sized for the finest level)
   const bool trellis = g->gd.kind == B200_GRID_TRELLIS;
   int bin_shift = 0;
   if (!trellis && g->gd.bins.total)
-    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 30 > n_call) ++bin_shift;
+    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 300 > n_call) ++bin_shift;
   const uint32_t n_nodes_alloc = trellis ? g->gd.tr.n_nodes : g->gd.bins.total;
   const uint32_t n_nodes = trellis ? g->gd.tr.n_nodes : (g->gd.bins.total ? bins_at_level(g->gd.bins, bin_shift) : 0u);
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;

@@ -76,6 +76,8 @@ struct NestDev {
   double rel, abs_;               // approx tolerance pair of (approx_.reciprocal, approx_.digit)
 };
 
+constexpr int NEST_MAX_DEPTH = 48;  // levels of a Nest the device walks (brille's default max_branchings is 5)
+
 // Mesh: layered tetrahedral meshes (triangulation_layers.hpp)
 struct MeshDev {
   uint32_t n_layers, n_tets_last;
@@ -101,6 +103,10 @@ struct BinDev {
   double lo[3], inv[3];  // finest bin of x along d: floor((x[d] - lo[d]) * inv[d]), clamped to [0, n[d])
   int n[3];              // finest level (64 per axis with an extent); a call uses every 2^shift-th bin (LocateOut::bin_shift)
   uint32_t total;        // bins of the finest level; 0: not available
+  // candidate tetrahedra per finest bin (CSR, ascending ids): every leaf (Nest) / finest-layer tetrahedron (Mesh) whose bounding
+  // box, slightly widened, meets the bin.  The fast path of the Nest / Mesh location tests only these (nest_locate, mesh_locate).
+  const uint32_t* cand_offset;  // (total + 1), or null
+  const uint32_t* cand_index;
 };
 __host__ __device__ inline uint32_t bins_at_level(const BinDev& b, int shift) {
   uint32_t t = 1;

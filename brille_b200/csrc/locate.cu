@@ -516,71 +516,101 @@ __device__ __forceinline__ void emit_tet(EmitOut& e, const uint32_t* vip, const 
   }
 }
 
-// Nest::indices_weights (nest.hpp:163-222): breadth-first over the nodes that contain x; among the containing
-// leaves the LAST one whose weights are all > 0 wins, else the first; ~0 weights are folded into the largest one
-__device__ __forceinline__ uint32_t nest_locate(const NestDev& t, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
-  e.n = 0;
-  e.slots = 0;
-  tet = -1;
-  cell = 0xffffffffu;
-  constexpr int QCAP = 32;  // ranges of children waiting to be visited (one per containing inner node)
-  uint32_t qb[QCAP], qe[QCAP];
-  int head = 0, tail = 0;
-  qb[0] = t.child_begin[0];
-  qe[0] = t.child_end[0];
-  tail = 1;
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path of the Nest / Mesh location.  The leaves of a Nest (the finest layer of a Mesh) tile the gridded volume, so a point
+// STRICTLY inside one of them -- all four weights above FAST_MARGIN, a million times the tolerances -- has exactly one containing
+// leaf, is inside every ancestor of it (every coarser tetrahedron on the way) with room to spare, and the reference's search,
+// whatever its order, ends with that leaf and the weights computed below (same arithmetic: tetgen_weights).  The candidates
+// come from a uniform grid of bins (BinDev::cand_*): the reference's weights are evaluated for a handful of tetrahedra instead of a descent
+// through every level.  Anything else -- a point within the margin of a face, or in no candidate -- takes the reference's search
+// as it is (nest_search / mesh_search).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr double FAST_MARGIN = 1e-9;
+__device__ __forceinline__ int fast_candidate(const BinDev& b, const double* pack, bool squared_radius, const double* x, double* w) {
+  if (!b.cand_offset) return -1;
+  int ib[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double f = (x[d] - b.lo[d]) * b.inv[d];
+    ib[d] = f > 0.0 ? (f < (double)b.n[d] ? (int)f : b.n[d] - 1) : 0;  // (NaN -> 0)
+  }
+  const uint32_t bin = (uint32_t)(ib[0] + b.n[0] * (ib[1] + b.n[1] * ib[2]));
+  const uint32_t c0 = b.cand_offset[bin], c1 = b.cand_offset[bin + 1];
+  // (measured and not kept: a bounding-box test in place of the circumsphere test with the weights of all lanes evaluated in
+  // lock step -- 12 more loads and 24 min/max per candidate cost more than the weights they save: Nest 2.17 -> 3.11 ms)
+  for (uint32_t c = c0; c < c1; ++c) {
+    const uint32_t id = b.cand_index[c];
+    const double* tp = pack + (size_t)TET_PACK * id;
+    const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+    const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+    const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
+    const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
+    // a point strictly inside a tetrahedron is strictly inside its circumsphere: candidates whose sphere (widened a little; the
+    // record holds r^2 for a Nest, r for a Mesh) does not hold x cannot be the leaf looked for
+    const double r2 = squared_radius ? c23.y : c23.y * c23.y;
+    if (d2 > r2 * (1.0 + 1e-9)) continue;
+    tetgen_weights(tp, x, w);
+    const double lo = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+    if (lo > FAST_MARGIN) return (int)id;  // strictly inside: the one containing leaf
+    if (lo >= -FAST_MARGIN) return -1;     // within the margin of a face: the reference's search decides
+  }
+  return -1;
+}
+
+// Nest::indices_weights (nest.hpp:163-222) as the reference defines it: every node whose ancestors all contain x (circumsphere
+// test, then no weight negative beyond tolerance) is visited; among the containing leaves the LAST one, in the reference's
+// breadth-first order, whose weights are all > 0 wins, else the first; ~0 weights are folded into the largest one.  The tree is
+// stored breadth-first, so "first" and "last" are the smallest and the largest node index: a depth-first walk with an explicit
+// stack (bounded by the depth of the tree, not by how many nodes contain the point) finds the same two leaves.
+__device__ __noinline__ uint32_t nest_search(const NestDev& t, const double* x, double* sw, uint32_t& node_out) {
+  uint32_t sb[NEST_MAX_DEPTH], se[NEST_MAX_DEPTH];
+  int depth = 0;
+  sb[0] = t.child_begin[0];
+  se[0] = t.child_end[0];
   int nsol = 0;
-  bool have_best = false, overflow = false;
-  uint32_t first_node = 0, best_node = 0;
-  double fw[4], bw[4], w[4];
-  while (head < tail) {
-    const uint32_t b = qb[head % QCAP], en = qe[head % QCAP];
-    ++head;
-    // two phases per block of <= 64 children (cf. the trellis): circumsphere mask first, then the weights of the candidates
-    for (uint32_t base = b; base < en; base += 64) {
-      const uint32_t nblk = min(64u, en - base);
-      unsigned long long cand = 0ull;
-      for (uint32_t k = 0; k < nblk; ++k) {
-        const double* tp = t.node_pack + (size_t)TET_PACK * (base + k);
-        const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
-        const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
-        const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
-        const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
-        if (d2 < c23.y || approx_eq(d2, c23.y, t.rel, t.abs_)) cand |= 1ull << k;  // might_contain (:114-122)
+  bool have_best = false;
+  uint32_t first_node = 0xffffffffu, best_node = 0;
+  double fw[4] = {0, 0, 0, 0}, bw[4] = {0, 0, 0, 0}, w[4];
+  while (depth >= 0) {
+    if (sb[depth] >= se[depth]) {
+      --depth;
+      continue;
+    }
+    const uint32_t node = sb[depth]++;
+    const double* tp = t.node_pack + (size_t)TET_PACK * node;
+    const double2 c01 = reinterpret_cast<const double2*>(tp)[0];
+    const double2 c23 = reinterpret_cast<const double2*>(tp)[1];
+    const double d0 = x[0] - c01.x, d1 = x[1] - c01.y, d2v = x[2] - c23.x;
+    const double d2 = ((0.0 + d0 * d0) + d1 * d1) + d2v * d2v;
+    if (!(d2 < c23.y || approx_eq(d2, c23.y, t.rel, t.abs_))) continue;  // might_contain (:114-122)
+    tetgen_weights(tp, x, w);
+    bool ok = true;  // none_negative (:43-48)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ok &= !(w[j] < 0.0 && !approx_eq(w[j], 0.0, t.rel, t.abs_));
+    if (!ok) continue;
+    if (t.node_is_leaf[node]) {
+      if (node < first_node) {
+        first_node = node;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fw[j] = w[j];
       }
-      while (cand) {
-        const uint32_t node = base + (uint32_t)(__ffsll((long long)cand) - 1);
-        cand &= cand - 1ull;
-        tetgen_weights(t.node_pack + (size_t)TET_PACK * node, x, w);
-        bool ok = true;  // none_negative (:43-48)
+      if (w[0] > 0.0 && w[1] > 0.0 && w[2] > 0.0 && w[3] > 0.0 && (!have_best || node > best_node)) {
+        best_node = node;
+        have_best = true;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ok &= !(w[j] < 0.0 && !approx_eq(w[j], 0.0, t.rel, t.abs_));
-        if (!ok) continue;
-        if (t.node_is_leaf[node]) {
-          if (nsol == 0) {
-            first_node = node;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) fw[j] = w[j];
-          }
-          if (w[0] > 0.0 && w[1] > 0.0 && w[2] > 0.0 && w[3] > 0.0) {
-            best_node = node;
-            have_best = true;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bw[j] = w[j];
-          }
-          ++nsol;
-        } else {
-          if (tail - head >= QCAP) { overflow = true; continue; }
-          qb[tail % QCAP] = t.child_begin[node];
-          qe[tail % QCAP] = t.child_end[node];
-          ++tail;
-        }
+        for (int j = 0; j < 4; ++j) bw[j] = w[j];
       }
+      ++nsol;
+    } else if (depth + 1 < NEST_MAX_DEPTH) {
+      ++depth;
+      sb[depth] = t.child_begin[node];
+      se[depth] = t.child_end[node];
     }
   }
-  if (nsol == 0 || overflow) return B200_ST_NOT_FOUND;
+  if (nsol == 0) return B200_ST_NOT_FOUND;
   uint32_t node = first_node;
-  double sw[4] = {fw[0], fw[1], fw[2], fw[3]};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sw[j] = fw[j];
   if (nsol > 1 && have_best) {
     node = best_node;
 #pragma unroll
@@ -593,6 +623,25 @@ __device__ __forceinline__ uint32_t nest_locate(const NestDev& t, const double* 
         if (!approx_eq(sw[j], 0.0, t.rel, t.abs_) && sw[j] > sw[max_at]) max_at = j;
       sw[max_at] += sw[i];
     }
+  node_out = node;
+  return 0u;
+}
+
+__device__ __forceinline__ uint32_t nest_locate(const BZDev& bz, const GridDev& gd, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
+  const NestDev& t = gd.ne;
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  cell = 0xffffffffu;
+  double sw[4];
+  uint32_t node = 0;
+  const int fast = fast_candidate(gd.bins, t.node_pack, true, x, sw);
+  if (fast >= 0) {
+    node = (uint32_t)fast;
+  } else {
+    const uint32_t st = nest_search(t, x, sw, node);
+    if (st) return st;
+  }
   emit_tet(e, t.node_vertices + 4 * (size_t)node, sw, t.rel, t.abs_);
   cell = node;
   tet = (int)node;
@@ -615,12 +664,8 @@ __device__ __forceinline__ bool mesh_contains(const BZDev& bz, const double* tp,
   for (int j = 0; j < 4; ++j) ok &= (w[j] > 0.0 || approx_eq(w[j], 0.0, bz.def_rel, bz.def_abs));
   return ok;
 }
-__device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const MeshDev& t, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
-  e.n = 0;
-  e.slots = 0;
-  tet = -1;
-  cell = 0xffffffffu;
-  double w[4];
+// TetTri::locate as the reference walks it (triangulation_layers.hpp:401-417): the slow path behind fast_candidate
+__device__ __noinline__ uint32_t mesh_search(const BZDev& bz, const MeshDev& t, const double* x, double* w, uint32_t& idx_out) {
   uint32_t idx = 0xffffffffu;
   for (uint32_t layer = 0; layer < t.n_layers; ++layer) {
     uint32_t found = 0xffffffffu;
@@ -646,6 +691,31 @@ __device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const MeshDev& 
     if (found == 0xffffffffu) return B200_ST_NOT_FOUND;
     idx = found;
   }
+  idx_out = idx;
+  return 0u;
+}
+
+__device__ __forceinline__ uint32_t mesh_locate(const BZDev& bz, const GridDev& gd, const double* x, EmitOut& e, uint32_t& cell, int& tet) {
+  const MeshDev& t = gd.me;
+  e.n = 0;
+  e.slots = 0;
+  tet = -1;
+  cell = 0xffffffffu;
+  double w[4];
+  uint32_t idx = 0xffffffffu;
+  {  // fast path: a point strictly inside a tetrahedron of the finest layer (see fast_candidate)
+    const uint32_t last = t.tet_offset[t.n_layers - 1];
+    const int fast = fast_candidate(gd.bins, t.tet_pack + (size_t)TET_PACK * last, false, x, w);
+    if (fast >= 0) {
+      idx = (uint32_t)fast;
+      emit_tet(e, t.tets + 4 * (size_t)(last + idx), w, bz.def_rel, bz.def_abs);
+      cell = idx;
+      tet = (int)idx;
+      return e.n < 1 ? (uint32_t)B200_ST_NOT_FOUND : 0u;
+    }
+  }
+  const uint32_t st = mesh_search(bz, t, x, w, idx);
+  if (st) return st;
   emit_tet(e, t.tets + 4 * (size_t)(t.tet_offset[t.n_layers - 1] + idx), w, bz.def_rel, bz.def_abs);
   cell = idx;
   tet = (int)idx;
@@ -811,8 +881,8 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
       e.v = out.vertex + 8 * i;
       e.w = out.weight + REC_DOUBLES * i;
       if (KIND == B200_GRID_TRELLIS) st |= trellis_locate(bz, tr, knots, x, e, cell, tet);
-      else if (KIND == B200_GRID_NEST) st |= nest_locate(gd.ne, x, e, cell, tet);
-      else st |= mesh_locate(bz, gd.me, x, e, cell, tet);
+      else if (KIND == B200_GRID_NEST) st |= nest_locate(bz, gd, x, e, cell, tet);
+      else st |= mesh_locate(bz, gd, x, e, cell, tet);
       if (e.n == 0) {  // not found: defined contents for the row
         for (int j = 0; j < 8; ++j) {
           e.v[j] = 0xffffffffu;
@@ -856,7 +926,7 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
 // node -- same branch (cube / triangulated), same tetrahedra, same trip counts, loads that broadcast.  Same arithmetic and
 // the same outputs as the tail of k_locate.
 template <int KIND>
-__global__ void __launch_bounds__(128, KIND == B200_GRID_TRELLIS ? 5 : 3)
+__global__ void __launch_bounds__(128, KIND == B200_GRID_TRELLIS ? 5 : 4)
 k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t mode, LocateOut out, const uint32_t* __restrict__ order,
                  unsigned long long* __restrict__ fail_count) {
   const TrellisDev& tr = gd.tr;
@@ -895,9 +965,9 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
     if (KIND == B200_GRID_TRELLIS) {
       if (!(st & B200_ST_NOT_FOUND)) st |= trellis_in_node(bz, tr, pp.x, cell, e, tet);
     } else if (KIND == B200_GRID_NEST) {
-      st |= nest_locate(gd.ne, pp.x, e, cell, tet);
+      st |= nest_locate(bz, gd, pp.x, e, cell, tet);
     } else {
-      st |= mesh_locate(bz, gd.me, pp.x, e, cell, tet);
+      st |= mesh_locate(bz, gd, pp.x, e, cell, tet);
     }
     if (e.n == 0) {  // not found: defined contents for the row
       for (int j = 0; j < 8; ++j) {

@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, GPU run K: bin-candidate fast path of the Nest / Mesh location: parity + timing
+mkdir -p gpurun_out
+timeout 2000 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py tests/test_consumer.py tests/test_dropin.py -m gpu -q -x -k "nest or mesh or Nest or Mesh or c4 or C4 or golden or shared or two_kernel or dropin_launches" > gpurun_out/pytest_r02k.log 2>&1
+for c in C3nest C3mesh C4; do timeout 300 python profiles/perf_ab.py $c > gpurun_out/perf_${c}_r02k.log 2>&1; done
+tail -4 gpurun_out/pytest_r02k.log; cat gpurun_out/perf_C*_r02k.log | cut -c1-250
