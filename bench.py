@@ -249,7 +249,10 @@ def measure_config(torch, dist, brille_b200, spec, local, rank, world, steps, pe
     achieved = bpq * nq / (k["interpolate"] * 1e-3) / 1e9 if k["interpolate"] > 0 else None
     names = {4: "k_interp_cell_tma (pipelined cell kernel)", 2: "k_interp_cell (on-the-fly cell kernel)", 8: "k_interp (general kernel)"}
     kernel = next((v for b_, v in names.items() if path & b_), "?")
-    traffic = (profiled_traffic() or {}).get("configs", {}).get(key)
+    # DRAM bytes of the interpolation kernel per step from the committed ncu captures (profiles/roofline_traffic.json), when one
+    # exists for this configuration with the same points per launch
+    tr = (profiled_traffic() or {}).get("configs", {}).get(key)
+    traffic = tr["dram_bytes_per_launch"] * (nq // c) if tr and tr.get("q_per_launch") == c else None
     out = {
         "workload": text, "value": world * nq / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "q_per_gpu_per_step": nq, "q_per_call": c,
         "modes": wl.modes, "atoms": wl.n_atoms, "vertices": int(wl.grid.rlu.shape[0]), "bytes_per_q": bpq, "gpu_launches_per_step": int(launches),

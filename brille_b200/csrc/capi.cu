@@ -515,8 +515,9 @@ static void build_bins(b200_grid* g, const double* vertices, size_t n_vertices) 
   }
 }
 
-// Candidate lists of the Nest / Mesh fast path: for every finest bin the tetrahedra `ids` (rows of `pack`, ascending) whose
-// bounding box, widened by 1e-6 of the grid's extent, meets the bin.
+// Candidate lists of the Nest / Mesh fast path: for every finest bin the tetrahedra `ids` (rows of `pack`, ascending) that meet the
+// bin, widened by 1e-6 of the grid's extent (bounding boxes first, then the four face planes: a tetrahedron fills about a sixth
+// of its box -- C3 on a Nest: 16 candidates per point by boxes alone, a quarter of that with the planes).
 static int build_bin_candidates(b200_grid* g, const std::vector<double>& pack, const std::vector<uint32_t>& ids, uint32_t id_base) {
   BinDev& b = g->gd.bins;
   b.cand_offset = nullptr;
@@ -537,6 +538,41 @@ static int build_bin_candidates(b200_grid* g, const std::vector<double>& pack, c
       hi[d] = std::max(0, std::min(b.n[d] - 1, (int)std::floor(fhi)));
     }
   };
+  // a bin inside the bounding box of a tetrahedron but wholly beyond one of its face planes does not meet it (the box corner
+  // nearest to the inside of the face decides); conservative: the edge-edge separating axes are not tested
+  struct Planes { double n[4][3], d[4]; };
+  auto planes_of = [&](uint32_t id) {
+    const double* p = &pack[(size_t)id * TET_PACK];
+    Planes P;
+    for (int f = 0; f < 4; ++f) {  // face f is opposite vertex f
+      const double* a = p + 4 + 3 * ((f + 1) & 3);
+      const double* bb = p + 4 + 3 * ((f + 2) & 3);
+      const double* c = p + 4 + 3 * ((f + 3) & 3);
+      const double* o = p + 4 + 3 * f;
+      const double u[3] = {bb[0] - a[0], bb[1] - a[1], bb[2] - a[2]}, v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+      double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+      const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      double side = n[0] * (o[0] - a[0]) + n[1] * (o[1] - a[1]) + n[2] * (o[2] - a[2]);
+      const double sgn = side > 0 ? -1.0 : 1.0;  // outward: away from the opposite vertex
+      for (int k = 0; k < 3; ++k) P.n[f][k] = len > 0 ? sgn * n[k] / len : 0.0;
+      P.d[f] = P.n[f][0] * a[0] + P.n[f][1] * a[1] + P.n[f][2] * a[2];
+    }
+    return P;
+  };
+  double cell[3], padlen = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    cell[d] = b.inv[d] > 0.0 ? 1.0 / b.inv[d] : 0.0;
+    padlen = std::max(padlen, 1e-6 * b.n[d] * cell[d]);
+  }
+  auto meets = [&](const Planes& P, int i, int j, int k) {
+    const double lo3[3] = {b.lo[0] + i * cell[0], b.lo[1] + j * cell[1], b.lo[2] + k * cell[2]};
+    for (int f = 0; f < 4; ++f) {
+      double m = -P.d[f];
+      for (int d = 0; d < 3; ++d) m += P.n[f][d] * (P.n[f][d] > 0 ? lo3[d] : lo3[d] + cell[d]);  // corner with the smallest n.p
+      if (m > padlen) return false;
+    }
+    return true;
+  };
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<uint32_t> fill;
     std::vector<uint32_t> index;
@@ -553,9 +589,11 @@ static int build_bin_candidates(b200_grid* g, const std::vector<double>& pack, c
     for (uint32_t id : ids) {
       int lo[3], hi[3];
       range(id, lo, hi);
+      const Planes P = planes_of(id);
       for (int k = lo[2]; k <= hi[2]; ++k)
         for (int j = lo[1]; j <= hi[1]; ++j)
           for (int i = lo[0]; i <= hi[0]; ++i) {
+            if (!meets(P, i, j, k)) continue;
             const size_t bin = (size_t)i + (size_t)b.n[0] * ((size_t)j + (size_t)b.n[1] * k);
             if (pass == 0) ++count[bin];
             else index[fill[bin]++] = id - id_base;
@@ -947,12 +985,12 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   }
   const uint32_t nsub = (uint32_t)g->h_bz.n_ops;
   // two-kernel trellis location (points regrouped by node between the halves): pays off once the nodes hold a few points each
-  // (nest / mesh: spatial bins, coarsened to about 1000 points of the call per bin -- the regrouping only has to make the lanes of a
-  // warp neighbours, and the scan over the buckets is serial; the work space is sized for the finest level)
+  // (nest / mesh: spatial bins, coarsened to about 100 points of the call per bin: the lanes of a warp then share the candidate list of
+  // the fast path; bins of 1000 points sort faster but the second kernel loses more than that; the work space is sized for the finest level)
   const bool trellis = g->gd.kind == B200_GRID_TRELLIS;
   int bin_shift = 0;
   if (!trellis && g->gd.bins.total)
-    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 300 > n_call) ++bin_shift;
+    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 30 > n_call) ++bin_shift;
   const uint32_t n_nodes_alloc = trellis ? g->gd.tr.n_nodes : g->gd.bins.total;
   const uint32_t n_nodes = trellis ? g->gd.tr.n_nodes : (g->gd.bins.total ? bins_at_level(g->gd.bins, bin_shift) : 0u);
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;

@@ -16,7 +16,13 @@ from bench import NQ, Q_SEED, build_workload  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 nq = int(float(sys.argv[2])) if len(sys.argv) > 2 else NQ
-wl = build_workload()
+config = os.environ.get("PROF_CONFIG", "C3")  # C3 (default), C2, C4, C3nest, C3mesh: the workload builders of brille_b200.workloads
+if config == "C3":
+    wl = build_workload()
+else:
+    from brille_b200 import host as _host, workloads as _W
+
+    wl = _W.BUILDERS[config](_host.get()) if config in _W.BUILDERS else _W.c3_p63mmc(_host.get(), cls={"C3nest": "BZNestQdc", "C3mesh": "BZMeshQdc"}[config])
 grid = brille_b200.accelerate(wl.grid)
 dQ = torch.from_numpy(wl.make_q(nq, Q_SEED)).cuda()
 vals = torch.empty((nq, wl.modes, 1), dtype=torch.float64, device="cuda")

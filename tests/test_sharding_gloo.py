@@ -51,10 +51,29 @@ def _worker(rank, world, port, q):
     pos = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
     sf = structure_factor(shard(Q, rank, world), w, coef, positions=pos)
     SF = gather_rows(torch.from_numpy(sf)).numpy()
+    # the powder sweep shards the DIRECTION sequence: every rank bins its slice of directions at every |Q| and the partial histograms
+    # meet in one all-reduce -- the only exchange of the path
+    from brille_b200.sharding import shard_bounds
+    from oracle.consumer import powder_histogram, powder_points
+
+    B = np.asarray(s["bz"]["to_xyz"]).reshape(3, 3)
+    qr, nqb, wr, nwb, n_dir = (0.3, 3.3), 6, (0.0, 60.0), 10, 40
+    lo, hi = shard_bounds(n_dir, rank, world)
+    Qp = powder_points(B, qr, nqb, n_dir, seed=9, dir_range=(lo, hi))
+    rc, pv, pw, _ = orc.interpolate_at(Qp, probe=False)
+    assert rc == 0
+    hist, counts = powder_histogram(Qp, B, pv, structure_factor(Qp, pw, coef, positions=pos), qr, nqb, wr, nwb, 1)
+    th, tc = torch.from_numpy(hist), torch.from_numpy(counts)
+    dist.all_reduce(th)
+    dist.all_reduce(tc)
     if rank == 0:
         rc, v1, w1, _ = orc.interpolate_at(Q, probe=False)
         ok = np.array_equal(V, v1) and np.array_equal(Wr, w1) and V.shape[0] == len(Q)
         ok = ok and np.array_equal(SF, structure_factor(Q, w1, coef, positions=pos))
+        Qa = powder_points(B, qr, nqb, n_dir, seed=9)
+        rc, av, aw, _ = orc.interpolate_at(Qa, probe=False)
+        h1, c1 = powder_histogram(Qa, B, av, structure_factor(Qa, aw, coef, positions=pos), qr, nqb, wr, nwb, 1)
+        ok = ok and np.array_equal(tc.numpy(), c1) and np.allclose(th.numpy(), h1, rtol=1e-12, atol=0) and c1.sum() == nqb * n_dir
         q.put(bool(ok))
     dist.barrier()
     dist.destroy_process_group()
