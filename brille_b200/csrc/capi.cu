@@ -232,6 +232,7 @@ struct b200_grid {
   int interp_path = 0;     // 0 auto, 1 general kernel only, 2 cell-batched kernel whenever eligible
   uint32_t chunk = 256;    // points per CTA item of the cell-batched kernel
   int split_locate = 1;    // trellis: two-kernel location with the points regrouped by node in between
+  size_t bin_points = 300;  // nest / mesh: the regrouping bins are coarsened until they hold about this many points of the call
   int coop_locate = 1;     // trellis: second location kernel in its warp-cooperative form (node records staged in shared memory)
   int tile = 4;            // points per register tile of the pipelined cell kernel (4: 2 CTAs/SM, 2: 3 CTAs/SM)
   int cell_kernel = 0;     // 0 auto (pipelined kernel when its cell table fits), 1 on-the-fly staging kernel, 2 pipelined only
@@ -990,7 +991,7 @@ static int enqueue(b200_grid* g, Workspace& ws, unsigned long long* d_fail, cons
   const bool trellis = g->gd.kind == B200_GRID_TRELLIS;
   int bin_shift = 0;
   if (!trellis && g->gd.bins.total)
-    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * 30 > n_call) ++bin_shift;
+    while (bin_shift < 4 && (size_t)bins_at_level(g->gd.bins, bin_shift) * g->bin_points > n_call) ++bin_shift;
   const uint32_t n_nodes_alloc = trellis ? g->gd.tr.n_nodes : g->gd.bins.total;
   const uint32_t n_nodes = trellis ? g->gd.tr.n_nodes : (g->gd.bins.total ? bins_at_level(g->gd.bins, bin_shift) : 0u);
   const bool split = cell && n_nodes && g->split_locate && !(mode & MODE_NO_LOCATE) && n_call >= 8 * (size_t)n_nodes;
@@ -1740,6 +1741,9 @@ extern "C" int b200_grid_set_option(b200_grid_t* g, const char* name, double val
     g->interp_path = (int)value;
   } else if (n == "split_locate") {
     g->split_locate = value != 0;
+  } else if (n == "bin_points") {
+    if (value < 1) return fail(B200_E_INVALID, "bin_points must be >= 1");
+    g->bin_points = (size_t)value;
   } else if (n == "coop_locate") {
     g->coop_locate = value != 0;
   } else if (n == "tile") {

@@ -325,6 +325,7 @@ struct PairWork {  // per-warp arrays of `dim` entries each, carved from dynamic
 __host__ __device__ inline size_t pair_work_bytes(uint32_t dim) { return (size_t)dim * (2 * sizeof(double) + 6 * sizeof(int)); }
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int SERIAL_BID_MAX_DIM = 32;
 __device__ __forceinline__ void lexmin_reduce(double& val, int& idx) {  // minimum value, lowest index among equals, in every lane
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -397,6 +398,47 @@ __device__ void match_pair(const int dim, const double* __restrict__ C, const Pa
     }
   }
   // ---- row bidding: two sweeps over the unassigned rows (the list is consumed and refilled in place) ----------------------
+  // The tolerance is small against the costs, so a pair can take thousands of bids, each a dependent step: for few modes a
+  // bid done by the whole warp is two 5-stage shuffle reductions for a dozen columns (the slowest pair of a grid then sets the
+  // kernel time, whatever the occupancy: C3 6 ms).  Up to SERIAL_BID_MAX_DIM columns one lane walks the row instead -- the same
+  // two lexicographic minima, read off a single pass.
+  if (dim <= SERIAL_BID_MAX_DIM) {
+    if (lane == 0) {
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        int k = 0;
+        const int n_todo = nfree;
+        nfree = 0;
+        while (k < n_todo) {
+          const int i = w.freerow[k++];
+          const double* ci = C + (size_t)i * dim;
+          double umin = ci[0] - w.v[0], usub = DBL_MAX;
+          int j1 = 0, j2 = dim;
+          for (int j = 1; j < dim; ++j) {  // (value, index) minimum and runner-up in one pass, lowest index among equals
+            const double h = ci[j] - w.v[j];
+            if (h < umin) { usub = umin; j2 = j1; umin = h; j1 = j; }
+            else if (h < usub) { usub = h; j2 = j; }
+          }
+          int i0 = w.colsol[j1];
+          const double vj = w.v[j1], lowered = vj - (usub + eps - umin);
+          const bool lowers = lowered < vj;
+          if (lowers) {
+            w.v[j1] = lowered;
+          } else if (i0 != -1) {
+            j1 = j2;
+            i0 = w.colsol[j2];
+          }
+          w.rowsol[i] = j1;
+          w.colsol[j1] = i;
+          if (i0 != -1) {
+            if (lowers) w.freerow[--k] = i0;
+            else w.freerow[nfree++] = i0;
+          }
+        }
+      }
+    }
+    nfree = __shfl_sync(FULL, nfree, 0);
+    __syncwarp();
+  } else
   for (int sweep = 0; sweep < 2; ++sweep) {
     int k = 0;
     const int n_todo = nfree;

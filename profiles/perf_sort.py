@@ -11,16 +11,18 @@ sys.path.insert(0, ROOT)
 import brille_b200  # noqa: E402
 from brille_b200 import workloads as W  # noqa: E402
 from brille_b200.grid import _bridge  # noqa: E402
-from oracle import ref  # noqa: E402
+from brille_b200 import host as _hostmod  # noqa: E402
 
-host, bridge = ref.host(), _bridge()
+host, bridge = _hostmod.get(), _bridge()
 for name, wl in (("C3 (12 modes)", W.c3_p63mmc(host)), ("C4 (72 modes, nest)", W.c4_p21c_nest(host))):
     plan = bridge.sort_plan(wl.grid)
     g = brille_b200.accelerate(wl.grid)
-    g.sort_pairs(plan["pairs"][:64], plan)  # warm-up
-    t0 = time.perf_counter()
-    row, col = g.sort_pairs(plan["pairs"], plan)
-    t_dev = time.perf_counter() - t0
+    g.sort_pairs(plan["pairs"], plan)  # warm-up at full size (work space, kernel attributes)
+    t_dev = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        row, col = g.sort_pairs(plan["pairs"], plan)
+        t_dev = min(t_dev, time.perf_counter() - t0)
     t0 = time.perf_counter()
     g.sort()
     t_all = time.perf_counter() - t0
