@@ -1120,6 +1120,8 @@ static int interpolate_device(b200_grid* g, const double* dQ, size_t nQ, uint32_
                               b200_probe_t* dprobe, cudaStream_t stream, uint64_t* n_failed) {
   int rc = check_ready(g, true, ir);
   if (rc) return rc;
+  // (point indices travel as 32-bit words through the sorts and the point records; the host-buffer entry points chunk on their own)
+  if (nQ >= 0xfffffff0ull) return fail(B200_E_INVALID, "at most 4294967279 points per device-buffer call");
   DeviceGuard guard;
   CU(cudaSetDevice(g->device));
   if (g->timing) g->kernel_ms.clear();
@@ -1423,6 +1425,7 @@ extern "C" int b200_ir_structure_factor_device(b200_grid_t* g, const double* dQ,
   if (nQ && (!dQ || !dvals || !dsf)) return fail(B200_E_INVALID, "NULL buffer");
   if (n_failed) *n_failed = 0;
   if (nQ == 0) return B200_OK;
+  if (nQ >= 0xfffffff0ull) return fail(B200_E_INVALID, "at most 4294967279 points per device-buffer call");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard;
   CU(cudaSetDevice(g->device));
