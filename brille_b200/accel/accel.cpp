@@ -4,14 +4,15 @@
 // wrap/_common_grid.hpp:272-341,408-437 and wrap/_bz.cpp:378-520, compiled here against brille's own headers WITHOUT editing
 // brille's sources.  For every grid class brille registers (BZ{Trellis,Nest,Mesh}Q{dd,dc,cc}: wrap/_trellis.hpp:29-101,
 // _nest.hpp:29-69, _mesh.hpp:29-55) a C++ subclass is registered as a Python subclass of brille's own class.  It inherits
-// everything -- constructors, properties, fill, sort, node queries -- and overrides
+// everything -- constructors, properties, fill, node queries -- and overrides
 //
 //     ir_interpolate_at(Q, useparallel=False, threads=-1, do_not_move_points=False)      wrap/_common_grid.hpp:276-301
 //     interpolate_at(Q, useparallel=False, threads=-1, do_not_move_points=False)          wrap/_common_grid.hpp:412-437 (trellis)
 //
 // with calls to the C ABI (include/brille_b200.h): the host object is flattened once (bridge/flatten.hpp) into the tables
-// b200_grid_create / b200_grid_set_data copy to the device; fill / sort / set_flags_weights run brille's host code and mark the
-// device copy of the data stale.  The GIL is released around the C-ABI calls; outputs are fresh numpy arrays of the shapes and
+// b200_grid_create / b200_grid_set_data copy to the device; fill / set_flags_weights run brille's host code and mark the
+// device copy of the data stale; sort() (and the `sort` argument of the other two) solves the mode assignments on the device
+// (b200_grid_sort_pairs) and writes them into brille's own permutation table.  The GIL is released around the C-ABI calls; outputs are fresh numpy arrays of the shapes and
 // dtypes brille returns; non-zero return codes become RuntimeError with brille's own texts.
 // BrillouinZone.isinside / moveinto / ir_moveinto / ir_moveinto_wedge (wrap/_bz.cpp:378-520) are replaced on brille's own class
 // by versions that run the same device kernel (b200_moveinto) and return what brille returns (rotation MATRICES).
@@ -24,11 +25,16 @@
 #include <pybind11/complex.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
+#include <array>
+#include <complex>
 #include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "flatten.hpp"
@@ -268,6 +274,61 @@ struct Accel : Base {
   void invalidate() {
     if (dev) dev->data_current = false;
   }
+  // DualInterpolator::sort() (interpolatordual.hpp:398-434) with its parallel loop -- the cost matrix and the Jonker-Volgenant
+  // assignment of every connected vertex pair -- on the device (b200_grid_sort_pairs), and determine_permutation_ij's
+  // PermutationTable::overwrite(i, j, row) / (j, i, col) (:426-433) applied here in the order of the pairs, i.e. what the
+  // reference does with one thread.  overwrite(i, j, vector) looks every permutation up by a linear scan of the list of distinct
+  // permutations (permutation_table.hpp:173-183,215-226); the same list is kept here with a hash index next to it and the
+  // pair is pointed at its entry with overwrite(i, j, index) (:164-170).  Real-valued eigenvectors stay with brille's host
+  // sort() (the device refuses them: the reference's anti-phase of real data reads an uninitialised buffer, utilities.tpp:530).
+  void sort_on_device() {
+    if constexpr (!std::is_same<R, std::complex<double>>::value) {
+      Base::sort();
+      invalidate();
+    } else {
+      DeviceGrid& g = ensure();
+      auto& dual = const_cast<std::remove_const_t<std::remove_reference_t<decltype(this->data())>>&>(this->data());
+      py::dict plan = sort_plan(dual);
+      auto pairs = plan["pairs"].cast<py::array_t<unsigned, py::array::c_style | py::array::forcecast>>();
+      const size_t n_pairs = static_cast<size_t>(pairs.shape(0));
+      if (!g.filled || n_pairs == 0) {  // nothing to assign: the reference's loop is empty too
+        Base::sort();
+        return;
+      }
+      b200_sort_config_t cfg{};
+      fill_fixed(cfg.values_costmult, plan["values_costmult"]);
+      fill_fixed(cfg.vectors_costmult, plan["vectors_costmult"]);
+      cfg.values_vector_cost = plan["values_vector_cost"].cast<int>();
+      cfg.vectors_vector_cost = plan["vectors_vector_cost"].cast<int>();
+      const size_t modes = this->data().branches();
+      std::vector<int32_t> row(n_pairs * modes), col(n_pairs * modes);
+      int rc;
+      {
+        py::gil_scoped_release release;
+        rc = b200_grid_sort_pairs(g.h, pairs.data(), n_pairs, &cfg, row.data(), col.data(), nullptr);
+      }
+      check(rc);
+      brille::PermutationTable& table = DualSpy<T, R>::table(dual);
+      auto& perms = PermSpy::perms(table);
+      std::unordered_map<std::string, size_t> index;  // permutation bytes -> position of its FIRST occurrence in the list
+      auto key_of = [modes](const brille::ind_t* p) { return std::string(reinterpret_cast<const char*>(p), modes * sizeof(brille::ind_t)); };
+      for (size_t i = 0; i < perms.size(); ++i)
+        if (perms[i].size() == modes) index.emplace(key_of(perms[i].data()), i);
+      std::vector<brille::ind_t> v(modes);
+      auto point_at = [&](size_t i, size_t j, const int32_t* src) {
+        for (size_t e = 0; e < modes; ++e) v[e] = static_cast<brille::ind_t>(src[e]);
+        auto found = index.emplace(key_of(v.data()), perms.size());
+        if (found.second) perms.push_back(v);
+        table.overwrite(i, j, found.first->second);
+      };
+      const unsigned* pr = pairs.data();
+      for (size_t k = 0; k < n_pairs; ++k) {
+        point_at(pr[2 * k], pr[2 * k + 1], row.data() + k * modes);
+        point_at(pr[2 * k + 1], pr[2 * k], col.data() + k * modes);
+      }
+      invalidate();
+    }
+  }
   template <class X>
   static py::array_t<X> output(size_t n, const std::vector<unsigned>& stored_shape) {
     std::vector<py::ssize_t> sh{static_cast<py::ssize_t>(n)};
@@ -293,6 +354,107 @@ struct Accel : Base {
     check(rc);
     return py::make_tuple(vals, vecs);
   }
+
+  // ---- device-resident consumers (the slot of the commented-out ir_interpolate_at_dw, wrap/_common_grid.hpp:343-405)
+  using dvec = py::array_t<double, py::array::c_style | py::array::forcecast>;
+  void set_structure_factor(py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> coef, py::object positions,
+                            py::object q_transform, py::object debye_waller, bool conjugate) {
+    DeviceGrid& g = ensure();
+    b200_sf_config_t c{};
+    c.n_atoms = static_cast<uint32_t>(coef.size());
+    c.coef = reinterpret_cast<const double*>(coef.data());
+    dvec pos, dw, qt;
+    if (!positions.is_none()) {
+      pos = dvec::ensure(positions);
+      if (!pos || static_cast<size_t>(pos.size()) != 3u * c.n_atoms) throw std::runtime_error("positions must be (n_atoms, 3)");
+      c.positions = pos.data();
+    }
+    if (!debye_waller.is_none()) {
+      dw = dvec::ensure(debye_waller);
+      if (!dw || static_cast<size_t>(dw.size()) != 9u * c.n_atoms) throw std::runtime_error("debye_waller must be (n_atoms, 3, 3)");
+      c.debye_waller = dw.data();
+    }
+    for (int i = 0; i < 9; ++i) c.q_transform[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (!q_transform.is_none()) {
+      qt = dvec::ensure(q_transform);
+      if (!qt || qt.size() != 9) throw std::runtime_error("q_transform must be 3x3");
+      for (int i = 0; i < 9; ++i) c.q_transform[i] = qt.data()[i];
+    }
+    c.conjugate = conjugate ? 1 : 0;
+    check(b200_grid_set_structure_factor(g.h, &c));
+  }
+  DeviceGrid& ready() {
+    DeviceGrid& g = ensure();
+    if (!g.filled) throw std::runtime_error("The interpolation data must be filled before interpolating.");
+    return g;
+  }
+  static void check_q(const dvec& Q) {
+    if (Q.ndim() != 2 || Q.shape(1) != 3) throw std::runtime_error("Interpolation requires one or more 3-vectors");
+  }
+  py::tuple structure_factor(dvec Q, bool no_move) {
+    check_q(Q);
+    DeviceGrid& g = ready();
+    const size_t n = static_cast<size_t>(Q.shape(0));
+    auto vs = this->data().values().shape();
+    py::array_t<T> vals = output<T>(n, std::vector<unsigned>(vs.begin(), vs.end()));
+    py::array_t<double> sf({static_cast<py::ssize_t>(n), static_cast<py::ssize_t>(this->data().branches())});
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = b200_ir_structure_factor(g.h, Q.data(), n, no_move ? B200_FLAG_NO_MOVE : 0u, vals.mutable_data(), sf.mutable_data());
+    }
+    check(rc);
+    return py::make_tuple(vals, sf);
+  }
+  static b200_powder_config_t powder_config(std::array<double, 2> q_range, uint32_t n_qbins, std::array<double, 2> w_range, uint32_t n_wbins, int weight) {
+    b200_powder_config_t c{};
+    c.n_qbins = n_qbins;
+    c.n_wbins = n_wbins;
+    c.q_lo = q_range[0];
+    c.q_hi = q_range[1];
+    c.w_lo = w_range[0];
+    c.w_hi = w_range[1];
+    c.weight = weight;
+    return c;
+  }
+  py::tuple powder_bin(dvec Q, std::array<double, 2> q_range, uint32_t n_qbins, std::array<double, 2> w_range, uint32_t n_wbins, int weight,
+                       bool no_move) {
+    check_q(Q);
+    DeviceGrid& g = ready();
+    const b200_powder_config_t c = powder_config(q_range, n_qbins, w_range, n_wbins, weight);
+    py::array_t<double> hist({static_cast<py::ssize_t>(n_qbins), static_cast<py::ssize_t>(n_wbins)}), counts(static_cast<py::ssize_t>(n_qbins));
+    std::fill_n(hist.mutable_data(), hist.size(), 0.0);
+    std::fill_n(counts.mutable_data(), counts.size(), 0.0);
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = b200_ir_powder_bin(g.h, Q.data(), static_cast<size_t>(Q.shape(0)), no_move ? B200_FLAG_NO_MOVE : 0u, &c, hist.mutable_data(),
+                              counts.mutable_data());
+    }
+    check(rc);
+    return py::make_tuple(hist, counts);
+  }
+  py::tuple powder_sweep(std::array<double, 2> q_range, uint32_t n_qbins, std::array<double, 2> w_range, uint32_t n_wbins, uint64_t n_dir,
+                         uint64_t seed, int weight, py::object dir_range) {
+    DeviceGrid& g = ready();
+    const b200_powder_config_t c = powder_config(q_range, n_qbins, w_range, n_wbins, weight);
+    uint64_t lo = 0, hi = n_dir;
+    if (!dir_range.is_none()) {
+      auto r = dir_range.cast<std::array<uint64_t, 2>>();
+      lo = r[0];
+      hi = r[1];
+    }
+    py::array_t<double> hist({static_cast<py::ssize_t>(n_qbins), static_cast<py::ssize_t>(n_wbins)}), counts(static_cast<py::ssize_t>(n_qbins));
+    std::fill_n(hist.mutable_data(), hist.size(), 0.0);
+    std::fill_n(counts.mutable_data(), counts.size(), 0.0);
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = b200_ir_powder_sweep(g.h, &c, n_dir, seed, lo, hi, hist.mutable_data(), counts.mutable_data());
+    }
+    check(rc);
+    return py::make_tuple(hist, counts);
+  }
 };
 
 template <class Base, class T, class R, int KIND>
@@ -314,16 +476,39 @@ void declare(py::module& m, py::module& host, const char* name) {
   }
   cls.def(py::init([](const Base& b) { return std::make_unique<A>(b); }), "host_grid"_a, "wrap an existing brille grid object (shares its data)");
   // host methods that change what the device holds: run brille's own, then mark the device copy stale
-  for (const char* meth : {"fill", "sort", "set_flags_weights"}) {
+  // (their trailing `sort` argument -- wrap/_common_grid.hpp:47,147,503: keyword or last positional -- is taken out and
+  // honoured with the device sort afterwards)
+  for (const char* meth : {"fill", "set_flags_weights"}) {
     py::object host_method = base.attr(meth);
+    const bool is_fill = std::string(meth) == "fill";
     cls.attr(meth) = py::cpp_function(
-        [host_method](py::object self, py::args a, py::kwargs k) {
-          py::object r = host_method(self, *a, **k);
-          self.cast<A&>().invalidate();
+        [host_method, is_fill](py::object self, py::args a, py::kwargs k) {
+          bool sort = false;
+          py::list pos;
+          for (auto x : a) pos.append(x);
+          py::dict kw;
+          for (auto item : k)
+            if (py::str(item.first).cast<std::string>() == "sort") sort = item.second.cast<bool>();
+            else kw[item.first] = item.second;
+          const size_t np = pos.size();
+          if (np == 5 || (is_fill && np == 7)) {
+            py::object last = pos[np - 1];
+            if (py::isinstance<py::bool_>(last)) {
+              sort = last.cast<bool>();
+              pos.attr("pop")();
+            }
+          }
+          py::object r = host_method(self, *py::tuple(pos), **kw);
+          A& g = self.cast<A&>();
+          g.invalidate();
+          if (sort) g.sort_on_device();
           return r;
         },
         py::is_method(cls), py::name(meth), py::doc(py::str(host_method.attr("__doc__")).cast<std::string>().c_str()));
   }
+  cls.def("sort", [](A& g) { g.sort_on_device(); },
+          "Determine the equivalent-mode permutation of every connected pair of vertices (brille's sort(), wrap/_common_grid.hpp:486): "
+          "cost matrices and assignments on the GPU, brille's permutation table updated with the result");
   const std::string doc = py::str(base.attr("ir_interpolate_at").attr("__doc__")).cast<std::string>();
   cls.def(
       "ir_interpolate_at",
@@ -339,6 +524,16 @@ void declare(py::module& m, py::module& host, const char* name) {
   cls.def_property_readonly("gpu_launches", [](A& g) { return g.dev && g.dev->h ? b200_grid_launch_count(g.dev->h) : (uint64_t)0; },
                             "kernels launched on the GPU for this grid so far");
   cls.def_property_readonly("gpu_last_path", [](A& g) { return g.dev && g.dev->h ? b200_grid_last_path(g.dev->h) : 0u; });
+  // device-resident consumers: the eigenvectors never leave the GPU (include/brille_b200.h: b200_grid_set_structure_factor ...)
+  cls.def("set_structure_factor", &A::set_structure_factor, "coef"_a, "positions"_a = py::none(), "q_transform"_a = py::none(),
+          "debye_waller"_a = py::none(), "conjugate"_a = true,
+          "configure |sum_k coef_k e^{-qv.W_k.qv} e^{2 pi i Q.r_k} (qv . eps_k^[*])|^2 with qv = q_transform Q (one complex 3-vector per atom)");
+  cls.def("ir_structure_factor", &A::structure_factor, "Q"_a, "do_not_move_points"_a = false,
+          "(values, |F(Q, mode)|^2) of the interpolated, rotated eigenvectors, reduced on the device");
+  cls.def("ir_powder_bin", &A::powder_bin, "Q"_a, "q_range"_a, "n_qbins"_a, "w_range"_a, "n_wbins"_a, "weight"_a = 0, "do_not_move_points"_a = false,
+          "(hist, counts): |F|^2 of the given points binned on (|Q|, eigenvalue) on the device");
+  cls.def("ir_powder_sweep", &A::powder_sweep, "q_range"_a, "n_qbins"_a, "w_range"_a, "n_wbins"_a, "n_dir"_a, "seed"_a = 0, "weight"_a = 0,
+          "dir_range"_a = py::none(), "(hist, counts) of a powder sweep whose points are generated on the device: nothing per Q crosses PCIe");
   cls.def("host", [](const A& g) { return Base(static_cast<const Base&>(g)); }, "a plain brille object of the base class (the reference's CPU path)");
 }
 

@@ -64,10 +64,12 @@ struct InterpSpy : Interpolator<T> {
 template <class T, class R>
 struct DualSpy : DualInterpolator<T, R> {
   static const PermutationTable& table(const DualInterpolator<T, R>& d) { return d.*(&DualSpy::permutation_table_); }
+  static PermutationTable& table(DualInterpolator<T, R>& d) { return d.*(&DualSpy::permutation_table_); }
 };
 struct PermSpy : PermutationTable {
   static const std::map<size_t, size_t>& map(const PermutationTable& p) { return p.*(&PermSpy::ijmap); }
   static const std::vector<std::vector<ind_t>>& perms(const PermutationTable& p) { return p.*(&PermSpy::permutations); }
+  static std::vector<std::vector<ind_t>>& perms(PermutationTable& p) { return p.*(&PermSpy::permutations); }
   static size_t nidx(const PermutationTable& p) { return p.*(&PermSpy::IndexSize); }
 };
 

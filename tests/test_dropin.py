@@ -42,7 +42,14 @@ def test_classes_are_subclasses_of_brilles_own(host, accel):
     assert isinstance(g, host.BZTrellisQdc) and np.array_equal(g.rlu, h.rlu)
     args = W._gamma_fill(g, 12, 4, 1)
     assert g.values.shape == (g.rlu.shape[0], 12, 1) and g.vectors.shape == (g.rlu.shape[0], 12, 4, 3)
-    g.sort()  # brille's host sort through the subclass
+    import torch
+
+    if not torch.cuda.is_available():  # sort() of complex eigenvectors is a device call like the interpolation
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            g.sort()
+    d = accel.BZTrellisQdd(bz, bz.ir_polyhedron.volume / 100)
+    d.fill(np.ones((d.rlu.shape[0], 2, 1)), (1,), np.ones((d.rlu.shape[0], 2, 3)), (0, 3, 0, 0, 3), True)
+    d.sort()  # real eigenvectors: brille's host sort through the subclass
     plain = g.host()
     assert type(plain) is host.BZTrellisQdc and np.shares_memory(plain.values, g.values)
     assert type(accel.BZTrellisQdc(plain)) is accel.BZTrellisQdc
@@ -123,6 +130,103 @@ def test_dropin_launches_kernels_and_equals_the_host_classes(host, accel):
         _bz_methods(bz, Q)
     finally:
         accel.unpatch_brillouinzone()  # (the other test modules use brille's own methods as the reference)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,args", [("BZTrellisQdc", ()), ("BZNestQdc", (5,)), ("BZMeshQdc", (3,)), ("BZTrellisQcc", ())])
+def test_dropin_sort_runs_on_the_device(host, accel, bridge, name, args):
+    """grid.sort(), fill(..., sort=True) and set_flags_weights(..., sort=True) of the drop-in classes: the cost matrices and
+    assignments come from the device (b200_grid_sort_pairs), brille's own PermutationTable holds the result.  Against brille's
+    host sort() on a copy of the same object: the same permutation for every vertex pair but the few whose assignment hangs
+    on the last bit of a cost (tests/test_gpu_parity.py::test_device_sort_matches_reference_and_oracle), and the table the
+    device sort leaves behind drives brille's HOST interpolation to the device's results."""
+    from helpers import assert_values_close
+
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    cls = getattr(accel, name)
+    g = cls(bz, bz.ir_polyhedron.volume / 300, *args)
+    nv = g.rlu.shape[0]
+    rng = np.random.default_rng(8)
+    vals = rng.uniform(1.0, 50.0, (nv, 12, 1))
+    if name.endswith("cc"):
+        vals = vals + 1j * rng.uniform(0.0, 1.0, vals.shape)
+    vecs = rng.normal(size=(nv, 12, 4, 3)) + 1j * rng.normal(size=(nv, 12, 4, 3))
+    fill = (vals, (1, 0, 0, 0, 3), vecs, (0, 12, 0, 2, 3))
+    g.fill(*fill)
+    ref = g.host()          # a plain brille object with its own copy of the (still unsorted) permutation table
+    before = g.gpu_launches
+    g.sort()
+    assert g.gpu_launches > before
+    ref.sort()              # brille's OpenMP sort
+    plan = bridge.sort_plan(ref)
+    mine, theirs = bridge.pair_permutations(g, plan["pairs"]), bridge.pair_permutations(ref, plan["pairs"])
+    assert (mine != np.arange(12)).any(), "the data must need sorting"
+    differ = np.flatnonzero((mine != theirs).any(axis=(1, 2)))
+    assert len(differ) <= max(1, len(mine) // 200), f"{len(differ)} of {len(mine)} pairs differ"
+    Q = rng.uniform(-3, 3, (50_000, 3))
+    v, w = g.ir_interpolate_at(Q)
+    hv, hw = g.host().ir_interpolate_at(Q[:5000], False, 1)   # brille's CPU path reading the table the device sort wrote
+    assert_values_close(v[:5000], hv)
+    assert_values_close(w[:5000], hw)
+    if len(differ) == 0:
+        rv, rw = ref.ir_interpolate_at(Q[:5000], False, 1)
+        assert_values_close(v[:5000], rv)
+        assert_values_close(w[:5000], rw)
+    # the `sort` argument of fill (positional and keyword) and of set_flags_weights
+    for how in ("positional", "keyword", "flags"):
+        g2 = cls(bz, bz.ir_polyhedron.volume / 300, *args)
+        if how == "positional":
+            g2.fill(*fill, True)
+        elif how == "keyword":
+            g2.fill(*fill, sort=True)
+        else:
+            g2.fill(*fill)
+            g2.set_flags_weights([0, 3, 0, 0], [1.0, 1.0, 1.0], [2, 3, 0, 0], [1.0, 1.0, 1.0], sort=True)
+        assert g2.gpu_launches > 0
+        assert np.array_equal(bridge.pair_permutations(g2, plan["pairs"]), mine), how
+    # a second sort() of sorted data changes nothing (the costs are those of the data as filled)
+    g.sort()
+    assert np.array_equal(bridge.pair_permutations(g, plan["pairs"]), mine)
+
+
+@pytest.mark.gpu
+def test_dropin_consumers_equal_the_ctypes_mirror(host, accel, bridge):
+    """set_structure_factor / ir_structure_factor / ir_powder_bin / ir_powder_sweep on the drop-in classes are the same C-ABI
+    calls as on the ctypes mirror (whose results tests/test_consumer.py checks against numpy on the reference's eigenvectors):
+    same bits."""
+    lat = W.p63mmc_lattice(host)
+    bz = host.BrillouinZone(lat)
+    g = accel.BZTrellisQdc(bz, bz.ir_polyhedron.volume / 300)
+    W._gamma_fill(g, 12, 4, 2)
+    m = brille_b200.accelerate(g.host())
+    rng = np.random.default_rng(4)
+    cfg = dict(coef=rng.normal(size=4) + 1j * rng.normal(size=4), positions=rng.uniform(0, 1, (4, 3)),
+               q_transform=np.asarray(bridge.flatten_bz(bz)["to_xyz"]).reshape(3, 3), debye_waller=None, conjugate=True)
+    with pytest.raises(RuntimeError, match="set_structure_factor"):
+        g.ir_structure_factor(np.zeros((2, 3)))
+    g.set_structure_factor(**cfg)
+    m.set_structure_factor(**cfg)
+    Q = rng.uniform(-3, 3, (100_000, 3))
+    v, sf = g.ir_structure_factor(Q)
+    mv, msf = m.ir_structure_factor(Q)
+    assert sf.shape == (len(Q), 12) and np.array_equal(v, mv) and np.array_equal(sf, msf)
+    qr, nqb, wr, nwb = (0.2, 6.2), 24, (0.0, 52.0), 40
+    h, c = g.ir_powder_sweep(qr, nqb, wr, nwb, 2000, seed=3, weight=1)
+    mh, mc = m.ir_powder_sweep(qr, nqb, wr, nwb, 2000, seed=3, weight=1)
+    assert h.shape == (nqb, nwb) and c.sum() == nqb * 2000 and np.array_equal(c, mc)
+    assert np.abs(h - mh).max() <= 1e-12 * mh.max()       # FP64 atomics: the order of the additions is not fixed
+    ha, ca = g.ir_powder_sweep(qr, nqb, wr, nwb, 2000, seed=3, weight=1, dir_range=(0, 700))
+    hb, cb = g.ir_powder_sweep(qr, nqb, wr, nwb, 2000, seed=3, weight=1, dir_range=(700, 2000))
+    assert np.array_equal(ca + cb, c) and np.abs(ha + hb - h).max() <= 1e-12 * h.max()
+    Qp = m.powder_points(qr, nqb, 2000, seed=3)
+    hp, cp = g.ir_powder_bin(Qp, qr, nqb, wr, nwb, weight=1)
+    assert np.array_equal(cp, c) and np.abs(hp - h).max() <= 1e-12 * h.max()
+    # a refill keeps the configuration (it belongs to the grid, not to the data)
+    W._gamma_fill(g, 12, 4, 9)
+    v2, sf2 = g.ir_structure_factor(Q[:1000])
+    assert not np.array_equal(sf2, sf[:1000])
+    m.close()
 
 
 def _bz_methods(bz, Q):
