@@ -14,7 +14,7 @@
 //   2. PERSISTENT CTAs, ONE BARRIER PER ITEM.  Each CTA walks its share of the work items (cell, <= chunk points)
 //      produced by the counting sort, which orders the points by (cell, point group operation).  While item n is
 //      computed, the record of the next cell is already in flight into the other half of a double buffer (TMA); every
-//      thread then turns the raw 96-byte record of "its" point of item n+1 (fetched with a per-point bulk copy issued
+//      thread then turns the raw record (96 bytes in a 128-byte line) of "its" point of item n+1 (fetched with a per-point bulk copy issued
 //      one item earlier, through the sort order loaded another item earlier) into the transposed weights, Gamma phases
 //      and indices of item n+1 in the other half of a second double buffer.  Nothing in that step needs another
 //      thread, so warps drift freely between the two steps and the trigonometry of one warp overlaps the stores of
@@ -151,7 +151,7 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t NO_ITEM = 0xffffffffu;
-constexpr uint32_t ITEM_BLOCK = 8;
+constexpr uint32_t ITEM_BLOCK = 8;  // (4 and 16 measured: 5.19 / 5.27 ms against 5.17)
 
 // SF: fused structure-factor finish (cell_sf_pass): |F|^2 per (Q, mode) instead of the eigenvectors (a.sf_out, a.Q, a.sf)
 template <int TQ, bool SF>
@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
     mbar_expect_tx(bar + b, bytes);
     bulk_g2s(b ? D1p : D0p, src, bytes, bar + b);
   };
-  // raw records of an item: every thread fetches the 96-byte record of its own point with one bulk copy; all of them
+  // raw records of an item: every thread fetches the record (REC_USED_BYTES of a 128-byte line) of its own point with one bulk copy; all of them
   // complete on bar[2 + (item & 1)], on which thread 0 announces the total.  Two barriers, because threads issue the copies
   // of item n+2 right after they have seen item n+1 complete, without a CTA barrier in between: with a single mbarrier a
   // copy of item n+2 could be counted in the phase of item n+1, and a late thread could miss a whole phase.
   auto issue_raw = [&](uint32_t q, uint32_t len, uint32_t item) {
     uint64_t* const rb = bar + 2 + (item & 1u);
-    if (tid == 0 && len) mbar_expect_tx(rb, len * REC_BYTES);
-    if ((uint32_t)tid < len) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_BYTES, rb);
+    if (tid == 0 && len) mbar_expect_tx(rb, len * REC_USED_BYTES);
+    if ((uint32_t)tid < len) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_USED_BYTES, rb);
   };
   auto wait_raw = [&](uint32_t item) {  // every thread, exactly once per item
     const uint32_t b = 2u + (item & 1u);
