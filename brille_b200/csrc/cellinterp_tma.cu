@@ -129,7 +129,8 @@ __host__ __device__ inline TmaPlan plan_smem_tma(uint32_t nvmax, uint32_t mpp, u
   const size_t tile = cell_tile_bytes(nvmax, mpp, S, no0v);
   p.D0 = take(tile);
   p.D1 = take(tile);
-  p.RW = take((size_t)chunk * REC_BYTES);  // raw per-point records of the next item (per-point bulk copies)
+  p.RW = take((size_t)chunk * REC_USED_BYTES);  // raw per-point records of the next item (per-point bulk copies), packed: a 128-byte
+                                                 // stride in shared memory would put the same field of every record in one bank
   // two sets of per-item tables (W, PH, QI, RI): the set of item n is read while the set of item n+1 is written
   const uint32_t set0 = o;
   p.W = take((size_t)nvmax * chunk * 8);
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
   auto issue_raw = [&](uint32_t q, uint32_t len, uint32_t item) {
     uint64_t* const rb = bar + 2 + (item & 1u);
     if (tid == 0 && len) mbar_expect_tx(rb, len * REC_USED_BYTES);
-    if ((uint32_t)tid < len) bulk_g2s(RW + REC_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_USED_BYTES, rb);
+    if ((uint32_t)tid < len) bulk_g2s(RW + REC_SMEM_DOUBLES * (size_t)tid, a.weight + REC_DOUBLES * (size_t)q, REC_USED_BYTES, rb);
   };
   auto wait_raw = [&](uint32_t item) {  // every thread, exactly once per item
     const uint32_t b = 2u + (item & 1u);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
       // share one sincos -- and, once per point, the row vector g = qv^T R, so that the finish is a plain dot product g . a.
       const uint32_t t = (uint32_t)tid % CH, part = (uint32_t)tid / CH, nrep = (uint32_t)nthr / CH;
       if (t < len) {
-        const double* rec = RW + REC_DOUBLES * (size_t)t;
+        const double* rec = RW + REC_SMEM_DOUBLES * (size_t)t;
         const uint32_t rot = *reinterpret_cast<const uint32_t*>(rec + 11);
         const uint32_t mi = (kind == 0 || kind == 1) ? (rot & 0xffffu) : (rot >> 16);
         const double* T = a.sf.T;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
       }
     }
     if ((uint32_t)tid < len) {
-      const double* rec = RW + REC_DOUBLES * (size_t)tid;  // weight[8] | q_ir[3] | rot, index
+      const double* rec = RW + REC_SMEM_DOUBLES * (size_t)tid;  // weight[8] | q_ir[3] | rot, index
       const uint2 ri2 = *reinterpret_cast<const uint2*>(rec + 11);
       const uint32_t my_r = ri2.x & 0xffffu, my_inv = ri2.x >> 16;
       // which matrix multiplies the interpolated vectors: gamma/axial use R^-1, real/recip use R (interpolator_*.tpp)
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(256, TQ == 2 ? 3 : 2) k_interp_cell_tma(const 
       const uint32_t nat_magic = 0xffffffffu / NAT + 1u;  // floor(u / NAT) == umulhi(u, magic) for u * NAT < 2^32
       for (uint32_t u = tid; u < len * NAT; u += nthr) {
         const uint32_t t = NAT == 1u ? u : __umulhi(u, nat_magic), k = u - t * NAT;
-        const double* rec = RW + REC_DOUBLES * (size_t)t;
+        const double* rec = RW + REC_SMEM_DOUBLES * (size_t)t;
         const uint32_t rot = *reinterpret_cast<const uint32_t*>(rec + 11);
         const uint32_t mi = (kind == 0 || kind == 1) ? (rot & 0xffffu) : (rot >> 16);
         const double* gv = GV + 3 * ((size_t)k * G + mi);

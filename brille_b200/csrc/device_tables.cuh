@@ -129,6 +129,7 @@ struct GridDev {
 // engine fetches every line a copy touches, and a 96-byte record at a 96-byte stride touches 1.5 lines on average (ncu:
 // 2.14 GB of DRAM reads per 1e7 points for 0.96 GB of records; with the padding the kernel is 1.3 % faster).
 constexpr uint32_t REC_DOUBLES = 16, REC_BYTES = 8 * REC_DOUBLES, REC_USED_BYTES = 96;  // stride in doubles / bytes, content
+constexpr uint32_t REC_SMEM_DOUBLES = REC_USED_BYTES / 8;  // the records of an item are packed in shared memory
 
 // A point parked between the two kernels of the split trellis location: what the second kernel needs, one 32-byte sector
 // (the first kernel already wrote the q_ir / rotation / index part of the point's record).
