@@ -776,7 +776,8 @@ k_locate(const BZDev* __restrict__ bzg, GridDev gd, const double* __restrict__ Q
   uint32_t* pending_at = nullptr;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double Qi[3] = {Q[3 * i], Q[3 * i + 1], Q[3 * i + 2]};
-    {  // the point of the next trip on its way into L2 (the warps of a CTA are too few to hide a DRAM round trip)
+    {  // the point of the next trip on its way into L2 (the warps of a CTA are too few to hide a DRAM round trip; staging it in
+       // shared memory by an asynchronous copy, as k_trellis_in_node_coop does, was measured slower here: 0.69 -> 0.73 ms)
       const size_t i_next = i + (size_t)gridDim.x * blockDim.x;
       if (i_next < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Q + 3 * i_next));
     }
@@ -932,26 +933,45 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
   const TrellisDev& tr = gd.tr;
   const BZDev& bz = *bzg;  // only the default tolerance pair is read
   unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
-  // software pipeline over the grid-stride loop: the sort order is loaded two trips ahead and the parked point of the next trip
-  // is pulled into L2 with a prefetch (no registers held across the trip: holding the prefetched point in registers made the
-  // compiler spill it, and the spill store waits for the load it was meant to hide)
+  // software pipeline over the grid-stride loop: the parked point of the next trip and the sort order of the trip after it are
+  // copied asynchronously into the thread's staging slots in shared memory while this trip runs (nothing is held in registers
+  // across the trip: the compiler spilled a prefetched register right behind its load, and the spill store waits for the load it
+  // was meant to hide)
+  __shared__ __align__(16) double s_park[128][4];
+  __shared__ uint32_t s_idx[128];
+  const uint32_t sp_addr = (uint32_t)__cvta_generic_to_shared(&s_park[threadIdx.x][0]);
+  const uint32_t si_addr = (uint32_t)__cvta_generic_to_shared(&s_idx[threadIdx.x]);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p_first = p;
   uint32_t i_cur = p < n ? order[p] : 0u, i_nxt = p + stride < n ? order[p + stride] : 0u;
+  double2 pa = make_double2(0.0, 0.0), pb = pa;
+  if (p < n) {
+    const double2* src = reinterpret_cast<const double2*>(out.parked + i_cur);
+    pa = src[0];
+    pb = src[1];
+  }
   for (; p < n; p += stride) {
-    const uint32_t i_nn = p + 2 * stride < n ? order[p + 2 * stride] : 0u;
-    if (p + stride < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(out.parked + i_nxt));
+    if (p != p_first) {  // what the previous trip requested
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      i_cur = i_nxt;
+      pa = *reinterpret_cast<const double2*>(&s_park[threadIdx.x][0]);
+      pb = *reinterpret_cast<const double2*>(&s_park[threadIdx.x][2]);
+      i_nxt = s_idx[threadIdx.x];
+    }
+    if (p + stride < n) {
+      const char* src = reinterpret_cast<const char*>(out.parked + i_nxt);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr + 16u), "l"(src + 16) : "memory");
+    }
+    if (p + 2 * stride < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(si_addr), "l"(order + p + 2 * stride) : "memory");
+    else s_idx[threadIdx.x] = 0u;
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const size_t i = i_cur;
     ParkedPoint pp;
-    {
-      const double2* src = reinterpret_cast<const double2*>(out.parked + i);
-      const double2 pa = src[0], pb = src[1];
-      pp.x[0] = pa.x; pp.x[1] = pa.y; pp.x[2] = pb.x;
-      pp.rot_st = (uint32_t)__double2loint(pb.y);
-      pp.cell = (uint32_t)__double2hiint(pb.y);
-    }
-    i_cur = i_nxt;
-    i_nxt = i_nn;
+    pp.x[0] = pa.x; pp.x[1] = pa.y; pp.x[2] = pb.x;
+    pp.rot_st = (uint32_t)__double2loint(pb.y);
+    pp.cell = (uint32_t)__double2hiint(pb.y);
     uint32_t st = pp.rot_st >> 16;
     uint32_t cell = pp.cell;  // trellis: the node; nest / mesh: the spatial bin (replaced by the containing tetrahedron below)
     const int invridx = (int)((pp.rot_st >> 8) & 0xffu);
@@ -1045,7 +1065,12 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
   const size_t n_tiles = (n + 31) / 32, tile_stride = (size_t)gridDim.x * COOP_WARPS;
   size_t tile = (size_t)blockIdx.x * COOP_WARPS + wib;
   if (tile >= n_tiles) return;
-  // pipeline registers: the point of this tile, and the sort order of the next
+  // Pipeline: the parked point of the warp's NEXT tile and the sort order of the tile after that are fetched while this tile is
+  // worked on -- by asynchronous copies into the warp's staging slots in shared memory, not into registers: a loaded register
+  // that stays live across the body was spilled by the compiler right behind its load, which waited for the load there
+  // (14 % of the samples of the kernel on that one local store; profiles/README.md).
+  __shared__ __align__(16) double s_park[COOP_WARPS][32][4];
+  __shared__ uint32_t s_idx[COOP_WARPS][32];
   auto order_at = [&](size_t t) { const size_t p = t * 32 + lane; return t < n_tiles && p < n ? order[p] : 0xffffffffu; };
   auto parked_at = [&](uint32_t i, double2& a, double2& b) {
     if (i != 0xffffffffu) {
@@ -1054,12 +1079,23 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
       b = src[1];
     }
   };
+  const uint32_t sp_addr = (uint32_t)__cvta_generic_to_shared(&s_park[wib][lane][0]);
+  const uint32_t si_addr = (uint32_t)__cvta_generic_to_shared(&s_idx[wib][lane]);
   uint32_t i_cur = order_at(tile), i_nxt = order_at(tile + tile_stride);
-  double2 pa = make_double2(0.0, 0.0), pb = pa, na = pa, nb = pa;
+  double2 pa = make_double2(0.0, 0.0), pb = pa;
   parked_at(i_cur, pa, pb);
   for (; tile < n_tiles; tile += tile_stride) {
-    const uint32_t i_nn = order_at(tile + 2 * tile_stride);
-    parked_at(i_nxt, na, nb);  // (in flight while this tile is worked on)
+    {
+      if (i_nxt != 0xffffffffu) {
+        const char* src = reinterpret_cast<const char*>(out.parked + i_nxt);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr + 16u), "l"(src + 16) : "memory");
+      }
+      const size_t t2 = tile + 2 * tile_stride, p2 = t2 * 32 + lane;
+      if (t2 < n_tiles && p2 < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(si_addr), "l"(order + p2) : "memory");
+      else s_idx[wib][lane] = 0xffffffffu;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const size_t p = tile * 32 + lane;
     const bool valid = i_cur != 0xffffffffu;
     const size_t i = valid ? i_cur : 0;
@@ -1259,10 +1295,13 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
       f_wedge += (st & B200_ST_OUTSIDE_WEDGE) != 0;
       f_find += (st & B200_ST_NOT_FOUND) != 0;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     i_cur = i_nxt;
-    i_nxt = i_nn;
-    pa = na;
-    pb = nb;
+    if (i_cur != 0xffffffffu) {
+      pa = *reinterpret_cast<const double2*>(&s_park[wib][lane][0]);
+      pb = *reinterpret_cast<const double2*>(&s_park[wib][lane][2]);
+    }
+    i_nxt = s_idx[wib][lane];
   }
   if (f_bz) atomicAdd(fail_count + 0, f_bz);
   if (f_wedge) atomicAdd(fail_count + 1, f_wedge);
