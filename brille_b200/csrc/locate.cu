@@ -1051,6 +1051,7 @@ k_locate_in_node(const BZDev* __restrict__ bzg, GridDev gd, size_t n, uint32_t m
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TET_BLOCK = 32;                            // tetrahedra staged per round
 constexpr int COOP_WARPS = 4;                            // warps per CTA
+constexpr int COOP_RUN = 2;                              // consecutive tiles per warp (2 / 4 / 8 / 16 measured: 0.770 / 0.786 / 0.781 / 0.828 ms)
 constexpr int COOP_SLICE = TET_BLOCK * TET_PACK;         // doubles per warp (4608 bytes; a cube record needs 28)
 
 __global__ void __launch_bounds__(COOP_WARPS * 32, 4)
@@ -1062,9 +1063,14 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
   const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   double* const rec = s_rec[wib];
   unsigned long long f_bz = 0, f_wedge = 0, f_find = 0;
-  const size_t n_tiles = (n + 31) / 32, tile_stride = (size_t)gridDim.x * COOP_WARPS;
-  size_t tile = (size_t)blockIdx.x * COOP_WARPS + wib;
-  if (tile >= n_tiles) return;
+  // A warp works on runs of COOP_RUN consecutive tiles (the tiles are in node order: within a run the node rarely changes, and
+  // the node's header and the records staged in shared memory are reused), the runs are dealt round-robin to the warps.
+  const size_t n_tiles = (n + 31) / 32, n_warps = (size_t)gridDim.x * COOP_WARPS, warp_id = (size_t)blockIdx.x * COOP_WARPS + wib;
+  auto tile_of = [&](size_t s) { return ((s / COOP_RUN) * n_warps + warp_id) * COOP_RUN + (s % COOP_RUN); };
+  if (tile_of(0) >= n_tiles) return;
+  uint32_t c_node = 0xffffffffu, c_payload = 0, c_t0 = 0, c_t1 = 0;  // header of the node seen last (warp-uniform)
+  bool c_cube = false;
+  uint32_t rec_node = 0xffffffffu, rec_base = 0;                       // what the warp's slice of shared memory holds
   // Pipeline: the parked point of the warp's NEXT tile and the sort order of the tile after that are fetched while this tile is
   // worked on -- by asynchronous copies into the warp's staging slots in shared memory, not into registers: a loaded register
   // that stays live across the body was spilled by the compiler right behind its load, which waited for the load there
@@ -1081,17 +1087,19 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
   };
   const uint32_t sp_addr = (uint32_t)__cvta_generic_to_shared(&s_park[wib][lane][0]);
   const uint32_t si_addr = (uint32_t)__cvta_generic_to_shared(&s_idx[wib][lane]);
-  uint32_t i_cur = order_at(tile), i_nxt = order_at(tile + tile_stride);
+  uint32_t i_cur = order_at(tile_of(0)), i_nxt = order_at(tile_of(1));
   double2 pa = make_double2(0.0, 0.0), pb = pa;
   parked_at(i_cur, pa, pb);
-  for (; tile < n_tiles; tile += tile_stride) {
+  for (size_t seq = 0;; ++seq) {
+    const size_t tile = tile_of(seq);
+    if (seq % COOP_RUN == 0 && tile >= n_tiles) break;  // (a run that starts past the end; tiles past the end inside a run are empty)
     {
       if (i_nxt != 0xffffffffu) {
         const char* src = reinterpret_cast<const char*>(out.parked + i_nxt);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr), "l"(src) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp_addr + 16u), "l"(src + 16) : "memory");
       }
-      const size_t t2 = tile + 2 * tile_stride, p2 = t2 * 32 + lane;
+      const size_t t2 = tile_of(seq + 2), p2 = t2 * 32 + lane;
       if (t2 < n_tiles && p2 < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(si_addr), "l"(order + p2) : "memory");
       else s_idx[wib][lane] = 0xffffffffu;
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1119,11 +1127,20 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
       const uint32_t node = __shfl_sync(FULL_MASK, cell, leader);
       const bool mine = valid && !(st & B200_ST_NOT_FOUND) && cell == node;
       todo &= ~__ballot_sync(FULL_MASK, mine);
-      const uint32_t payload = tr.node_index[node];
-      if (tr.node_type[node] == B200_NODE_CUBE) {
+      if (node != c_node) {  // (dependent loads from L2: worth skipping for the tiles of a run)
+        c_node = node;
+        c_payload = tr.node_index[node];
+        c_cube = tr.node_type[node] == B200_NODE_CUBE;
+        if (!c_cube) { c_t0 = tr.poly_offsets[c_payload]; c_t1 = tr.poly_offsets[c_payload + 1]; }
+      }
+      const uint32_t payload = c_payload;
+      if (c_cube) {
         // corners (24 doubles) through shared memory; CubeNode::indices_weights (trellis_node.hpp:130-149)
-        if (lane < 12) reinterpret_cast<double2*>(rec)[lane] = reinterpret_cast<const double2*>(tr.cube_pack + 24 * (size_t)payload)[lane];
-        __syncwarp();
+        if (rec_node != node) {
+          if (lane < 12) reinterpret_cast<double2*>(rec)[lane] = reinterpret_cast<const double2*>(tr.cube_pack + 24 * (size_t)payload)[lane];
+          rec_node = node;
+          __syncwarp();
+        }
         if (mine) {
           is_cube = true;
           const double vol = (fabs(rec[0] - rec[21]) * fabs(rec[1] - rec[22])) * fabs(rec[2] - rec[23]);
@@ -1141,7 +1158,7 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
         __syncwarp();
       } else {
         // PolyNode::indices_weights (trellis_node.hpp:273-308): first tetrahedron, in storage order, that contains the point
-        const uint32_t t0 = tr.poly_offsets[payload], t1 = tr.poly_offsets[payload + 1];
+        const uint32_t t0 = c_t0, t1 = c_t1;
         double best = 0.0;
         uint32_t best_at = t0;
         bool have_best = false;
@@ -1149,11 +1166,13 @@ k_trellis_in_node_coop(const BZDev* __restrict__ bzg, GridDev gd, size_t n, Loca
         for (uint32_t base = t0; base < t1; base += TET_BLOCK) {
           if (!__ballot_sync(FULL_MASK, mine && found < 0)) break;
           const uint32_t nblk = min((uint32_t)TET_BLOCK, t1 - base);
-          {
+          if (rec_node != node || rec_base != base) {
             const double2* src = reinterpret_cast<const double2*>(tr.tet_pack + (size_t)TET_PACK * base);
             for (uint32_t c = lane; c < nblk * (TET_PACK / 2); c += 32) reinterpret_cast<double2*>(rec)[c] = src[c];
+            rec_node = node;
+            rec_base = base;
+            __syncwarp();
           }
-          __syncwarp();
           if (mine && found < 0) {
             // circumsphere test of every tetrahedron of the block (tetrahedra_might_contain :349-364), then the weights of the
             // candidates in storage order (first accepted wins, :284-290); `best` keeps max_element's first-maximum rule
@@ -1312,7 +1331,7 @@ cudaError_t launch_locate_in_node(const BZDev* bzg, const GridDev& gd, size_t n,
                                   unsigned long long* fail_count, int sm_count, cudaStream_t stream, bool coop) {
   if (n == 0) return cudaSuccess;
   if (coop && gd.kind == B200_GRID_TRELLIS) {
-    const size_t tiles = (n + 31) / 32, want_c = (tiles + COOP_WARPS - 1) / COOP_WARPS, cap_c = (size_t)sm_count * 16;
+    const size_t tiles = (n + 31) / 32, per_cta = (size_t)COOP_WARPS * COOP_RUN, want_c = (tiles + per_cta - 1) / per_cta, cap_c = (size_t)sm_count * 16;
     k_trellis_in_node_coop<<<(unsigned)(want_c < cap_c ? want_c : cap_c), COOP_WARPS * 32, 0, stream>>>(bzg, gd, n, out, order, fail_count);
     return cudaGetLastError();
   }
