@@ -13,7 +13,9 @@ The printed JSON line follows the driver's contract.  `value` is timed with CUDA
 resident in HBM; `e2e` goes through the host-buffer C-ABI call (pinned host buffers, H2D of Q and D2H of both
 results inside the timed region); `roofline` is the dominant (interpolation) kernel against the measured HBM copy
 bandwidth; `cpu_baseline` is the reference's own OpenMP implementation (the unmodified build, third_party/brille_host) on
-the host cores.
+the host cores.  Beside the contract's keys: `configs` (every other BASELINE configuration, device resident), `consumer` (the
+fused structure-factor and powder-average calls) and, on a single-GPU run, `sort` (the device sort() of the C3 grid beside the
+reference's OpenMP sort()).
 """
 from __future__ import annotations
 
@@ -572,6 +574,15 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001 - a failing side configuration must not take the headline line with it
                 configs[spec[0]] = {"workload": spec[1], "error": f"{type(e).__name__}: {e}"}
 
+    # sort() on a fresh grid (the reference's sort() changes the host object), rank 0 of a single-GPU run only:
+    # it times the reference's OpenMP sort() beside the device call (a few seconds of host time)
+    sort_block = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_consumer:
+        try:
+            sort_block = measure_sort(brille_b200, local)
+        except Exception as e:  # noqa: BLE001 - a side measurement must not take the headline line with it
+            sort_block = {"error": f"{type(e).__name__}: {e}"}
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -606,6 +617,7 @@ def run_ours(args):
                          "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None},
             "cpu_baseline": cpu,
             "consumer": consumer,
+            "sort": sort_block,
             "configs": configs,
         }
         print(json.dumps(line))
@@ -614,6 +626,37 @@ def run_ours(args):
         dist.destroy_process_group()
     grid.close()
     return 0
+
+
+def measure_sort(brille_b200, device):
+    """sort() of the C3 grid -- the mode assignment of every connected vertex pair (interpolatordual.hpp:398-434): cost matrices and
+    Jonker-Volgenant assignments on the device through b200_grid_sort_pairs (host buffers in and out) beside the reference's own
+    OpenMP sort() on the box's cores."""
+    from brille_b200 import _bridge
+
+    wl = build_workload()
+    g = brille_b200.accelerate(wl.grid, device=device)
+    plan = _bridge.sort_plan(wl.grid)
+    pairs = plan["pairs"]
+    g.sort_pairs(pairs, plan)  # warm-up: work space
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        row, col = g.sort_pairs(pairs, plan)
+        best = min(best, time.perf_counter() - t0)
+    launches = g.launch_count
+    t0 = time.perf_counter()
+    wl.grid.sort()
+    t_ref = time.perf_counter() - t0
+    ref = _bridge.pair_permutations(wl.grid, pairs)
+    same = float((row.astype(np.uint32) == ref[:, 0, :]).all(axis=1).mean())
+    g.close()
+    cores = os.cpu_count() or 1
+    return {"what": "sort(): cost matrix + assignment of every connected vertex pair of the C3 grid, b200_grid_sort_pairs (host buffers) "
+                    "against the reference's OpenMP sort()",
+            "pairs": int(len(pairs)), "modes": int(row.shape[1]), "device_ms": best * 1e3, "pairs_per_s": len(pairs) / best,
+            "reference_s": t_ref, "reference_cores": cores, "speedup": t_ref / best, "identical_permutations": same,
+            "gpu_launches": int(launches)}
 
 
 def main():
